@@ -1,0 +1,170 @@
+#!/usr/bin/env python
+"""Generate golden vectors by EXECUTING THE REFERENCE (unmodified, imported from
+/root/reference on CPU).  Run in the authoring container only:
+
+    python tests/golden/make_golden.py
+
+The reference has no tests or golden vectors of its own, so these files
+are what pins the oracle (tests/test_oracle_vs_golden.py) and, through it and directly,
+the CUDA path (tests/test_gpu_*.py).  /root/reference does not exist on the GPU box;
+nothing but this script reads it.
+
+Reference entry points exercised (all fp32, CPU):
+  utils/utils_edited.py : meshgrid, pose_vec2mat, compute_rigid_flow, flow_warp,
+                          bilinear_sampler, DSSIM, compute_multi_scale_intrinsics, scale_pyramid
+  models/loss_functions.py : image_similarity, smooth_loss
+composed exactly as models/baseline.py:895-970 (build_rigid_warp_flow) and :1125-1161
+(build_losses) compose them.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+
+def import_reference():
+    def _stub(name, **kw):
+        m = types.ModuleType(name); m.__dict__.update(kw); sys.modules[name] = m; return m
+    mpl = _stub("matplotlib", use=lambda *a, **k: None); mpl.pyplot = _stub("matplotlib.pyplot")
+    sys.path.insert(0, "/root/reference")
+    import utils.utils_edited as U
+    import models.loss_functions as L
+    return U, L
+
+
+def reference_loss_path(U, L, inp, alpha=0.85, w_rigid=1.0, w_smooth=0.5, keep=False):
+    """build_rigid_warp_flow + build_losses with the reference's own functions."""
+    B, S, ns = inp.B, inp.S, inp.num_scales
+    tgt_pyr = [t.permute(0, 2, 3, 1) for t in inp.tgt_pyr]           # NHWC views, as scale_pyramid returns
+    src_pyr = [t.permute(0, 2, 3, 1) for t in inp.src_pyr]
+    tgt_tile = [t.repeat(S, 1, 1, 1) for t in tgt_pyr]
+    loss_rigid, loss_smooth = 0, 0
+    rec = dict(fwd_flow=[], bwd_flow=[], fwd_warp=[], bwd_warp=[], fwd_err=[], bwd_err=[], fwd_mean=[], bwd_mean=[], smooth=[])
+    for s in range(ns):
+        fl_f, fl_b = [], []
+        for k in range(S):
+            fl_f.append(U.compute_rigid_flow(inp.poses[:, k, :], inp.depth_pyr[s][:B], inp.K_ms[:, s], False))
+            fl_b.append(U.compute_rigid_flow(inp.poses[:, k, :], inp.depth_pyr[s][B * (k + 1):B * (k + 2)], inp.K_ms[:, s], True))
+        fwd_flow, bwd_flow = torch.cat(fl_f, 0), torch.cat(fl_b, 0)
+        fwd_warp = U.flow_warp(src_pyr[s], fwd_flow)
+        bwd_warp = U.flow_warp(tgt_tile[s], bwd_flow)
+        fwd_err = L.image_similarity(alpha, tgt_tile[s], fwd_warp)
+        bwd_err = L.image_similarity(alpha, src_pyr[s], bwd_warp)
+        fm, bm = torch.mean(fwd_err), torch.mean(bwd_err)
+        sm = L.smooth_loss(inp.depth_pyr[s].unsqueeze(3), torch.cat((tgt_pyr[s], src_pyr[s]), 0))
+        loss_rigid = loss_rigid + w_rigid * S / 2 * (fm + bm)
+        loss_smooth = loss_smooth + w_smooth / (2 ** s) * sm
+        rec["fwd_mean"].append(fm.item()); rec["bwd_mean"].append(bm.item()); rec["smooth"].append(sm.item())
+        if keep:
+            for k_, v in (("fwd_flow", fwd_flow), ("bwd_flow", bwd_flow), ("fwd_warp", fwd_warp), ("bwd_warp", bwd_warp),
+                          ("fwd_err", fwd_err), ("bwd_err", bwd_err)):
+                rec[k_].append(v.detach().numpy().copy())
+    return loss_rigid, loss_smooth, rec
+
+
+def run_case(U, L, name, keep, **gen):
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**gen)
+    for d in inp.depth_pyr:
+        d.requires_grad_(True)
+    inp.poses.requires_grad_(True)
+    lr, ls, rec = reference_loss_path(U, L, inp, keep=keep)
+    total = lr + ls
+    total.backward()
+    out = dict(loss_rigid_warp=np.float64(lr.item()), loss_disp_smooth=np.float64(ls.item()), loss_total=np.float64(total.item()),
+               fwd_mean=np.array(rec["fwd_mean"]), bwd_mean=np.array(rec["bwd_mean"]), smooth=np.array(rec["smooth"]),
+               grad_poses=inp.poses.grad.numpy().copy(),
+               gen=np.array(repr(sorted(gen.items()))))
+    for s, d in enumerate(inp.depth_pyr):
+        g = d.grad.numpy()
+        if keep:
+            out[f"grad_depth_{s}"] = g.copy()
+        out[f"grad_depth_{s}_l2"] = np.float64(np.sqrt((g.astype(np.float64) ** 2).sum()))
+        out[f"grad_depth_{s}_sum"] = np.float64(g.astype(np.float64).sum())
+        # a fixed pseudo-random projection: a cheap checksum sensitive to position
+        rng = np.random.default_rng(1234 + s)
+        out[f"grad_depth_{s}_proj"] = np.float64((g.astype(np.float64) * rng.standard_normal(g.shape)).sum())
+    if keep:
+        for k_ in ("fwd_flow", "bwd_flow", "fwd_warp", "bwd_warp", "fwd_err", "bwd_err"):
+            for s, v in enumerate(rec[k_]):
+                out[f"{k_}_{s}"] = v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "loss_total", out["loss_total"], "rigid", out["loss_rigid_warp"], "smooth", out["loss_disp_smooth"])
+
+
+def kats(U, L):
+    """Known-answer tables for the pieces (sampler edge semantics, grid tables, pose matrices)."""
+    out = {}
+    for n in (2, 3, 13, 16, 52, 104, 128, 208, 416, 480, 640, 1248, 2048):
+        out[f"grid_{n}"] = ((torch.linspace(-1, 1, n) + 1) * 0.5 * (n - 1)).numpy()
+    img = torch.arange(20.).view(1, 4, 5, 1)
+    xs = [-2.3, -1.0, -0.5, 0.0, 0.25, 3.999, 4.0, 4.5, 6.0]
+    ys = [-1.5, -0.25, 0.0, 1.0, 2.5, 2.999, 3.0, 3.7]
+    tab = np.zeros((len(ys), len(xs)), np.float32)
+    for i, y in enumerate(ys):
+        for j, x in enumerate(xs):
+            tab[i, j] = U.bilinear_sampler(img, torch.tensor([[[[x, y]]]])).item()
+    out["sampler_xs"], out["sampler_ys"], out["sampler_tab"] = np.array(xs, np.float32), np.array(ys, np.float32), tab
+    g = torch.Generator().manual_seed(7)
+    vec = torch.randn(16, 6, generator=g) * torch.tensor([0.3, 0.3, 0.3, 0.5, 0.5, 0.5])
+    out["pose_vec"] = vec.numpy()
+    out["pose_mat"] = U.pose_vec2mat(vec).numpy()
+    out["pose_mat_inv"] = torch.inverse(U.pose_vec2mat(vec)).numpy()
+    # random-coordinate sampler case incl. far out-of-range coordinates, with gradients
+    imgs = torch.rand(2, 9, 11, 3, generator=g)
+    coords = (torch.rand(2, 7, 8, 2, generator=g) * torch.tensor([14.0, 12.0]) - 2.0).requires_grad_(True)
+    imgs.requires_grad_(True)
+    o = U.bilinear_sampler(imgs, coords)
+    go = torch.randn(o.shape, generator=g)
+    o.backward(go)
+    out.update(bs_img=imgs.detach().numpy(), bs_coords=coords.detach().numpy(), bs_out=o.detach().numpy(), bs_gout=go.numpy(),
+               bs_gcoords=coords.grad.numpy(), bs_gimg=imgs.grad.numpy())
+    # image_similarity with arbitrary upstream gradient, both inputs differentiable
+    x = (torch.rand(2, 10, 12, 3, generator=g) * 2 - 1).requires_grad_(True)
+    y = (torch.rand(2, 10, 12, 3, generator=g) * 2 - 1).requires_grad_(True)
+    e = L.image_similarity(0.85, x, y)
+    ge = torch.randn(e.shape, generator=g)
+    e.backward(ge)
+    out.update(is_x=x.detach().numpy(), is_y=y.detach().numpy(), is_err=e.detach().numpy(), is_gerr=ge.numpy(),
+               is_gx=x.grad.numpy(), is_gy=y.grad.numpy(), is_dssim=U.DSSIM(x.detach(), y.detach()).numpy())
+    # smooth_loss
+    d = (torch.rand(3, 10, 12, 1, generator=g) + 0.1).requires_grad_(True)
+    im = torch.rand(3, 10, 12, 3, generator=g) * 2 - 1
+    sl = L.smooth_loss(d, im)
+    sl.backward()
+    out.update(sm_depth=d.detach().numpy(), sm_img=im.numpy(), sm_loss=np.float64(sl.item()), sm_gdepth=d.grad.numpy())
+    # compute_rigid_flow incl. the matrices it builds internally
+    Bk, hk, wk = 3, 12, 20
+    Kk = torch.tensor([[0.58 * wk, 0, 0.5 * wk], [0, 1.92 * hk, 0.5 * hk], [0, 0, 1]]).repeat(Bk, 1, 1)
+    Kk[1, 0, 1] = 0.3  # skew on one sample: exercises the general 3x3 inverse
+    pk = (torch.randn(Bk, 6, generator=g) * torch.tensor([0.1, 0.1, 0.1, 0.05, 0.05, 0.05])).requires_grad_(True)
+    dk = (1.0 / (torch.rand(Bk, hk, wk, generator=g) * 9 + 0.5)).requires_grad_(True)
+    for rev in (False, True):
+        fl = U.compute_rigid_flow(pk, dk, Kk, rev)
+        gfl = torch.randn(fl.shape, generator=g)
+        gp, gd = torch.autograd.grad(fl, (pk, dk), gfl)
+        tag = "rev" if rev else "fwd"
+        out.update({f"rf_{tag}_flow": fl.detach().numpy(), f"rf_{tag}_gflow": gfl.numpy(), f"rf_{tag}_gpose": gp.numpy(),
+                    f"rf_{tag}_gdepth": gd.numpy()})
+    out.update(rf_K=Kk.numpy(), rf_pose=pk.detach().numpy(), rf_depth=dk.detach().numpy(), rf_Kinv=torch.inverse(Kk).numpy())
+    np.savez_compressed(os.path.join(HERE, "kats.npz"), **out)
+    print("kats written:", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    U, L = import_reference()
+    kats(U, L)
+    # small cases with every intermediate kept (a few hundred KB each)
+    run_case(U, L, "small_smooth", True, B=2, S=2, H=32, W=64, num_scales=3, seed=1, smooth=True, motion="small")
+    run_case(U, L, "small_noise_large_motion", True, B=2, S=2, H=24, W=40, num_scales=2, seed=2, smooth=False, motion="large")
+    run_case(U, L, "small_s1_nyu", True, B=1, S=1, H=30, W=44, num_scales=2, seed=3, smooth=True, motion="large", intrinsics="nyu")
+    # BASELINE config 1 (the reference's CPU-runnable case), scalars + checksums only
+    run_case(U, L, "config1_noise", False, B=4, S=2, H=128, W=416, num_scales=4, seed=0, smooth=False, motion="small")
+    run_case(U, L, "config1_smooth", False, B=4, S=2, H=128, W=416, num_scales=4, seed=0, smooth=True, motion="small")
