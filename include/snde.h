@@ -1,0 +1,178 @@
+/*
+ * snde.h -- C ABI of libsnde.so: B200 (sm_100a) kernels for the self-supervised
+ * rigid-warp + photometric (L1 + 3x3 SSIM) + edge-aware smoothness loss path.
+ *
+ * The reference (Eisoc/Self-supervised-Normal-Depth-Estimation) is pure Python: its
+ * "plugin boundary" for this path is a set of Python functions in two modules.  Each
+ * entry point below names the reference function(s) it replaces (file:line under the
+ * reference root).  The Python side (snde_b200/loss_functions.py, utils_edited.py)
+ * re-exports the reference names on top of these calls via ctypes.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no torch types.  All tensors are fp32 DEVICE
+ *    pointers owned by the caller; the library never allocates, frees or keeps them.
+ *  - Strides are in ELEMENTS.  Images are addressed as logical (n, c, y, x) through
+ *    (sn, sc, sh, sw), so planar NCHW memory, NHWC memory and permuted views all work
+ *    (the reference hands NHWC views of NCHW memory around).
+ *  - Every call launches asynchronously on the given stream (a cudaStream_t passed as
+ *    void*) and returns 0 or a negative SndeStatus; no internal synchronisation.
+ *  - Batch order of every N = S*B sized tensor is source-major: n = src*B + b
+ *    (models/baseline.py:772-775, 915-922).
+ */
+#ifndef SNDE_H_
+#define SNDE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SNDE_API __attribute__((visibility("default")))
+#else
+#define SNDE_API
+#endif
+
+#define SNDE_VERSION 100      /* 0.1.0 */
+#define SNDE_MAX_SCALES 6
+
+typedef enum SndeStatus {
+    SNDE_OK = 0,
+    SNDE_ERR_NULL = -1,        /* a required pointer is NULL */
+    SNDE_ERR_SHAPE = -2,       /* non-positive / unsupported dimension (C must be 3 where stated; h,w >= 2 for smoothness) */
+    SNDE_ERR_TOO_LARGE = -3,   /* an index would not fit 31 bits (N*h*w >= 2^31) */
+    SNDE_ERR_WORKSPACE = -4,   /* workspace missing, too small or misaligned (needs 16-byte alignment) */
+    SNDE_ERR_ARG = -5,         /* bad enum / flag / scalar */
+    SNDE_ERR_CUDA = -6         /* cudaGetLastError() after launch != cudaSuccess */
+} SndeStatus;
+
+typedef enum SndePadding {
+    SNDE_PAD_ZEROS = 0,        /* the reference's sampler: value 0 outside [0,w-1) x [0,h-1)  (utils_edited.py:435-484) */
+    SNDE_PAD_BORDER = 1        /* extension (unpinned by the reference): clamp coordinates to the image, == grid_sample(border, align_corners=True) */
+} SndePadding;
+
+/* 3-channel image batch, logical (n, c, y, x) */
+typedef struct SndeImage { const float *ptr; int64_t sn, sc, sh, sw; } SndeImage;
+typedef struct SndeImageOut { float *ptr; int64_t sn, sc, sh, sw; } SndeImageOut;
+/* single-channel map batch, logical (n, y, x) */
+typedef struct SndeMap { const float *ptr; int64_t sn, sh, sw; } SndeMap;
+typedef struct SndeMapOut { float *ptr; int64_t sn, sh, sw; } SndeMapOut;
+
+SNDE_API int snde_version(void);
+SNDE_API const char *snde_strerror(int status);
+
+/* meshgrid 1-D table  t[i] = (linspace(-1,1,n)[i] + 1) * 0.5 * (n-1), bit-identical to the
+ * reference's (utils/utils_edited.py:307-317; NOT exact integers).  HOST function, host buffer. */
+SNDE_API int snde_fill_grid_table(int n, float *host_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused loss: everything GeoNetModel.build_rigid_warp_flow (models/baseline.py:867-970) and
+ * build_losses (:1115-1161) compute between (pyramids, depth, poses, intrinsics) and
+ * loss_total, forward AND backward in one pass:
+ *   pose_vec2mat/euler2mat/inverse/K4@T  (utils_edited.py:171-214, 268-289, 343-357)
+ *   meshgrid, pixel2cam, cam2pixel, compute_rigid_flow, flow_warp, bilinear_sampler (:216-486)
+ *   DSSIM, image_similarity (:121-141, loss_functions.py:4-6), torch.mean, smooth_loss (:8-24)
+ * and their autograd backward to depth, poses and (extension) intrinsics.
+ *
+ *   loss_rigid_warp  = sum_s photo_weight[s] * (mean(fwd_err_s) + mean(bwd_err_s))
+ *   loss_disp_smooth = sum_s smooth_weight[s] * smooth_loss(depth_s, cat(tgt_s, src_s))
+ * (the reference uses photo_weight = w_rigid*S/2 and smooth_weight = w_smooth/2^s).
+ * Gradients are d(loss_rigid_warp + loss_disp_smooth)/d(input), i.e. for upstream gradient 1.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct SndeLossScale {
+    int32_t h, w;
+    SndeImage tgt;              /* (B,3,h,w) */
+    SndeImage src;              /* (S*B,3,h,w) source-major */
+    SndeMap depth;              /* (B*(1+S),h,w): B target depths then S*B source depths (models/baseline.py:905-912) */
+    SndeMapOut grad_depth;      /* same shape; written completely when SNDE_LOSS_GRAD is set */
+    const float *K;             /* (B,3,3) contiguous: this scale's intrinsics (compute_multi_scale_intrinsics, utils_edited.py:149) */
+    const float *xtab, *ytab;   /* device copies of snde_fill_grid_table(w), (h) */
+    float photo_weight, smooth_weight;
+    SndeMap mask_fwd, mask_bwd;         /* optional (ptr may be NULL): explainability weight per pixel, (S*B,h,w); extension */
+    SndeImageOut warped_fwd, warped_bwd;/* optional outputs (S*B,3,h,w): flow_warp results (logged by the reference every 10k it) */
+    SndeImageOut err_fwd, err_bwd;      /* optional outputs (S*B,3,h,w): image_similarity maps */
+} SndeLossScale;
+
+enum {
+    SNDE_LOSS_GRAD = 1,         /* also produce grad_depth / grad_poses (/ grad_K) */
+    SNDE_LOSS_GRAD_K = 2,       /* also produce grad_K (needs SNDE_LOSS_GRAD) */
+    SNDE_LOSS_NO_PHOTO = 4,     /* skip the warp/photometric term */
+    SNDE_LOSS_NO_SMOOTH = 8     /* skip the smoothness term */
+};
+
+typedef struct SndeLossArgs {
+    int32_t B, S, num_scales;
+    int32_t flags;              /* SNDE_LOSS_* */
+    int32_t padding_mode;       /* SndePadding */
+    float alpha;                /* SSIM weight (reference: simi_alpha = 0.85) */
+    const float *poses;         /* (B,S,6) contiguous [tx,ty,tz,rx,ry,rz] */
+    SndeLossScale scale[SNDE_MAX_SCALES];
+    float *loss_out;            /* 3 + 3*num_scales floats: total, rigid_warp, disp_smooth, then per scale (mean fwd_err, mean bwd_err, smooth_loss) */
+    float *grad_poses;          /* (B,S,6) contiguous, written when SNDE_LOSS_GRAD */
+    float *grad_K;              /* (B,num_scales,3,3) contiguous, written when SNDE_LOSS_GRAD_K */
+    void *workspace;            /* device scratch, >= snde_loss_workspace_bytes(), 16-byte aligned; contents undefined on entry */
+    size_t workspace_bytes;
+} SndeLossArgs;
+
+/* sizeof(SndeLossArgs) as compiled: lets an FFI binding verify its struct layout */
+SNDE_API size_t snde_sizeof_loss_args(void);
+SNDE_API size_t snde_loss_workspace_bytes(int B, int S, int num_scales);
+/* launches: 1 memset + 3 kernels (matrix prep, fused tile kernel over every scale/direction/tile, finalize) */
+SNDE_API int snde_loss_fwdbwd(const SndeLossArgs *args, void *stream);
+/* number of CTAs the fused tile kernel would launch for these shapes (host only; used by tests/bench) */
+SNDE_API int64_t snde_loss_num_tiles(const SndeLossArgs *args);
+
+/* ------------------------------------------------------------------------------------------
+ * Reference-signature pieces (each materialises its output exactly like the reference).
+ * ---------------------------------------------------------------------------------------- */
+
+/* pose_vec2mat + optional inverse + K4 @ pose, and inverse(K): the per-sample matrices of
+ * compute_rigid_flow (utils_edited.py:343-357, :231).  poses (B,6) with element stride
+ * pose_stride between samples, K (B,3,3) contiguous -> P (B,3,4) rows 0..2 of the 4x4
+ * projection, Kinv (B,3,3). */
+SNDE_API int snde_pose_matrices(int B, const float *poses, int64_t pose_stride, const float *K, int reverse_pose,
+                       float *P, float *Kinv, void *stream);
+/* backward of the above: gP (B,3,4), gKinv (B,3,3) doubles (accumulators of snde_rigid_flow_bwd) ->
+ * grad_poses (B,6) contiguous [written], grad_K (B,3,3) [written, may be NULL] */
+SNDE_API int snde_pose_matrices_bwd(int B, const float *poses, int64_t pose_stride, const float *K, int reverse_pose,
+                           const double *gP, const double *gKinv, float *grad_poses, float *grad_K, void *stream);
+
+/* compute_rigid_flow's per-pixel part (utils_edited.py:331-362): depth (B,h,w) -> flow (B,h,w,2) contiguous */
+SNDE_API int snde_rigid_flow_fwd(int B, int h, int w, SndeMap depth, const float *Kinv, const float *P,
+                        const float *xtab, const float *ytab, float *flow, void *stream);
+/* gflow (B,h,w,2) contiguous -> gdepth (written); gP (B,3,4), gKinv (B,3,3) double accumulators (+=; zero them first; gKinv may be NULL) */
+SNDE_API int snde_rigid_flow_bwd(int B, int h, int w, SndeMap depth, const float *Kinv, const float *P,
+                        const float *xtab, const float *ytab, const float *gflow,
+                        SndeMapOut gdepth, double *gP, double *gKinv, void *stream);
+
+/* bilinear_sampler (utils_edited.py:402-486): img (N,C,hs,ws) strided, coords (N,ht,wt,2) contiguous
+ * -> out (N,ht,wt,C) contiguous (NHWC, like the reference).  add_grid != 0: coords are a FLOW and the
+ * meshgrid tables (of wt / ht entries) are added first == flow_warp (utils_edited.py:386-399). */
+SNDE_API int snde_bilinear_sampler_fwd(int N, int C, int hs, int ws, SndeImage img, int ht, int wt, const float *coords,
+                              int add_grid, const float *xtab, const float *ytab, int padding_mode,
+                              float *out, float *valid /* optional (N,ht,wt) */, void *stream);
+/* gout (N,ht,wt,C) -> gcoords (N,ht,wt,2) written; gimg optional (N,C,hs,ws strided; += with atomics, zero it first) */
+SNDE_API int snde_bilinear_sampler_bwd(int N, int C, int hs, int ws, SndeImage img, int ht, int wt, const float *coords,
+                              int add_grid, const float *xtab, const float *ytab, int padding_mode,
+                              const float *gout, float *gcoords, SndeImageOut gimg, void *stream);
+
+/* image_similarity(alpha,x,y) = alpha*DSSIM(x,y) + (1-alpha)*|x-y| (loss_functions.py:4-6, utils_edited.py:121-141).
+ * alpha = 1 gives DSSIM.  x,y (N,3,h,w) strided -> err (N,h,w,3) contiguous NHWC */
+SNDE_API int snde_image_similarity_fwd(int N, int h, int w, float alpha, SndeImage x, SndeImage y, float *err, void *stream);
+/* gerr (N,h,w,3) contiguous -> gx, gy (N,h,w,3) contiguous, written (either may be NULL) */
+SNDE_API int snde_image_similarity_bwd(int N, int h, int w, float alpha, SndeImage x, SndeImage y, const float *gerr,
+                              float *gx, float *gy, void *stream);
+
+/* smooth_loss(depth, image) (loss_functions.py:8-24): depth (M,h,w) strided, image (M,3,h,w) strided.
+ * sums: 2 doubles (sum|dx*wx|, sum|dy*wy|), += (zero first); loss = sums[0]/(M*h*(w-1)) + sums[1]/(M*(h-1)*w) */
+SNDE_API int snde_smooth_loss_fwd(int M, int h, int w, SndeMap depth, SndeImage img, double *sums, void *stream);
+/* gdepth (M,h,w) written = gscale * dloss/ddepth, gscale read from a DEVICE float (the upstream gradient) */
+SNDE_API int snde_smooth_loss_bwd(int M, int h, int w, SndeMap depth, SndeImage img, const float *gscale_dev,
+                         SndeMapOut gdepth, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNDE_H_ */

@@ -1,0 +1,499 @@
+// snde_kernels.cu -- sm_100a kernels + the C ABI declared in include/snde.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false (see build.py).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "snde.h"
+#include "snde_tile.cuh"
+#include "snde_loss_setup.cuh"
+
+using namespace snde;
+
+#define SNDE_CHECK_LAUNCH() do { if (cudaGetLastError() != cudaSuccess) return SNDE_ERR_CUDA; } while (0)
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// =============================================================================================
+// small helpers
+// =============================================================================================
+extern "C" int snde_version(void) { return SNDE_VERSION; }
+
+extern "C" const char *snde_strerror(int status) {
+    switch (status) {
+        case SNDE_OK: return "ok";
+        case SNDE_ERR_NULL: return "snde: required pointer is NULL";
+        case SNDE_ERR_SHAPE: return "snde: bad shape (non-positive dimension, C != 3, or h,w < 2 for smoothness)";
+        case SNDE_ERR_TOO_LARGE: return "snde: tensor too large (N*h*w must stay below 2^31)";
+        case SNDE_ERR_WORKSPACE: return "snde: workspace missing, too small or not 16-byte aligned";
+        case SNDE_ERR_ARG: return "snde: bad argument (enum, flag or scalar out of range)";
+        case SNDE_ERR_CUDA: return "snde: CUDA launch failed";
+        default: return "snde: unknown status";
+    }
+}
+
+// reference: utils/utils_edited.py:307-317 -- (linspace(-1,1,n)+1)*0.5*(n-1); torch.linspace rounds
+// start + step*i (first half) / end - step*(n-1-i) (second half) once, i.e. as an FMA.
+extern "C" int snde_fill_grid_table(int n, float *out) {
+    if (!out) return SNDE_ERR_NULL;
+    if (n <= 0) return SNDE_ERR_SHAPE;
+    if (n == 1) { out[0] = 0.f; return SNDE_OK; }
+    const float step = 2.f / (float)(n - 1);
+    const int half = n / 2;
+    for (int i = 0; i < n; ++i) {
+        volatile float lin = (i < half) ? fmaf(step, (float)i, -1.f) : fmaf(-step, (float)(n - i - 1), 1.f);
+        volatile float t = lin + 1.f;
+        t = t * 0.5f;
+        out[i] = t * (float)(n - 1);
+    }
+    return SNDE_OK;
+}
+
+
+__global__ void __launch_bounds__(128) loss_prep_kernel(int B, int S, int ns, const float *__restrict__ poses, PrepParams kp,
+                                                        float *__restrict__ P, float *__restrict__ Kinv) {
+    loss_prep_thread(blockIdx.x * blockDim.x + threadIdx.x, B, S, ns, poses, kp, P, Kinv);
+}
+
+__global__ void __launch_bounds__(128) loss_final_kernel(int B, int S, int ns, int flags, const float *__restrict__ poses,
+                                                         FinalParams fp, const double *__restrict__ gP,
+                                                         const double *__restrict__ gKinv, const double *__restrict__ loss,
+                                                         float *__restrict__ loss_out, float *__restrict__ grad_poses,
+                                                         float *__restrict__ grad_K) {
+    loss_final_thread(blockIdx.x * blockDim.x + threadIdx.x, B, S, ns, flags, poses, fp, gP, gKinv, loss, loss_out, grad_poses, grad_K);
+}
+
+template <bool GRAD, bool GRADK>
+__global__ void __launch_bounds__(TileCfg::NT, 3) loss_tile_kernel(const __grid_constant__ DevLoss p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
+    Regs regs;
+    loss_tile<GRAD, GRADK>(p, (int)blockIdx.x, sm, &regs);
+}
+
+extern "C" size_t snde_sizeof_loss_args(void) { return sizeof(SndeLossArgs); }
+
+extern "C" size_t snde_loss_workspace_bytes(int B, int S, int num_scales) {
+    if (B <= 0 || S <= 0 || num_scales <= 0) return 0;
+    return loss_ws_layout(B, S, num_scales).end;
+}
+
+extern "C" int64_t snde_loss_num_tiles(const SndeLossArgs *args) {
+    DevLoss d; int64_t n = 0;
+    SndeLossArgs tmp;
+    if (!args) return SNDE_ERR_NULL;
+    tmp = *args;
+    int rc = build_dev_loss(&tmp, d, nullptr, &n);
+    return rc ? rc : n;
+}
+
+extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
+    if (!a) return SNDE_ERR_NULL;
+    if (!a->poses || !a->loss_out) return SNDE_ERR_NULL;
+    if ((a->flags & SNDE_LOSS_GRAD) && !a->grad_poses) return SNDE_ERR_NULL;
+    if ((a->flags & SNDE_LOSS_GRAD_K) && !a->grad_K) return SNDE_ERR_NULL;
+    if (a->B <= 0 || a->S <= 0 || a->num_scales <= 0 || a->num_scales > SNDE_MAX_SCALES) return SNDE_ERR_SHAPE;
+    const LossWorkspace lay = loss_ws_layout(a->B, a->S, a->num_scales);
+    if (!a->workspace || a->workspace_bytes < lay.end || ((uintptr_t)a->workspace & 15)) return SNDE_ERR_WORKSPACE;
+    DevLoss d; int64_t tiles = 0;
+    int rc = build_dev_loss(a, d, &lay, &tiles);
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream_);
+    const int B = a->B, S = a->S, ns = a->num_scales, N = B * S;
+    unsigned char *ws = (unsigned char *)a->workspace;
+    if (cudaMemsetAsync(ws + lay.gP, 0, lay.end - lay.gP, st) != cudaSuccess) return SNDE_ERR_CUDA;
+    PrepParams kp; FinalParams fp;
+    build_prep_final(a, kp, fp);
+    loss_prep_kernel<<<(ns * N + 127) / 128, 128, 0, st>>>(B, S, ns, a->poses, kp, (float *)(ws + lay.P), (float *)(ws + lay.Kinv));
+    SNDE_CHECK_LAUNCH();
+    const size_t smem = sizeof(TileSmem);
+    const bool grad = a->flags & SNDE_LOSS_GRAD, gradk = a->flags & SNDE_LOSS_GRAD_K;
+    auto launch = [&](auto kern) -> int {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SNDE_ERR_CUDA;
+        kern<<<(unsigned)tiles, TileCfg::NT, smem, st>>>(d);
+        return SNDE_OK;
+    };
+    if (!grad) rc = launch(loss_tile_kernel<false, false>);
+    else if (!gradk) rc = launch(loss_tile_kernel<true, false>);
+    else rc = launch(loss_tile_kernel<true, true>);
+    if (rc) return rc;
+    SNDE_CHECK_LAUNCH();
+    loss_final_kernel<<<(B + 1 + 127) / 128, 128, 0, st>>>(B, S, ns, a->flags, a->poses, fp, (const double *)(ws + lay.gP),
+                                                           (const double *)(ws + lay.gKinv), (const double *)(ws + lay.loss),
+                                                           a->loss_out, a->grad_poses, a->grad_K);
+    SNDE_CHECK_LAUNCH();
+    return SNDE_OK;
+}
+
+// =============================================================================================
+// Reference-signature pieces
+// =============================================================================================
+__global__ void __launch_bounds__(128) pose_matrices_kernel(int B, const float *__restrict__ poses, long long stride,
+                                                            const float *__restrict__ K, int reverse, float *__restrict__ P,
+                                                            float *__restrict__ Kinv) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float vec[6], Km[9], T[12], Ti[12], Pm[12], Ki[9];
+    for (int j = 0; j < 6; ++j) vec[j] = poses[b * stride + j];
+    for (int j = 0; j < 9; ++j) Km[j] = K[b * 9 + j];
+    pose_to_T(vec, T, Ti);
+    k_times_T(Km, reverse ? Ti : T, Pm);
+    for (int j = 0; j < 12; ++j) P[b * 12 + j] = Pm[j];
+    if (!inverse3(Km, Ki)) for (int j = 0; j < 9; ++j) Ki[j] = nanf("");
+    for (int j = 0; j < 9; ++j) Kinv[b * 9 + j] = Ki[j];
+}
+
+extern "C" int snde_pose_matrices(int B, const float *poses, int64_t pose_stride, const float *K, int reverse_pose,
+                                  float *P, float *Kinv, void *stream) {
+    if (!poses || !K || !P || !Kinv) return SNDE_ERR_NULL;
+    if (B <= 0) return SNDE_ERR_SHAPE;
+    pose_matrices_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(B, poses, pose_stride, K, reverse_pose, P, Kinv);
+    SNDE_CHECK_LAUNCH();
+    return SNDE_OK;
+}
+
+__global__ void __launch_bounds__(128) pose_matrices_bwd_kernel(int B, const float *__restrict__ poses, long long stride,
+                                                                const float *__restrict__ K, int reverse,
+                                                                const double *__restrict__ gP, const double *__restrict__ gKinv,
+                                                                float *__restrict__ grad_poses, float *__restrict__ grad_K) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float vec[6], Km[9];
+    for (int j = 0; j < 6; ++j) vec[j] = poses[b * stride + j];
+    for (int j = 0; j < 9; ++j) Km[j] = K[b * 9 + j];
+    double gv[6] = {0, 0, 0, 0, 0, 0}, gK[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    pose_prep_bwd(vec, Km, reverse ? nullptr : gP + b * 12, reverse ? gP + b * 12 : nullptr,
+                  (gKinv && grad_K) ? gKinv + b * 9 : nullptr, gv, grad_K ? gK : nullptr);
+    for (int j = 0; j < 6; ++j) grad_poses[b * 6 + j] = (float)gv[j];
+    if (grad_K) for (int j = 0; j < 9; ++j) grad_K[b * 9 + j] = (float)gK[j];
+}
+
+extern "C" int snde_pose_matrices_bwd(int B, const float *poses, int64_t pose_stride, const float *K, int reverse_pose,
+                                      const double *gP, const double *gKinv, float *grad_poses, float *grad_K, void *stream) {
+    if (!poses || !K || !gP || !grad_poses) return SNDE_ERR_NULL;
+    if (B <= 0) return SNDE_ERR_SHAPE;
+    pose_matrices_bwd_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(B, poses, pose_stride, K, reverse_pose, gP, gKinv,
+                                                                            grad_poses, grad_K);
+    SNDE_CHECK_LAUNCH();
+    return SNDE_OK;
+}
+
+// ---- compute_rigid_flow, per-pixel part: grid (ceil(h*w/256), B) ----
+__global__ void __launch_bounds__(256) rigid_flow_fwd_kernel(int h, int w, DevMap depth, const float *__restrict__ Kinv,
+                                                             const float *__restrict__ P, const float *__restrict__ xtab,
+                                                             const float *__restrict__ ytab, float *__restrict__ flow) {
+    const int b = blockIdx.y;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= h * w) return;
+    const int iy = pix / w, ix = pix - iy * w;
+    float Ki[9], Pm[12];
+    for (int j = 0; j < 9; ++j) Ki[j] = __ldg(Kinv + b * 9 + j);
+    for (int j = 0; j < 12; ++j) Pm[j] = __ldg(P + b * 12 + j);
+    const float xt = __ldg(xtab + ix), yt = __ldg(ytab + iy);
+    Reproj rp; reproject(Ki, Pm, xt, yt, ld_map(depth, b, iy, ix), rp);
+    float2 o; o.x = rp.xn - xt; o.y = rp.yn - yt;
+    reinterpret_cast<float2 *>(flow)[(size_t)b * h * w + pix] = o;
+}
+
+extern "C" int snde_rigid_flow_fwd(int B, int h, int w, SndeMap depth, const float *Kinv, const float *P, const float *xtab,
+                                   const float *ytab, float *flow, void *stream) {
+    if (!depth.ptr || !Kinv || !P || !xtab || !ytab || !flow) return SNDE_ERR_NULL;
+    if (B <= 0 || h <= 0 || w <= 0) return SNDE_ERR_SHAPE;
+    if ((long long)B * h * w >= (1LL << 31) || B > 65535) return SNDE_ERR_TOO_LARGE;
+    dim3 grid((h * w + 255) / 256, B);
+    rigid_flow_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(h, w, dev(depth), Kinv, P, xtab, ytab, flow);
+    SNDE_CHECK_LAUNCH();
+    return SNDE_OK;
+}
+
+template <int NV>
+__device__ __forceinline__ void block_atomic_add(float (&v)[NV], double *dst, float *red /*[8][NV]*/) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) red[warp * NV + i] = x;
+    }
+    __syncthreads();
+    if (tid < NV) {
+        double s = 0.0;
+        for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) s += (double)red[wq * NV + tid];
+        if (s != 0.0) atomicAdd(dst + tid, s);
+    }
+    __syncthreads();
+}
+
+template <bool GRADK>
+__global__ void __launch_bounds__(256) rigid_flow_bwd_kernel(int h, int w, DevMap depth, const float *__restrict__ Kinv,
+                                                             const float *__restrict__ P, const float *__restrict__ xtab,
+                                                             const float *__restrict__ ytab, const float *__restrict__ gflow,
+                                                             DevMapOut gdepth, double *__restrict__ gP, double *__restrict__ gKinv) {
+    __shared__ float red[8 * 12];
+    const int b = blockIdx.y;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    float aP[12], aK[9];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) aP[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) aK[j] = 0.f;
+    if (pix < h * w) {
+        const int iy = pix / w, ix = pix - iy * w;
+        float Ki[9], Pm[12];
+        for (int j = 0; j < 9; ++j) Ki[j] = __ldg(Kinv + b * 9 + j);
+        for (int j = 0; j < 12; ++j) Pm[j] = __ldg(P + b * 12 + j);
+        const float xt = __ldg(xtab + ix), yt = __ldg(ytab + iy), d = ld_map(depth, b, iy, ix);
+        Reproj rp; reproject(Ki, Pm, xt, yt, d, rp);
+        const float2 g = reinterpret_cast<const float2 *>(gflow)[(size_t)b * h * w + pix];
+        float gu[3], gcam[3];
+        const float gd = reproject_bwd(Pm, rp, g.x, g.y, gu, gcam);
+        gdepth.p[b * gdepth.sn + (long long)iy * gdepth.sh + (long long)ix * gdepth.sw] = gd;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            aP[q * 4 + 0] = gu[q] * rp.cam[0]; aP[q * 4 + 1] = gu[q] * rp.cam[1]; aP[q * 4 + 2] = gu[q] * rp.cam[2]; aP[q * 4 + 3] = gu[q];
+            if (GRADK) { const float gray = gcam[q] * d; aK[q * 3 + 0] = gray * xt; aK[q * 3 + 1] = gray * yt; aK[q * 3 + 2] = gray; }
+        }
+    }
+    block_atomic_add<12>(aP, gP + b * 12, red);
+    if (GRADK) block_atomic_add<9>(aK, gKinv + b * 9, red);
+}
+
+extern "C" int snde_rigid_flow_bwd(int B, int h, int w, SndeMap depth, const float *Kinv, const float *P, const float *xtab,
+                                   const float *ytab, const float *gflow, SndeMapOut gdepth, double *gP, double *gKinv,
+                                   void *stream) {
+    if (!depth.ptr || !Kinv || !P || !xtab || !ytab || !gflow || !gdepth.ptr || !gP) return SNDE_ERR_NULL;
+    if (B <= 0 || h <= 0 || w <= 0) return SNDE_ERR_SHAPE;
+    if ((long long)B * h * w >= (1LL << 31) || B > 65535) return SNDE_ERR_TOO_LARGE;
+    dim3 grid((h * w + 255) / 256, B);
+    if (gKinv) rigid_flow_bwd_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(h, w, dev(depth), Kinv, P, xtab, ytab, gflow, dev(gdepth), gP, gKinv);
+    else rigid_flow_bwd_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(h, w, dev(depth), Kinv, P, xtab, ytab, gflow, dev(gdepth), gP, gKinv);
+    SNDE_CHECK_LAUNCH();
+    return SNDE_OK;
+}
+
+// ---- bilinear_sampler / flow_warp ----
+__global__ void __launch_bounds__(256) sampler_fwd_kernel(long long total, int C, int hs, int ws, DevImage img, int ht, int wt,
+                                                          const float *__restrict__ coords, int add_grid,
+                                                          const float *__restrict__ xtab, const float *__restrict__ ytab, int border,
+                                                          float *__restrict__ out, float *__restrict__ valid) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(i % wt); const long long t = i / wt; const int iy = (int)(t % ht); const long long n = t / ht;
+        const float2 cf = reinterpret_cast<const float2 *>(coords)[i];
+        float x = cf.x, y = cf.y;
+        if (add_grid) { x = __ldg(xtab + ix) + x; y = __ldg(ytab + iy) + y; }
+        Taps tp; make_taps(x, y, hs, ws, border, tp);
+        const float *base = img.p + n * img.sn;
+        const long long o00 = (long long)tp.y0 * img.sh + (long long)tp.x0 * img.sw, o01 = (long long)tp.y1 * img.sh + (long long)tp.x0 * img.sw;
+        const long long o10 = (long long)tp.y0 * img.sh + (long long)tp.x1 * img.sw, o11 = (long long)tp.y1 * img.sh + (long long)tp.x1 * img.sw;
+        for (int c = 0; c < C; ++c) {
+            const float *bc = base + c * img.sc;
+            out[i * C + c] = tap_blend(tp, __ldg(bc + o00), __ldg(bc + o01), __ldg(bc + o10), __ldg(bc + o11));
+        }
+        if (valid) valid[i] = tap_valid(x, y, hs, ws, border);
+    }
+}
+
+extern "C" int snde_bilinear_sampler_fwd(int N, int C, int hs, int ws, SndeImage img, int ht, int wt, const float *coords,
+                                         int add_grid, const float *xtab, const float *ytab, int padding_mode, float *out,
+                                         float *valid, void *stream) {
+    if (!img.ptr || !coords || !out || (add_grid && (!xtab || !ytab))) return SNDE_ERR_NULL;
+    if (N <= 0 || C <= 0 || hs <= 0 || ws <= 0 || ht <= 0 || wt <= 0) return SNDE_ERR_SHAPE;
+    if (padding_mode != SNDE_PAD_ZEROS && padding_mode != SNDE_PAD_BORDER) return SNDE_ERR_ARG;
+    const long long total = (long long)N * ht * wt;
+    if (total * C >= (1LL << 31) || (long long)N * hs * ws * C >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
+    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    sampler_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, C, hs, ws, dev(img), ht, wt, coords, add_grid, xtab, ytab,
+                                                             padding_mode, out, valid);
+    SNDE_CHECK_LAUNCH();
+    return SNDE_OK;
+}
+
+__global__ void __launch_bounds__(256) sampler_bwd_kernel(long long total, int C, int hs, int ws, DevImage img, int ht, int wt,
+                                                          const float *__restrict__ coords, int add_grid,
+                                                          const float *__restrict__ xtab, const float *__restrict__ ytab, int border,
+                                                          const float *__restrict__ gout, float *__restrict__ gcoords, DevImageOut gimg) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(i % wt); const long long t = i / wt; const int iy = (int)(t % ht); const long long n = t / ht;
+        const float2 cf = reinterpret_cast<const float2 *>(coords)[i];
+        float x = cf.x, y = cf.y;
+        if (add_grid) { x = __ldg(xtab + ix) + x; y = __ldg(ytab + iy) + y; }
+        Taps tp; make_taps(x, y, hs, ws, border, tp);
+        const float *base = img.p + n * img.sn;
+        const long long o00 = (long long)tp.y0 * img.sh + (long long)tp.x0 * img.sw, o01 = (long long)tp.y1 * img.sh + (long long)tp.x0 * img.sw;
+        const long long o10 = (long long)tp.y0 * img.sh + (long long)tp.x1 * img.sw, o11 = (long long)tp.y1 * img.sh + (long long)tp.x1 * img.sw;
+        const float w00 = tp.wx0 * tp.wy0, w01 = tp.wx0 * tp.wy1, w10 = tp.wx1 * tp.wy0, w11 = tp.wx1 * tp.wy1;
+        float g00 = 0.f, g01 = 0.f, g10 = 0.f, g11 = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float *bc = base + c * img.sc;
+            const float g = gout[i * C + c];
+            g00 += g * __ldg(bc + o00); g01 += g * __ldg(bc + o01); g10 += g * __ldg(bc + o10); g11 += g * __ldg(bc + o11);
+            if (gimg.p) {
+                float *gb = gimg.p + n * gimg.sn + c * gimg.sc;
+                atomicAdd(gb + (long long)tp.y0 * gimg.sh + (long long)tp.x0 * gimg.sw, w00 * g);
+                atomicAdd(gb + (long long)tp.y1 * gimg.sh + (long long)tp.x0 * gimg.sw, w01 * g);
+                atomicAdd(gb + (long long)tp.y0 * gimg.sh + (long long)tp.x1 * gimg.sw, w10 * g);
+                atomicAdd(gb + (long long)tp.y1 * gimg.sh + (long long)tp.x1 * gimg.sw, w11 * g);
+            }
+        }
+        const float gwx0 = g00 * tp.wy0 + g01 * tp.wy1, gwx1 = g10 * tp.wy0 + g11 * tp.wy1;
+        const float gwy0 = g00 * tp.wx0 + g10 * tp.wx1, gwy1 = g01 * tp.wx0 + g11 * tp.wx1;
+        float2 o; o.x = (gwx1 - gwx0) * tp.dx; o.y = (gwy1 - gwy0) * tp.dy;
+        reinterpret_cast<float2 *>(gcoords)[i] = o;
+    }
+}
+
+extern "C" int snde_bilinear_sampler_bwd(int N, int C, int hs, int ws, SndeImage img, int ht, int wt, const float *coords,
+                                         int add_grid, const float *xtab, const float *ytab, int padding_mode, const float *gout,
+                                         float *gcoords, SndeImageOut gimg, void *stream) {
+    if (!img.ptr || !coords || !gout || !gcoords || (add_grid && (!xtab || !ytab))) return SNDE_ERR_NULL;
+    if (N <= 0 || C <= 0 || hs <= 0 || ws <= 0 || ht <= 0 || wt <= 0) return SNDE_ERR_SHAPE;
+    if (padding_mode != SNDE_PAD_ZEROS && padding_mode != SNDE_PAD_BORDER) return SNDE_ERR_ARG;
+    const long long total = (long long)N * ht * wt;
+    if (total * C >= (1LL << 31) || (long long)N * hs * ws * C >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
+    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    sampler_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, C, hs, ws, dev(img), ht, wt, coords, add_grid, xtab, ytab,
+                                                             padding_mode, gout, gcoords, dev(gimg));
+    SNDE_CHECK_LAUNCH();
+    return SNDE_OK;
+}
+
+// ---- image_similarity / DSSIM (materialising, reference-signature version) ----
+// one thread per (n, y, x); 5x5 neighbourhoods come straight from global memory (L1/L2 resident).
+// The fused tile kernel is the fast path; this one exists so the reference's own call sequence runs.
+__device__ __forceinline__ float img_or_zero(const DevImage &im, long long n, int c, int y, int x, int h, int w) {
+    return (y >= 0 && y < h && x >= 0 && x < w) ? ld_img(im, n, c, y, x) : 0.f;
+}
+
+__device__ __forceinline__ void ssim_at(const DevImage &X, const DevImage &Y, long long n, int c, int cy, int cx, int h, int w, Ssim &ss) {
+    float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+#pragma unroll
+    for (int dr = -1; dr <= 1; ++dr)
+#pragma unroll
+        for (int dc = -1; dc <= 1; ++dc) {
+            const float xv = img_or_zero(X, n, c, cy + dr, cx + dc, h, w), yv = img_or_zero(Y, n, c, cy + dr, cx + dc, h, w);
+            sx = sx + xv; sy = sy + yv; sxx = sxx + xv * xv; syy = syy + yv * yv; sxy = sxy + xv * yv;
+        }
+    ssim_from_sums(sx, sy, sxx, syy, sxy, ss);
+}
+
+__global__ void __launch_bounds__(256) similarity_fwd_kernel(long long total, int h, int w, float alpha, float oma, DevImage X, DevImage Y,
+                                                             float *__restrict__ err) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(i % w); const long long t = i / w; const int iy = (int)(t % h); const long long n = t / h;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Ssim ss; ssim_at(X, Y, n, c, iy, ix, h, w, ss);
+            float v;
+            err[i * 3 + c] = similarity_value(alpha, oma, ss.S, ld_img(X, n, c, iy, ix), ld_img(Y, n, c, iy, ix), v);
+        }
+    }
+}
+
+extern "C" int snde_image_similarity_fwd(int N, int h, int w, float alpha, SndeImage x, SndeImage y, float *err, void *stream) {
+    if (!x.ptr || !y.ptr || !err) return SNDE_ERR_NULL;
+    if (N <= 0 || h <= 0 || w <= 0) return SNDE_ERR_SHAPE;
+    const long long total = (long long)N * h * w;
+    if (total * 3 >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
+    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    similarity_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, h, w, alpha, (float)(1.0 - (double)alpha), dev(x), dev(y), err);
+    SNDE_CHECK_LAUNCH();
+    return SNDE_OK;
+}
+
+__global__ void __launch_bounds__(256) similarity_bwd_kernel(long long total, int h, int w, float alpha, float oma, DevImage X, DevImage Y,
+                                                             const float *__restrict__ gerr, float *__restrict__ gx, float *__restrict__ gy) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(i % w); const long long t = i / w; const int iy = (int)(t % h); const long long n = t / h;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float bmx = 0.f, bmy = 0.f, be = 0.f, bxy = 0.f;
+            for (int dr = -1; dr <= 1; ++dr)
+                for (int dc = -1; dc <= 1; ++dc) {
+                    const int qy = iy + dr, qx = ix + dc;
+                    if (qy < 0 || qy >= h || qx < 0 || qx >= w) continue;
+                    Ssim ss; ssim_at(X, Y, n, c, qy, qx, h, w, ss);
+                    const float v = (1.f - ss.S) / 2.f;
+                    const float g = gerr[((n * h + qy) * (long long)w + qx) * 3 + c];
+                    const float gS = (v >= 0.f && v <= 1.f) ? -0.5f * alpha * g : 0.f;
+                    float cmx, cmy, ce, cxy; ssim_bwd_coeffs(ss, gS, cmx, cmy, ce, cxy);
+                    bmx += cmx; bmy += cmy; be += ce; bxy += cxy;
+                }
+            const float xv = ld_img(X, n, c, iy, ix), yv = ld_img(Y, n, c, iy, ix);
+            const float l1 = oma * gerr[i * 3 + c] * signf(xv - yv);
+            if (gx) gx[i * 3 + c] = (bmx + 2.f * xv * be + yv * bxy) / 9.f + l1;
+            if (gy) gy[i * 3 + c] = (bmy + 2.f * yv * be + xv * bxy) / 9.f - l1;
+        }
+    }
+}
+
+extern "C" int snde_image_similarity_bwd(int N, int h, int w, float alpha, SndeImage x, SndeImage y, const float *gerr, float *gx,
+                                         float *gy, void *stream) {
+    if (!x.ptr || !y.ptr || !gerr) return SNDE_ERR_NULL;
+    if (N <= 0 || h <= 0 || w <= 0) return SNDE_ERR_SHAPE;
+    const long long total = (long long)N * h * w;
+    if (total * 3 >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
+    if (!gx && !gy) return SNDE_OK;
+    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    similarity_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, h, w, alpha, (float)(1.0 - (double)alpha), dev(x), dev(y), gerr, gx, gy);
+    SNDE_CHECK_LAUNCH();
+    return SNDE_OK;
+}
+
+// ---- smooth_loss ----
+__device__ __forceinline__ float pair_weight(const DevImage &I, long long m, int y0, int x0, int y1, int x1) {
+    return edge_weight3(ld_img(I, m, 0, y0, x0), ld_img(I, m, 1, y0, x0), ld_img(I, m, 2, y0, x0),
+                        ld_img(I, m, 0, y1, x1), ld_img(I, m, 1, y1, x1), ld_img(I, m, 2, y1, x1));
+}
+
+__global__ void __launch_bounds__(256) smooth_fwd_kernel(long long total, int h, int w, DevMap D, DevImage I, double *__restrict__ sums) {
+    __shared__ float red[8 * 2];
+    float acc[2] = {0.f, 0.f};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(i % w); const long long t = i / w; const int iy = (int)(t % h); const long long m = t / h;
+        const float d = ld_map(D, m, iy, ix);
+        if (ix + 1 < w) acc[0] += fabsf((d - ld_map(D, m, iy, ix + 1)) * pair_weight(I, m, iy, ix, iy, ix + 1));
+        if (iy + 1 < h) acc[1] += fabsf((d - ld_map(D, m, iy + 1, ix)) * pair_weight(I, m, iy, ix, iy + 1, ix));
+    }
+    block_atomic_add<2>(acc, sums, red);
+}
+
+extern "C" int snde_smooth_loss_fwd(int M, int h, int w, SndeMap depth, SndeImage img, double *sums, void *stream) {
+    if (!depth.ptr || !img.ptr || !sums) return SNDE_ERR_NULL;
+    if (M <= 0 || h < 2 || w < 2) return SNDE_ERR_SHAPE;
+    const long long total = (long long)M * h * w;
+    if (total * 3 >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    smooth_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, h, w, dev(depth), dev(img), sums);
+    SNDE_CHECK_LAUNCH();
+    return SNDE_OK;
+}
+
+__global__ void __launch_bounds__(256) smooth_bwd_kernel(long long total, int h, int w, DevMap D, DevImage I, const float *__restrict__ gscale,
+                                                         double inv_nx, double inv_ny, DevMapOut G) {
+    const float gs = __ldg(gscale);
+    const float cx = (float)((double)gs * inv_nx), cy = (float)((double)gs * inv_ny);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(i % w); const long long t = i / w; const int iy = (int)(t % h); const long long m = t / h;
+        const float d = ld_map(D, m, iy, ix);
+        float g = 0.f;
+        if (ix + 1 < w) { const float wg = pair_weight(I, m, iy, ix, iy, ix + 1); g += cx * signf((d - ld_map(D, m, iy, ix + 1)) * wg) * wg; }
+        if (ix >= 1)    { const float wg = pair_weight(I, m, iy, ix - 1, iy, ix); g -= cx * signf((ld_map(D, m, iy, ix - 1) - d) * wg) * wg; }
+        if (iy + 1 < h) { const float wg = pair_weight(I, m, iy, ix, iy + 1, ix); g += cy * signf((d - ld_map(D, m, iy + 1, ix)) * wg) * wg; }
+        if (iy >= 1)    { const float wg = pair_weight(I, m, iy - 1, ix, iy, ix); g -= cy * signf((ld_map(D, m, iy - 1, ix) - d) * wg) * wg; }
+        G.p[m * G.sn + (long long)iy * G.sh + (long long)ix * G.sw] = g;
+    }
+}
+
+extern "C" int snde_smooth_loss_bwd(int M, int h, int w, SndeMap depth, SndeImage img, const float *gscale_dev, SndeMapOut gdepth,
+                                    void *stream) {
+    if (!depth.ptr || !img.ptr || !gscale_dev || !gdepth.ptr) return SNDE_ERR_NULL;
+    if (M <= 0 || h < 2 || w < 2) return SNDE_ERR_SHAPE;
+    const long long total = (long long)M * h * w;
+    if (total * 3 >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    smooth_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, h, w, dev(depth), dev(img), gscale_dev,
+                                                            1.0 / ((double)M * h * (w - 1)), 1.0 / ((double)M * (h - 1) * w), dev(gdepth));
+    SNDE_CHECK_LAUNCH();
+    return SNDE_OK;
+}

@@ -1,0 +1,172 @@
+// snde_loss_setup.cuh -- host-side setup of the fused loss (argument validation, workspace layout,
+// work table) and the per-thread bodies of its two tiny companion kernels (matrix prep, finalize).
+// Shared by snde_kernels.cu (the product) and the host-emulation test harness.
+#pragma once
+#include <string.h>
+
+#include "snde.h"
+#include "snde_tile.cuh"
+
+namespace snde {
+
+static inline DevImage dev(const SndeImage &v) { return DevImage{v.ptr, v.sn, v.sc, v.sh, v.sw}; }
+static inline DevImageOut dev(const SndeImageOut &v) { return DevImageOut{v.ptr, v.sn, v.sc, v.sh, v.sw}; }
+static inline DevMap dev(const SndeMap &v) { return DevMap{v.ptr, v.sn, v.sh, v.sw}; }
+static inline DevMapOut dev(const SndeMapOut &v) { return DevMapOut{v.ptr, v.sn, v.sh, v.sw}; }
+
+// =============================================================================================
+// Fused loss
+// =============================================================================================
+struct LossWorkspace {   // offsets in bytes
+    size_t P, Kinv, gP, gKinv, loss, end;
+};
+static inline LossWorkspace loss_ws_layout(int B, int S, int ns) {
+    LossWorkspace o;
+    auto up = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t N = (size_t)B * S;
+    o.P = 0;
+    o.Kinv = up(o.P + sizeof(float) * ns * N * 24);
+    o.gP = up(o.Kinv + sizeof(float) * ns * B * 9);
+    o.gKinv = up(o.gP + sizeof(double) * ns * N * 24);
+    o.loss = up(o.gKinv + sizeof(double) * ns * B * 9);
+    o.end = up(o.loss + sizeof(double) * ns * 4);
+    return o;
+}
+
+
+// one thread per (scale, n): P_fwd = K_s @ T, P_bwd = K_s @ inv(T); threads with k == 0 also write Kinv
+struct PrepParams { const float *K[SNDE_MAX_SCALES]; };
+
+SNDE_HD void loss_prep_thread(int i, int B, int S, int ns, const float *poses, PrepParams kp, float *P, float *Kinv) {
+    const int N = B * S;
+    if (i >= ns * N) return;
+    const int s = i / N, n = i - s * N;
+    const int k = n / B, b = n - k * B;
+    float vec[6], K[9], T[12], Ti[12], Pm[12];
+    for (int j = 0; j < 6; ++j) vec[j] = poses[(b * S + k) * 6 + j];
+    for (int j = 0; j < 9; ++j) K[j] = kp.K[s][b * 9 + j];
+    pose_to_T(vec, T, Ti);
+    float *dst = P + ((size_t)s * N + n) * 24;
+    k_times_T(K, T, Pm);  for (int j = 0; j < 12; ++j) dst[j] = Pm[j];
+    k_times_T(K, Ti, Pm); for (int j = 0; j < 12; ++j) dst[12 + j] = Pm[j];
+    if (k == 0) {
+        float Ki[9];
+        if (!inverse3(K, Ki)) for (int j = 0; j < 9; ++j) Ki[j] = nanf("");
+        for (int j = 0; j < 9; ++j) Kinv[((size_t)s * B + b) * 9 + j] = Ki[j];
+    }
+}
+
+struct FinalParams {
+    const float *K[SNDE_MAX_SCALES];
+    float photo_weight[SNDE_MAX_SCALES], smooth_weight[SNDE_MAX_SCALES];
+    double inv_count[SNDE_MAX_SCALES], inv_nx[SNDE_MAX_SCALES], inv_ny[SNDE_MAX_SCALES];
+};
+
+// thread b < B: pose / intrinsics gradients of batch element b; thread B: the loss scalars
+SNDE_HD void loss_final_thread(int i, int B, int S, int ns, int flags, const float *poses, FinalParams fp, const double *gP,
+                               const double *gKinv, const double *loss, float *loss_out, float *grad_poses, float *grad_K) {
+    const int N = B * S;
+    if (i == B) {
+        double rigid = 0.0, smooth = 0.0;
+        for (int s = 0; s < ns; ++s) {
+            const double fm = loss[s * 4 + 0] * fp.inv_count[s], bm = loss[s * 4 + 1] * fp.inv_count[s];
+            const double sm = loss[s * 4 + 2] * fp.inv_nx[s] + loss[s * 4 + 3] * fp.inv_ny[s];
+            rigid += (double)fp.photo_weight[s] * (fm + bm);
+            smooth += (double)fp.smooth_weight[s] * sm;
+            loss_out[3 + 3 * s + 0] = (float)fm; loss_out[3 + 3 * s + 1] = (float)bm; loss_out[3 + 3 * s + 2] = (float)sm;
+        }
+        loss_out[0] = (float)(rigid + smooth); loss_out[1] = (float)rigid; loss_out[2] = (float)smooth;
+        return;
+    }
+    if (i > B || !(flags & FLAG_GRAD)) return;
+    const int b = i;
+    const bool wantK = (flags & FLAG_GRAD_K) != 0;
+    double gK[SNDE_MAX_SCALES][9];
+    for (int s = 0; s < ns; ++s) for (int j = 0; j < 9; ++j) gK[s][j] = 0.0;
+    for (int k = 0; k < S; ++k) {
+        const int n = k * B + b;
+        float vec[6];
+        for (int j = 0; j < 6; ++j) vec[j] = poses[(b * S + k) * 6 + j];
+        double gv[6] = {0, 0, 0, 0, 0, 0};
+        for (int s = 0; s < ns; ++s) {
+            float K[9];
+            for (int j = 0; j < 9; ++j) K[j] = fp.K[s][b * 9 + j];
+            const double *g = gP + ((size_t)s * N + n) * 24;
+            pose_prep_bwd(vec, K, g, g + 12, (wantK && k == 0) ? gKinv + ((size_t)s * B + b) * 9 : nullptr, gv,
+                          wantK ? gK[s] : nullptr);
+        }
+        for (int j = 0; j < 6; ++j) grad_poses[(b * S + k) * 6 + j] = (float)gv[j];
+    }
+    if (wantK) for (int s = 0; s < ns; ++s) for (int j = 0; j < 9; ++j) grad_K[((size_t)b * ns + s) * 9 + j] = (float)gK[s][j];
+}
+
+static inline int build_dev_loss(const SndeLossArgs *a, DevLoss &d, const LossWorkspace *lay, int64_t *num_tiles) {
+    if (!a) return SNDE_ERR_NULL;
+    if (a->B <= 0 || a->S <= 0 || a->num_scales <= 0 || a->num_scales > SNDE_MAX_SCALES) return SNDE_ERR_SHAPE;
+    if (a->padding_mode != SNDE_PAD_ZEROS && a->padding_mode != SNDE_PAD_BORDER) return SNDE_ERR_ARG;
+    if (a->flags & ~15) return SNDE_ERR_ARG;
+    if ((a->flags & SNDE_LOSS_GRAD_K) && !(a->flags & SNDE_LOSS_GRAD)) return SNDE_ERR_ARG;
+    if (!(a->alpha >= 0.f && a->alpha <= 1.f)) return SNDE_ERR_ARG;
+    memset(&d, 0, sizeof(d));
+    const int B = a->B, S = a->S, ns = a->num_scales;
+    const long long N = (long long)B * S, M = (long long)B * (1 + S);
+    d.B = B; d.S = S; d.num_scales = ns; d.flags = a->flags; d.padding = a->padding_mode;
+    d.alpha = a->alpha; d.oma = (float)(1.0 - (double)a->alpha);
+    unsigned char *ws = (unsigned char *)a->workspace;
+    for (int s = 0; s < ns; ++s) {
+        const SndeLossScale &in = a->scale[s];
+        DevScale &o = d.sc[s];
+        if (in.h < 2 || in.w < 2) return SNDE_ERR_SHAPE;
+        if (M * in.h * in.w >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
+        if (!in.tgt.ptr || !in.src.ptr || !in.depth.ptr || !in.K || !in.xtab || !in.ytab) return SNDE_ERR_NULL;
+        if ((a->flags & SNDE_LOSS_GRAD) && !in.grad_depth.ptr) return SNDE_ERR_NULL;
+        o.h = in.h; o.w = in.w;
+        o.tiles_x = (in.w + TileCfg::TW - 1) / TileCfg::TW;
+        o.tiles_y = (in.h + TileCfg::TH - 1) / TileCfg::TH;
+        o.tgt = dev(in.tgt); o.src = dev(in.src); o.depth = dev(in.depth); o.gdepth = dev(in.grad_depth);
+        o.xtab = in.xtab; o.ytab = in.ytab;
+        if (lay) {
+            o.P = (const float *)(ws + lay->P) + (size_t)s * N * 24;
+            o.Kinv = (const float *)(ws + lay->Kinv) + (size_t)s * B * 9;
+            o.gP = (double *)(ws + lay->gP) + (size_t)s * N * 24;
+            o.gKinv = (double *)(ws + lay->gKinv) + (size_t)s * B * 9;
+            o.loss = (double *)(ws + lay->loss) + (size_t)s * 4;
+        }
+        o.gphoto = (float)((double)in.photo_weight / ((double)N * in.h * in.w * 3.0));
+        o.gsx = (float)((double)in.smooth_weight / ((double)M * in.h * (in.w - 1)));
+        o.gsy = (float)((double)in.smooth_weight / ((double)M * (in.h - 1) * in.w));
+        o.mask_fwd = dev(in.mask_fwd); o.mask_bwd = dev(in.mask_bwd);
+        o.warped_fwd = dev(in.warped_fwd); o.warped_bwd = dev(in.warped_bwd);
+        o.err_fwd = dev(in.err_fwd); o.err_bwd = dev(in.err_bwd);
+    }
+    // work table: the heavy class-F items (S warps each) first, then the class-R items
+    long long total = 0;
+    int ne = 0;
+    for (int cls = 0; cls < 2; ++cls)
+        for (int s = 0; s < ns; ++s) {
+            const long long cnt = (long long)d.sc[s].tiles_x * d.sc[s].tiles_y * (cls == 0 ? B : N);
+            if (total + cnt >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
+            d.entry[ne++] = DevEntry{(int)total, (int)cnt, s, cls};
+            total += cnt;
+        }
+    d.num_entries = ne;
+    if (num_tiles) *num_tiles = total;
+    return SNDE_OK;
+}
+
+
+// fill the per-scale parameter blocks of the prep / finalize kernels
+static inline void build_prep_final(const SndeLossArgs *a, PrepParams &kp, FinalParams &fp) {
+    memset(&kp, 0, sizeof kp); memset(&fp, 0, sizeof fp);
+    const int B = a->B, S = a->S, N = B * S;
+    for (int s = 0; s < a->num_scales; ++s) {
+        const SndeLossScale &in = a->scale[s];
+        kp.K[s] = in.K; fp.K[s] = in.K;
+        fp.photo_weight[s] = in.photo_weight; fp.smooth_weight[s] = in.smooth_weight;
+        fp.inv_count[s] = 1.0 / ((double)N * in.h * in.w * 3.0);
+        fp.inv_nx[s] = 1.0 / ((double)B * (1 + S) * in.h * (in.w - 1));
+        fp.inv_ny[s] = 1.0 / ((double)B * (1 + S) * (in.h - 1) * in.w);
+    }
+}
+
+}  // namespace snde
