@@ -35,7 +35,7 @@ def multi_scale_intrinsics(orc: Oracle, K, num_scales):
 
 
 def geonet_loss(orc: Oracle, tgt_pyr, src_pyr, depth_pyr, poses, K_ms, alpha=0.85, w_rigid=1.0,
-                w_smooth=0.5, want_grad=True, keep_maps=False):
+                w_smooth=0.5, want_grad=True, keep_maps=False, masks=None):
     """tgt_pyr[s] (B,h,w,3); src_pyr[s] (S*B,h,w,3) source-major; depth_pyr[s] (B(1+S),h,w);
     poses (B,S,6); K_ms (B,scales,3,3).  Returns a dict of losses (+ grads, + maps)."""
     num_scales = len(tgt_pyr)
@@ -67,7 +67,12 @@ def geonet_loss(orc: Oracle, tgt_pyr, src_pyr, depth_pyr, poses, K_ms, alpha=0.8
         bwd_warp = orc.bilinear_sampler(tgt_tile, bwd_coords)
         fwd_err = orc.image_similarity(alpha, tgt_tile, fwd_warp)
         bwd_err = orc.image_similarity(alpha, src, bwd_warp)
-        fm, bm = orc.mean(fwd_err), orc.mean(bwd_err)
+        if masks is not None:   # extension: explainability weights (S*B,h,w) multiply the error before the mean
+            mf = np.asarray(masks[s][0], orc.dt)[..., None]; mb = np.asarray(masks[s][1], orc.dt)[..., None]
+        else:
+            mf = mb = None
+        fm = orc.mean(fwd_err * mf) if mf is not None else orc.mean(fwd_err)
+        bm = orc.mean(bwd_err * mb) if mb is not None else orc.mean(bwd_err)
         img_cat = np.concatenate([tgt, src], 0)
         sm = orc.smooth_loss(depth, img_cat)
         out["fwd_mean"].append(fm); out["bwd_mean"].append(bm); out["smooth"].append(sm)
@@ -80,8 +85,8 @@ def geonet_loss(orc: Oracle, tgt_pyr, src_pyr, depth_pyr, poses, K_ms, alpha=0.8
         if want_grad:
             g = orc.dt(w_rigid * S / 2 / fwd_err.size)
             gerr = np.full(fwd_err.shape, g, orc.dt)
-            _, gy_f = orc.image_similarity_bwd(alpha, tgt_tile, fwd_warp, gerr)
-            _, gy_b = orc.image_similarity_bwd(alpha, src, bwd_warp, gerr)
+            _, gy_f = orc.image_similarity_bwd(alpha, tgt_tile, fwd_warp, gerr * mf if mf is not None else gerr)
+            _, gy_b = orc.image_similarity_bwd(alpha, src, bwd_warp, gerr * mb if mb is not None else gerr)
             gc_f, _ = orc.bilinear_sampler_bwd(src, fwd_coords, gy_f)
             gc_b, _ = orc.bilinear_sampler_bwd(tgt_tile, bwd_coords, gy_b)
             gd_f, gPf, gKi_f = orc.rigid_flow_bwd(d_fwd, Kinv_n, Pf, gc_f)

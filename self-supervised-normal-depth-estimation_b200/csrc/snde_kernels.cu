@@ -108,14 +108,22 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     SNDE_CHECK_LAUNCH();
     const size_t smem = sizeof(TileSmem);
     const bool grad = a->flags & SNDE_LOSS_GRAD, gradk = a->flags & SNDE_LOSS_GRAD_K;
-    auto launch = [&](auto kern) -> int {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SNDE_ERR_CUDA;
+    // opt in to > 48 KB dynamic shared memory once per kernel variant and device (not a stream operation; kept out of
+    // the per-call path so the call can be captured into a CUDA graph after one eager warm-up)
+    static bool attr_done[3][64] = {};
+    int devi = 0;
+    cudaGetDevice(&devi);
+    auto launch = [&](auto kern, int variant) -> int {
+        if (devi < 0 || devi >= 64 || !attr_done[variant][devi]) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SNDE_ERR_CUDA;
+            if (devi >= 0 && devi < 64) attr_done[variant][devi] = true;
+        }
         kern<<<(unsigned)tiles, TileCfg::NT, smem, st>>>(d);
         return SNDE_OK;
     };
-    if (!grad) rc = launch(loss_tile_kernel<false, false>);
-    else if (!gradk) rc = launch(loss_tile_kernel<true, false>);
-    else rc = launch(loss_tile_kernel<true, true>);
+    if (!grad) rc = launch(loss_tile_kernel<false, false>, 0);
+    else if (!gradk) rc = launch(loss_tile_kernel<true, false>, 1);
+    else rc = launch(loss_tile_kernel<true, true>, 2);
     if (rc) return rc;
     SNDE_CHECK_LAUNCH();
     loss_final_kernel<<<(B + 1 + 127) / 128, 128, 0, st>>>(B, S, ns, a->flags, a->poses, fp, (const double *)(ws + lay.gP),

@@ -1,0 +1,130 @@
+"""Drop-in names of the reference's ``models/loss_functions.py`` (image_similarity, smooth_loss,
+flow_smooth_loss) plus the north-star compositions (inverse_warp, photometric_reconstruction_loss)
+and the fully fused step loss (geonet_loss), all backed by libsnde.so.  CUDA only.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .utils_edited import compute_rigid_flow, flow_warp, _Sampler  # noqa: F401  (re-exported like the reference's import *)
+
+
+class _ImageSimilarity(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alpha, x, y):
+        xd, yd = x.detach(), y.detach()
+        ctx.save_for_backward(xd, yd)
+        ctx.alpha = float(alpha)
+        return ops.similarity_fwd(alpha, xd, yd)
+
+    @staticmethod
+    def backward(ctx, gerr):
+        x, y = ctx.saved_tensors
+        gx, gy = ops.similarity_bwd(ctx.alpha, x, y, gerr, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+        return None, gx, gy
+
+
+def image_similarity(alpha, x, y):
+    """reference models/loss_functions.py:4-6 -- alpha*DSSIM(x,y) + (1-alpha)*|x-y| on (N,h,w,3) -> (N,h,w,3)."""
+    return _ImageSimilarity.apply(float(alpha), x.float(), y.float())
+
+
+class _SmoothLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, image):
+        d = depth.detach()
+        d3 = d.reshape(d.shape[0], d.shape[1], d.shape[2])
+        ctx.save_for_backward(d3, image.detach())
+        ctx.shape = depth.shape
+        return ops.smooth_fwd(d3, image.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        d3, image = ctx.saved_tensors
+        return ops.smooth_bwd(d3, image, g).view(ctx.shape), None
+
+
+def smooth_loss(depth, image):
+    """reference models/loss_functions.py:8-24 -- depth (M,h,w,1), image (M,h,w,3) -> scalar
+    mean|dx(depth)*exp(-mean_c|dx(image)|)| + same in y.  No gradient to the image (as in the reference)."""
+    return _SmoothLoss.apply(depth.float(), image.float())
+
+
+def flow_smooth_loss(flow, img):
+    """reference models/loss_functions.py:26-32 -- mean over the two flow channels of smooth_loss.
+    flow (b,2,h,w): each channel is passed on as (b,1,h,w) exactly like the reference does."""
+    s = 0
+    for i in range(2):
+        s = s + smooth_loss(flow[:, i, :, :].unsqueeze(1), img)
+    return s / 2
+
+
+# ---- north-star compositions ----------------------------------------------------------------------
+def inverse_warp(img, depth, pose, intrinsics, reverse_pose=False, padding_mode="zeros"):
+    """img (N,h,w,3), depth (N,h,w), pose (N,6), intrinsics (N,3,3) ->
+    (warped (N,h,w,3), valid (N,h,w)); == flow_warp(img, compute_rigid_flow(pose, depth, K, reverse_pose)).
+    'zeros' = the reference sampler's semantics; 'border' is an extension (unpinned by the reference)."""
+    flow = compute_rigid_flow(pose, depth, intrinsics, reverse_pose)
+    warped = _Sampler.apply(img.float(), flow, True, padding_mode)
+    with torch.no_grad():
+        _, valid = ops.sampler_fwd(img.detach().float(), flow.detach(), True, padding_mode, True)
+    return warped, valid
+
+
+class _FusedLoss(torch.autograd.Function):
+    """loss_total (differentiable w.r.t. poses, depth_pyr, K_ms) + (loss_rigid_warp, loss_disp_smooth) for logging.
+    Gradients are produced in the same single pass as the loss and scaled by the upstream gradient here."""
+
+    @staticmethod
+    def forward(ctx, cfg, poses, K_ms, *rest):
+        ns = cfg["ns"]
+        depth_pyr = [t.detach() for t in rest[:ns]]
+        tgt_pyr, src_pyr = rest[ns:2 * ns], rest[2 * ns:3 * ns]
+        need = any(ctx.needs_input_grad)
+        want_K = ctx.needs_input_grad[2]
+        plan = ops.FusedLossPlan(tgt_pyr, src_pyr, depth_pyr, poses.detach(), K_ms.detach(), cfg["alpha"], cfg["photo_weights"],
+                                 cfg["smooth_weights"], want_grad=need, want_grad_K=want_K, padding_mode=cfg["padding_mode"],
+                                 masks=cfg["masks"], no_photo=cfg["no_photo"], no_smooth=cfg["no_smooth"])
+        plan.run()
+        ctx.plan = plan if need else None
+        out = plan.loss_out
+        ctx.mark_non_differentiable(out)
+        return out[0].clone(), out
+
+    @staticmethod
+    def backward(ctx, g, _g_all):
+        plan = ctx.plan
+        ns = plan.ns
+        gd = [t * g for t in plan.grad_depth]
+        return (None, plan.grad_poses * g if ctx.needs_input_grad[1] else None,
+                plan.grad_K * g if plan.grad_K is not None else None, *gd, *([None] * (2 * ns)))
+
+
+def geonet_loss(tgt_pyr: Sequence[torch.Tensor], src_pyr: Sequence[torch.Tensor], depth_pyr: Sequence[torch.Tensor],
+                poses: torch.Tensor, K_ms: torch.Tensor, alpha: float = 0.85, loss_weight_rigid_warp: float = 1.0,
+                loss_weight_disparity_smooth: float = 0.5, padding_mode: str = "zeros", masks=None,
+                no_photo: bool = False, no_smooth: bool = False):
+    """Everything GeoNetModel.build_rigid_warp_flow + build_losses compute (models/baseline.py:867-970,
+    1115-1161) in one fused pass.  tgt_pyr[s] (B,3,h,w), src_pyr[s] (S*B,3,h,w) source-major (any strides, e.g.
+    the reference's NHWC views permuted back), depth_pyr[s] (B*(1+S),h,w), poses (B,S,6), K_ms (B,scales,3,3).
+    Returns (loss_total, detail) with detail = [total, rigid_warp, disp_smooth, then per scale mean fwd err,
+    mean bwd err, smooth_loss]."""
+    ns = len(tgt_pyr)
+    S = poses.shape[1]
+    cfg = dict(ns=ns, alpha=float(alpha), padding_mode=padding_mode, masks=masks, no_photo=no_photo, no_smooth=no_smooth,
+               photo_weights=[loss_weight_rigid_warp * S / 2] * ns,
+               smooth_weights=[loss_weight_disparity_smooth / 2 ** s for s in range(ns)])
+    return _FusedLoss.apply(cfg, poses, K_ms, *depth_pyr, *tgt_pyr, *src_pyr)
+
+
+def photometric_reconstruction_loss(tgt_pyr, src_pyr, intrinsics_ms, depth_pyr, poses, explainability_mask=None,
+                                    alpha: float = 0.85, weight: float = 1.0, padding_mode: str = "zeros"):
+    """North-star name: the reference's loss_rigid_warp (both directions, all scales) as one scalar.
+    explainability_mask: optional list per scale of (mask_fwd, mask_bwd), each (S*B,h,w), multiplying the
+    per-pixel error before the mean (extension: the reference's PoseNet has no mask head)."""
+    total, _ = geonet_loss(tgt_pyr, src_pyr, depth_pyr, poses, intrinsics_ms, alpha, weight, 0.0, padding_mode,
+                           explainability_mask, no_smooth=True)
+    return total

@@ -1,0 +1,122 @@
+"""CPU checks of the C-ABI library: it loads, exports every symbol include/snde.h declares, its struct
+layout matches the ctypes mirror, host helpers are bit-exact, and argument validation returns the documented
+codes BEFORE any launch (no compute calls are made here -- there is no GPU in this suite)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cases import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def abi():
+    from snde_b200 import _abi, build
+    build.build()
+    return _abi
+
+
+def test_exports_every_declared_symbol(abi):
+    header = open(os.path.join(ROOT, "include", "snde.h")).read()
+    declared = set(re.findall(r"SNDE_API[^;(]*?\b(snde_\w+)\s*\(", header))
+    assert len(declared) >= 17
+    lib = C.CDLL(abi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(abi.SIGNATURES), declared ^ set(abi.SIGNATURES)
+
+
+def test_version_and_layout(abi):
+    lib = abi.lib()
+    assert lib.snde_version() == 100
+    assert lib.snde_sizeof_loss_args() == C.sizeof(abi.SndeLossArgs)
+    assert b"NULL" in lib.snde_strerror(-1) and lib.snde_strerror(0) == b"ok"
+
+
+def test_grid_table_matches_reference_bits(abi):
+    k = load_golden("kats")
+    for key in k.files:
+        if key.startswith("grid_"):
+            n = int(key.split("_")[1])
+            out = np.empty(n, np.float32)
+            assert abi.lib().snde_fill_grid_table(n, out.ctypes.data_as(abi.c_float_p)) == 0
+            assert np.array_equal(out, k[key]), n
+    assert abi.lib().snde_fill_grid_table(0, out.ctypes.data_as(abi.c_float_p)) == -2
+    assert abi.lib().snde_fill_grid_table(4, None) == -1
+
+
+def test_workspace_size_monotone(abi):
+    lib = abi.lib()
+    assert lib.snde_loss_workspace_bytes(0, 2, 4) == 0
+    a, b = lib.snde_loss_workspace_bytes(4, 2, 4), lib.snde_loss_workspace_bytes(32, 2, 4)
+    assert 0 < a < b and a % 16 == 0 and b % 16 == 0
+
+
+def test_argument_validation_without_launch(abi):
+    lib = abi.lib()
+    args = abi.SndeLossArgs()
+    assert lib.snde_loss_fwdbwd(None, None) == -1
+    assert lib.snde_loss_fwdbwd(C.byref(args), None) == -1          # poses / loss_out NULL
+    dummy = np.zeros(64, np.float32)
+    args.poses = dummy.ctypes.data; args.loss_out = dummy.ctypes.data
+    assert lib.snde_loss_fwdbwd(C.byref(args), None) == -2          # B = 0
+    args.B, args.S, args.num_scales = 1, 1, 7
+    assert lib.snde_loss_fwdbwd(C.byref(args), None) == -2          # too many scales
+    args.num_scales = 1
+    assert lib.snde_loss_fwdbwd(C.byref(args), None) == -4          # workspace missing
+    ws = np.zeros(4096, np.float64)
+    args.workspace = (ws.ctypes.data + 15) & ~15; args.workspace_bytes = 16
+    assert lib.snde_loss_fwdbwd(C.byref(args), None) == -4          # too small
+    args.workspace_bytes = 4096 * 8 - 16
+    args.alpha = 2.0
+    assert lib.snde_loss_fwdbwd(C.byref(args), None) == -5          # alpha out of range
+    args.alpha = 0.85
+    args.scale[0].h, args.scale[0].w = 1, 8
+    assert lib.snde_loss_fwdbwd(C.byref(args), None) == -2          # h < 2 (smoothness undefined)
+    args.scale[0].h = 8
+    assert lib.snde_loss_fwdbwd(C.byref(args), None) == -1          # image pointers NULL
+    # reference-signature entry points
+    z = abi.SndeMap(); zi = abi.SndeImage()
+    assert lib.snde_rigid_flow_fwd(1, 4, 4, z, None, None, None, None, None, None) == -1
+    assert lib.snde_smooth_loss_fwd(1, 1, 4, z, zi, None, None) == -1
+    m = abi.SndeMap(dummy.ctypes.data, 16, 4, 1); im = abi.SndeImage(dummy.ctypes.data, 48, 16, 4, 1)
+    assert lib.snde_smooth_loss_fwd(1, 1, 4, m, im, dummy.ctypes.data, None) == -2
+    assert lib.snde_bilinear_sampler_fwd(1, 3, 4, 4, im, 4, 4, dummy.ctypes.data, 0, None, None, 7, dummy.ctypes.data, None, None) == -5
+    assert lib.snde_image_similarity_fwd(0, 4, 4, 0.85, im, im, dummy.ctypes.data, None) == -2
+
+
+def test_num_tiles(abi):
+    """work table: class-F items (B per scale) + class-R items (S*B per scale), 60x16 inner tiles"""
+    lib = abi.lib()
+    dummy = np.zeros(64, np.float32)
+    args = abi.SndeLossArgs()
+    args.B, args.S, args.num_scales, args.alpha = 32, 2, 4, 0.85
+    for s, (h, w) in enumerate([(128, 416), (64, 208), (32, 104), (16, 52)]):
+        sc = args.scale[s]
+        sc.h, sc.w = h, w
+        for f in ("tgt", "src"):
+            getattr(sc, f).ptr = dummy.ctypes.data
+        sc.depth.ptr = dummy.ctypes.data; sc.K = dummy.ctypes.data; sc.xtab = dummy.ctypes.data; sc.ytab = dummy.ctypes.data
+    per_img = [7 * 8, 4 * 4, 2 * 2, 1 * 1]
+    assert lib.snde_loss_num_tiles(C.byref(args)) == sum(per_img) * 32 * 3
+
+
+def test_no_fallback_when_library_missing(abi, monkeypatch):
+    monkeypatch.setattr(abi, "_lib", None)
+    monkeypatch.setattr(abi, "LIB_PATH", "/nonexistent/libsnde.so")
+    with pytest.raises(abi.SndeLibraryError):
+        abi.lib()
+
+
+def test_cpu_tensors_are_rejected():
+    import torch
+    from snde_b200.loss_functions import image_similarity, smooth_loss
+    x = torch.rand(1, 8, 8, 3)
+    with pytest.raises(RuntimeError):
+        image_similarity(0.85, x, x)
+    with pytest.raises(RuntimeError):
+        smooth_loss(torch.rand(1, 8, 8, 1), x)

@@ -1,0 +1,294 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via the reference-named Python functions) against
+the CPU oracle and against the golden vectors generated from the reference.  Run with -m gpu on a B200.
+
+Tolerances (BASELINE.json north_star): forward loss and warped image 1e-5 relative, gradients 1e-4
+relative (relative L2; isolated discontinuity pixels set aside, see cases.close_except_flips)."""
+import numpy as np
+import pytest
+import torch
+
+from cases import CASES, SMALL, close_except_flips, load_golden, oracle_inputs, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def _fused(inp, want_maps=False, **kw):
+    from snde_b200 import ops
+    d = inp.to(DEV)
+    plan = ops.FusedLossPlan(d.tgt_pyr, d.src_pyr, d.depth_pyr, d.poses, d.K_ms, want_grad=True, want_grad_K=True,
+                             want_maps=want_maps, **kw)
+    plan.run()
+    torch.cuda.synchronize()
+    lo = plan.loss_out.cpu().numpy()
+    out = dict(loss_total=float(lo[0]), loss_rigid_warp=float(lo[1]), loss_disp_smooth=float(lo[2]), fwd_mean=lo[3::3],
+               bwd_mean=lo[4::3], smooth=lo[5::3], grad_depth=[g.cpu().numpy() for g in plan.grad_depth],
+               grad_poses=plan.grad_poses.cpu().numpy(), grad_K_ms=plan.grad_K.cpu().numpy())
+    if want_maps:
+        for k in ("warped_fwd", "warped_bwd", "err_fwd", "err_bwd"):
+            out[k] = [m[k].permute(0, 2, 3, 1).cpu().numpy() for m in plan.maps]
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused loss
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", SMALL)
+def test_fused_vs_oracle_and_golden_small(oracle32, name):
+    from oracle.compose import geonet_loss
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**CASES[name])
+    e = _fused(inp, want_maps=True)
+    o = geonet_loss(oracle32, **oracle_inputs(inp), keep_maps=True)
+    g = load_golden(name)
+    smooth = CASES[name]["smooth"]
+    assert abs(e["loss_total"] - o["loss_total"]) < 1e-5 * abs(o["loss_total"])
+    assert abs(e["loss_total"] - g["loss_total"]) < 1e-5 * abs(g["loss_total"])
+    assert abs(e["loss_rigid_warp"] - g["loss_rigid_warp"]) < 1e-5 * abs(g["loss_rigid_warp"])
+    assert abs(e["loss_disp_smooth"] - g["loss_disp_smooth"]) < 1e-5 * abs(g["loss_disp_smooth"])
+    wtol = 1e-5 if smooth else 1e-4      # white-noise frames: the reference's own fp32 floor is 3.4e-5
+    for s in range(inp.num_scales):
+        assert rel_l2(e["warped_fwd"][s], o["fwd_warp"][s]) < wtol
+        assert rel_l2(e["warped_bwd"][s], o["bwd_warp"][s]) < wtol
+        assert rel_l2(e["warped_fwd"][s], g[f"fwd_warp_{s}"]) < wtol
+        assert rel_l2(e["warped_bwd"][s], g[f"bwd_warp_{s}"]) < wtol
+        assert rel_l2(e["err_fwd"][s], g[f"fwd_err_{s}"]) < 10 * wtol
+        assert rel_l2(e["err_bwd"][s], g[f"bwd_err_{s}"]) < 10 * wtol
+        for ref in (o["grad_depth"][s], g[f"grad_depth_{s}"]):
+            ok, rel, frac = close_except_flips(e["grad_depth"][s], ref, max_flip_frac=2e-3)
+            assert ok, (s, rel, frac)
+    assert rel_l2(e["grad_poses"], o["grad_poses"]) < 1e-4
+    assert rel_l2(e["grad_poses"], g["grad_poses"]) < 1e-4
+    assert rel_l2(e["grad_K_ms"], o["grad_K_ms"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["config1_smooth", "config1_noise"])
+def test_fused_config1_vs_oracle_and_golden(oracle32, name):
+    """BASELINE config 1 (128x416, B=4, S=2, 4 scales)"""
+    from oracle.compose import geonet_loss
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**CASES[name])
+    e = _fused(inp)
+    o = geonet_loss(oracle32, **oracle_inputs(inp))
+    g = load_golden(name)
+    noisy = not CASES[name]["smooth"]
+    assert abs(e["loss_total"] - g["loss_total"]) < 1e-5 * abs(g["loss_total"])
+    assert abs(e["loss_total"] - o["loss_total"]) < 1e-5 * abs(o["loss_total"])
+    np.testing.assert_allclose(e["fwd_mean"], g["fwd_mean"], rtol=1e-5)
+    np.testing.assert_allclose(e["bwd_mean"], g["bwd_mean"], rtol=1e-5)
+    np.testing.assert_allclose(e["smooth"], g["smooth"], rtol=1e-5)
+    for s in range(4):
+        ok, rel, frac = close_except_flips(e["grad_depth"][s], o["grad_depth"][s], max_flip_frac=2e-3 if noisy else 1e-4)
+        assert ok, (s, rel, frac)
+        gd = e["grad_depth"][s].astype(np.float64)
+        assert abs(np.sqrt((gd ** 2).sum()) - g[f"grad_depth_{s}_l2"]) < 1e-4 * g[f"grad_depth_{s}_l2"]
+    assert rel_l2(e["grad_poses"], o["grad_poses"]) < (2e-2 if noisy else 1e-3)
+    assert rel_l2(e["grad_poses"], g["grad_poses"]) < (2e-2 if noisy else 1e-3)
+
+
+def test_fused_masks_border_and_flags(oracle32):
+    from oracle.compose import geonet_loss
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**CASES["small_smooth"])
+    rng = np.random.default_rng(5)
+    masks = []
+    for s in range(inp.num_scales):
+        _, _, h, w = inp.tgt_pyr[s].shape
+        masks.append((rng.random((inp.B * inp.S, h, w), np.float32), rng.random((inp.B * inp.S, h, w), np.float32)))
+    e = _fused(inp, masks=[(_t(a), _t(b)) for a, b in masks])
+    o = geonet_loss(oracle32, **oracle_inputs(inp), masks=masks)
+    assert abs(e["loss_total"] - o["loss_total"]) < 1e-5 * abs(o["loss_total"])
+    for s in range(inp.num_scales):
+        ok, rel, frac = close_except_flips(e["grad_depth"][s], o["grad_depth"][s], max_flip_frac=2e-3)
+        assert ok, (s, rel, frac)
+    ep, es, et = _fused(inp, no_smooth=True), _fused(inp, no_photo=True), _fused(inp)
+    assert abs(ep["loss_total"] + es["loss_total"] - et["loss_total"]) < 1e-5
+    for s in range(inp.num_scales):
+        assert rel_l2(ep["grad_depth"][s] + es["grad_depth"][s], et["grad_depth"][s]) < 1e-5
+
+
+def test_fused_strided_views_identical():
+    from snde_b200.synthetic import LossInputs, make_inputs
+    inp = make_inputs(**CASES["small_noise_large_motion"])
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    inp2 = LossInputs([nhwc(t) for t in inp.tgt_pyr], [nhwc(t) for t in inp.src_pyr], inp.depth_pyr, inp.poses, inp.K, inp.K_ms)
+    # .to(device) keeps the permuted strides
+    a, b = _fused(inp), _fused(inp2)
+    assert abs(a["loss_total"] - b["loss_total"]) < 1e-6
+    for s in range(inp.num_scales):
+        assert rel_l2(a["grad_depth"][s], b["grad_depth"][s]) < 1e-6
+
+
+def test_fused_autograd_matches_plan_and_scales_with_upstream():
+    from snde_b200.loss_functions import geonet_loss
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**CASES["small_smooth"])
+    ref = _fused(inp)
+    d = inp.to(DEV)
+    depth = [t.clone().requires_grad_(True) for t in d.depth_pyr]
+    poses = d.poses.clone().requires_grad_(True)
+    total, detail = geonet_loss(d.tgt_pyr, d.src_pyr, depth, poses, d.K_ms)
+    (3.0 * total).backward()
+    assert abs(total.item() - ref["loss_total"]) < 1e-6
+    assert abs(detail[1].item() - ref["loss_rigid_warp"]) < 1e-6
+    for s in range(inp.num_scales):
+        assert rel_l2(depth[s].grad.cpu().numpy(), 3.0 * ref["grad_depth"][s]) < 1e-6
+    assert rel_l2(poses.grad.cpu().numpy(), 3.0 * ref["grad_poses"]) < 1e-6
+    with torch.no_grad():
+        t2, _ = geonet_loss(d.tgt_pyr, d.src_pyr, d.depth_pyr, d.poses, d.K_ms)
+    assert abs(t2.item() - ref["loss_total"]) < 1e-6
+
+
+def test_fused_full_size_properties():
+    """BASELINE config 2 shape (B=32): size-independent properties instead of an oracle run.
+    (1) the loss of a batch is the mean of the losses of its halves (samples are independent);
+    (2) gradients of the halves, rescaled, tile the gradient of the batch;
+    (3) photometric term vanishes in gradient where the mask is zero."""
+    from snde_b200.synthetic import LossInputs, make_inputs
+    inp = make_inputs(B=32, S=2, H=128, W=416, num_scales=4, seed=11, smooth=True)
+    full = _fused(inp)
+    B, S = 32, 2
+    def half(lo, hi):
+        sel_t = slice(lo, hi)
+        src_idx = torch.cat([torch.arange(k * B + lo, k * B + hi) for k in range(S)])
+        dep_idx = torch.cat([torch.arange(lo, hi), B + src_idx])
+        return LossInputs([t[sel_t] for t in inp.tgt_pyr], [t[src_idx] for t in inp.src_pyr], [d[dep_idx] for d in inp.depth_pyr],
+                          inp.poses[sel_t], inp.K[sel_t], inp.K_ms[sel_t]), dep_idx
+    (ia, da), (ib, db) = half(0, 16), half(16, 32)
+    a, b = _fused(ia), _fused(ib)
+    assert abs(0.5 * (a["loss_total"] + b["loss_total"]) - full["loss_total"]) < 1e-5 * full["loss_total"]
+    for s in range(4):
+        gfull = full["grad_depth"][s]
+        assert rel_l2(0.5 * a["grad_depth"][s], gfull[da.numpy()]) < 1e-5
+        assert rel_l2(0.5 * b["grad_depth"][s], gfull[db.numpy()]) < 1e-5
+    assert rel_l2(0.5 * a["grad_poses"], full["grad_poses"][:16]) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference-signature pieces against the golden known-answer tables
+# ---------------------------------------------------------------------------------------------------
+def test_sampler_known_answers_and_grads():
+    from snde_b200.utils_edited import bilinear_sampler
+    k = load_golden("kats")
+    img = torch.arange(20, dtype=torch.float32, device=DEV).view(1, 4, 5, 1)
+    for i, y in enumerate(k["sampler_ys"]):
+        for j, x in enumerate(k["sampler_xs"]):
+            got = bilinear_sampler(img, torch.tensor([[[[x, y]]]], device=DEV)).item()
+            assert abs(got - k["sampler_tab"][i, j]) <= 1e-6, (x, y)
+    imgs = _t(k["bs_img"]).requires_grad_(True)
+    coords = _t(k["bs_coords"]).requires_grad_(True)
+    out = bilinear_sampler(imgs, coords)
+    assert np.abs(out.detach().cpu().numpy() - k["bs_out"]).max() < 1e-6
+    out.backward(_t(k["bs_gout"]))
+    assert rel_l2(coords.grad.cpu().numpy(), k["bs_gcoords"]) < 1e-5
+    assert rel_l2(imgs.grad.cpu().numpy(), k["bs_gimg"]) < 1e-5
+
+
+def test_image_similarity_and_dssim():
+    from snde_b200.loss_functions import image_similarity
+    from snde_b200.utils_edited import DSSIM
+    k = load_golden("kats")
+    x, y = _t(k["is_x"]).requires_grad_(True), _t(k["is_y"]).requires_grad_(True)
+    e = image_similarity(0.85, x, y)
+    assert np.abs(e.detach().cpu().numpy() - k["is_err"]).max() < 2e-6
+    assert np.abs(DSSIM(x.detach(), y.detach()).cpu().numpy() - k["is_dssim"]).max() < 2e-6
+    e.backward(_t(k["is_gerr"]))
+    assert rel_l2(x.grad.cpu().numpy(), k["is_gx"]) < 1e-4
+    assert rel_l2(y.grad.cpu().numpy(), k["is_gy"]) < 1e-4
+
+
+def test_smooth_loss():
+    from snde_b200.loss_functions import flow_smooth_loss, smooth_loss
+    k = load_golden("kats")
+    d = _t(k["sm_depth"]).requires_grad_(True)
+    im = _t(k["sm_img"])
+    sl = smooth_loss(d, im)
+    assert abs(sl.item() - k["sm_loss"]) < 1e-5 * abs(k["sm_loss"])
+    (2.0 * sl).backward()
+    assert rel_l2(d.grad.cpu().numpy(), 2.0 * k["sm_gdepth"]) < 1e-5
+
+
+@pytest.mark.parametrize("rev", [False, True])
+def test_compute_rigid_flow(rev):
+    from snde_b200.utils_edited import compute_rigid_flow
+    k = load_golden("kats")
+    tag = "rev" if rev else "fwd"
+    pose, depth, K = _t(k["rf_pose"]).requires_grad_(True), _t(k["rf_depth"]).requires_grad_(True), _t(k["rf_K"])
+    flow = compute_rigid_flow(pose, depth, K, rev)
+    assert np.abs(flow.detach().cpu().numpy() - k[f"rf_{tag}_flow"]).max() < 2e-4     # pixels
+    flow.backward(_t(k[f"rf_{tag}_gflow"]))
+    assert rel_l2(depth.grad.cpu().numpy(), k[f"rf_{tag}_gdepth"]) < 1e-4
+    assert rel_l2(pose.grad.cpu().numpy(), k[f"rf_{tag}_gpose"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_reference_call_sequence_matches_golden(name):
+    """The reference's own composition (models/baseline.py:895-970, 1125-1161) written with the drop-in names."""
+    from snde_b200.loss_functions import image_similarity, smooth_loss
+    from snde_b200.synthetic import make_inputs
+    from snde_b200.utils_edited import compute_rigid_flow, flow_warp
+    g = load_golden(name)
+    inp = make_inputs(**CASES[name]).to(DEV)
+    B, S, ns = inp.B, inp.S, inp.num_scales
+    depth = [d.clone().requires_grad_(True) for d in inp.depth_pyr]
+    poses = inp.poses.clone().requires_grad_(True)
+    tgt_pyr = [t.permute(0, 2, 3, 1) for t in inp.tgt_pyr]
+    src_pyr = [t.permute(0, 2, 3, 1) for t in inp.src_pyr]
+    tgt_tile = [t.repeat(S, 1, 1, 1) for t in tgt_pyr]
+    rigid, smooth = 0, 0
+    for s in range(ns):
+        ff = torch.cat([compute_rigid_flow(poses[:, k, :], depth[s][:B], inp.K_ms[:, s], False) for k in range(S)], 0)
+        fb = torch.cat([compute_rigid_flow(poses[:, k, :], depth[s][B * (k + 1):B * (k + 2)], inp.K_ms[:, s], True) for k in range(S)], 0)
+        fw, bw = flow_warp(src_pyr[s], ff), flow_warp(tgt_tile[s], fb)
+        assert rel_l2(fw.detach().cpu().numpy(), g[f"fwd_warp_{s}"]) < (1e-5 if CASES[name]["smooth"] else 1e-4)
+        fe, be = image_similarity(0.85, tgt_tile[s], fw), image_similarity(0.85, src_pyr[s], bw)
+        rigid = rigid + 1.0 * S / 2 * (fe.mean() + be.mean())
+        smooth = smooth + 0.5 / 2 ** s * smooth_loss(depth[s].unsqueeze(3), torch.cat((tgt_pyr[s], src_pyr[s]), 0))
+    total = rigid + smooth
+    total.backward()
+    assert abs(total.item() - g["loss_total"]) < 1e-5 * abs(g["loss_total"])
+    for s in range(ns):
+        ok, rel, frac = close_except_flips(depth[s].grad.cpu().numpy(), g[f"grad_depth_{s}"], max_flip_frac=2e-3)
+        assert ok, (s, rel, frac)
+    assert rel_l2(poses.grad.cpu().numpy(), g["grad_poses"]) < 1e-4
+
+
+def test_inverse_warp_and_border_mode():
+    import torch.nn.functional as F
+    from snde_b200.loss_functions import inverse_warp
+    from snde_b200.synthetic import make_inputs
+    from snde_b200.utils_edited import compute_rigid_flow, flow_warp, meshgrid
+    inp = make_inputs(B=2, S=1, H=24, W=40, num_scales=1, seed=9, smooth=True, motion="large").to(DEV)
+    img = inp.src_pyr[0].permute(0, 2, 3, 1)
+    depth, pose, K = inp.depth_pyr[0][:2], inp.poses[:, 0], inp.K
+    warped, valid = inverse_warp(img, depth, pose, K)
+    flow = compute_rigid_flow(pose, depth, K, False)
+    assert torch.equal(warped, flow_warp(img, flow))
+    coords = meshgrid(2, 24, 40, False, device=img.device).permute(0, 2, 3, 1) + flow
+    x, y = coords[..., 0], coords[..., 1]
+    assert torch.equal(valid, ((x >= 0) & (x < 39) & (y >= 0) & (y < 23)).float())
+    assert (warped[valid == 0].abs() < 1e-6).all()
+    # border mode == grid_sample(padding_mode='border', align_corners=True)
+    wb, vb = inverse_warp(img, depth, pose, K, padding_mode="border")
+    grid = torch.stack([2 * x / 39 - 1, 2 * y / 23 - 1], -1)
+    ref = F.grid_sample(inp.src_pyr[0], grid, mode="bilinear", padding_mode="border", align_corners=True).permute(0, 2, 3, 1)
+    assert (wb - ref).abs().max() < 2e-5
+    assert torch.equal(vb, ((x >= 0) & (x <= 39) & (y >= 0) & (y <= 23)).float())
+
+
+def test_large_batch_indices_beyond_2_pow_24():
+    """N*h*w > 2^24: the reference gathers wrong pixels here (float32 flat indices); integers do not."""
+    from snde_b200.utils_edited import bilinear_sampler
+    g = torch.Generator().manual_seed(3)
+    N, h, w = 9, 1024, 2048
+    img = torch.rand(N, h, w, 1, generator=g).to(DEV)
+    coords = torch.rand(1, 64, 64, 2, generator=g) * torch.tensor([w - 2.0, h - 2.0])
+    coords = coords.to(DEV)
+    full = bilinear_sampler(img, coords.expand(N, -1, -1, -1).contiguous())
+    last = bilinear_sampler(img[8:9].contiguous(), coords)
+    assert torch.equal(full[8:9], last)

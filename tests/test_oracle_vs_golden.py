@@ -118,3 +118,23 @@ def test_loss_path_config1(oracle32, name):
         proj = (gd * rng.standard_normal(gd.shape)).sum()
         assert abs(proj - g[f"grad_depth_{s}_proj"]) < (8e-3 if noisy else 5e-4) * g[f"grad_depth_{s}_l2"]
     assert rel_l2(o["grad_poses"], g["grad_poses"]) < (2e-2 if noisy else 1e-4)
+
+
+@pytest.mark.parametrize("name", ["small_smooth", "config1_noise"])
+def test_torch_port_matches_golden(name):
+    """oracle/torch_port.py (the CPU-baseline restatement in ATen ops) reproduces the reference's numbers."""
+    import torch
+    from oracle import torch_port
+    from snde_b200.synthetic import make_inputs
+    g = load_golden(name)
+    inp = make_inputs(**CASES[name])
+    depth = [d.clone().requires_grad_(True) for d in inp.depth_pyr]
+    poses = inp.poses.clone().requires_grad_(True)
+    total, rigid, smooth = torch_port.loss_path(inp.tgt_pyr, inp.src_pyr, depth, poses, inp.K_ms)
+    total.backward()
+    assert abs(total.item() - g["loss_total"]) < 2e-6 * abs(g["loss_total"])
+    assert abs(rigid.item() - g["loss_rigid_warp"]) < 2e-6 * abs(g["loss_rigid_warp"])
+    assert rel_l2(poses.grad.numpy(), g["grad_poses"]) < (2e-2 if name == "config1_noise" else 1e-4)
+    for s in range(inp.num_scales):
+        gd = depth[s].grad.numpy().astype(np.float64)
+        assert abs(np.sqrt((gd ** 2).sum()) - g[f"grad_depth_{s}_l2"]) < 1e-4 * g[f"grad_depth_{s}_l2"]

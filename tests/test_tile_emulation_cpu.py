@@ -1,0 +1,107 @@
+"""The fused loss TILE PROGRAM (csrc/snde_tile.cuh), compiled for the host by tests/host_emul and run on
+numpy buffers, against the oracle.  This checks the device code's logic (work table, halos, zero padding,
+gradient ownership, finalize) in the GPU-less container; the GPU tests then check the real kernels."""
+import numpy as np
+import pytest
+
+import emul
+from cases import CASES, SMALL, load_golden, oracle_inputs, rel_l2
+
+
+def _nhwc(a):
+    return a.transpose(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_emulated_tiles_match_oracle(oracle32, name):
+    from oracle.compose import geonet_loss
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**CASES[name])
+    e = emul.run_loss(inp, flags=3, want_maps=True)
+    o = geonet_loss(oracle32, **oracle_inputs(inp), keep_maps=True)
+    assert abs(e["loss_total"] - o["loss_total"]) < 1e-6 * abs(o["loss_total"])
+    for s in range(inp.num_scales):
+        assert not np.isnan(e["grad_depth"][s]).any()
+        assert rel_l2(_nhwc(e["warped_fwd"][s]), o["fwd_warp"][s]) < 1e-5
+        assert rel_l2(_nhwc(e["warped_bwd"][s]), o["bwd_warp"][s]) < 1e-5
+        assert rel_l2(_nhwc(e["err_fwd"][s]), o["fwd_err"][s]) < 1e-5
+        assert rel_l2(_nhwc(e["err_bwd"][s]), o["bwd_err"][s]) < 1e-5
+        assert rel_l2(e["grad_depth"][s], o["grad_depth"][s]) < 1e-4
+        np.testing.assert_allclose(e["smooth"][s], o["smooth"][s], rtol=1e-6)
+    assert rel_l2(e["grad_poses"], o["grad_poses"]) < 1e-4
+    assert rel_l2(e["grad_K_ms"], o["grad_K_ms"]) < 1e-4
+
+
+def test_emulated_tiles_match_reference_golden_config1():
+    """BASELINE config 1 against the reference's own numbers (tests/golden/config1_smooth.npz)."""
+    from snde_b200.synthetic import make_inputs
+    g = load_golden("config1_smooth")
+    inp = make_inputs(**CASES["config1_smooth"])
+    e = emul.run_loss(inp, flags=1)
+    assert abs(e["loss_total"] - g["loss_total"]) < 1e-5 * abs(g["loss_total"])
+    np.testing.assert_allclose(e["fwd_mean"], g["fwd_mean"], rtol=1e-5)
+    np.testing.assert_allclose(e["bwd_mean"], g["bwd_mean"], rtol=1e-5)
+    np.testing.assert_allclose(e["smooth"], g["smooth"], rtol=1e-5)
+    for s in range(4):
+        gd = e["grad_depth"][s].astype(np.float64)
+        assert abs(np.sqrt((gd ** 2).sum()) - g[f"grad_depth_{s}_l2"]) < 1e-4 * g[f"grad_depth_{s}_l2"]
+        rng = np.random.default_rng(1234 + s)
+        # position-sensitive checksum; a few discontinuity pixels (see cases.close_except_flips) move it by ~1e-3
+        assert abs((gd * rng.standard_normal(gd.shape)).sum() - g[f"grad_depth_{s}_proj"]) < 5e-3 * g[f"grad_depth_{s}_l2"]
+    assert rel_l2(e["grad_poses"], g["grad_poses"]) < 1e-3     # sums over the same few flipped pixels (measured 3e-4)
+
+
+def test_emulated_tiles_match_oracle_config1(oracle32):
+    """config 1 shape, every depth-gradient pixel against the oracle (discontinuity pixels set aside)"""
+    from oracle.compose import geonet_loss
+    from snde_b200.synthetic import make_inputs
+    from cases import close_except_flips
+    inp = make_inputs(**CASES["config1_smooth"])
+    e = emul.run_loss(inp, flags=1)
+    o = geonet_loss(oracle32, **oracle_inputs(inp))
+    assert abs(e["loss_total"] - o["loss_total"]) < 1e-6 * abs(o["loss_total"])
+    for s in range(4):
+        ok, rel, frac = close_except_flips(e["grad_depth"][s], o["grad_depth"][s])
+        assert ok, (s, rel, frac)
+    assert rel_l2(e["grad_poses"], o["grad_poses"]) < 1e-3
+
+
+def test_emulated_masks_and_flags(oracle32):
+    from oracle.compose import geonet_loss
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**CASES["small_smooth"])
+    rng = np.random.default_rng(5)
+    masks = []
+    for s in range(inp.num_scales):
+        _, _, h, w = inp.tgt_pyr[s].shape
+        masks.append((rng.random((inp.B * inp.S, h, w), np.float32), rng.random((inp.B * inp.S, h, w), np.float32)))
+    e = emul.run_loss(inp, flags=1, masks=masks)
+    o = geonet_loss(oracle32, **oracle_inputs(inp), masks=masks)
+    assert abs(e["loss_total"] - o["loss_total"]) < 1e-6 * abs(o["loss_total"])
+    for s in range(inp.num_scales):
+        assert rel_l2(e["grad_depth"][s], o["grad_depth"][s]) < 1e-4
+    assert rel_l2(e["grad_poses"], o["grad_poses"]) < 1e-4
+    # photometric only / smoothness only add up to the total
+    ep = emul.run_loss(inp, flags=1 | 8)
+    es = emul.run_loss(inp, flags=1 | 4)
+    et = emul.run_loss(inp, flags=1)
+    assert abs(ep["loss_total"] + es["loss_total"] - et["loss_total"]) < 1e-6
+    for s in range(inp.num_scales):
+        assert rel_l2(ep["grad_depth"][s] + es["grad_depth"][s], et["grad_depth"][s]) < 1e-6
+    # forward-only mode leaves the gradient buffers untouched and gives the same loss
+    ef = emul.run_loss(inp, flags=0)
+    assert abs(ef["loss_total"] - et["loss_total"]) < 1e-7
+    assert np.isnan(ef["grad_depth"][0]).all()
+
+
+def test_emulated_strided_views():
+    """NHWC memory handed over as permuted views (the reference's layout) gives identical results"""
+    import torch
+    from snde_b200.synthetic import make_inputs, LossInputs
+    inp = make_inputs(**CASES["small_noise_large_motion"])
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    inp2 = LossInputs([nhwc(t) for t in inp.tgt_pyr], [nhwc(t) for t in inp.src_pyr], inp.depth_pyr, inp.poses, inp.K, inp.K_ms)
+    a, b = emul.run_loss(inp, flags=1), emul.run_loss(inp2, flags=1)
+    assert a["loss_total"] == b["loss_total"]
+    for s in range(inp.num_scales):
+        assert np.array_equal(a["grad_depth"][s], b["grad_depth"][s])
