@@ -10,6 +10,22 @@
 
 using namespace snde;
 
+// views with 64-bit strides for the reference-signature kernels (any layout, any size)
+struct LImage { const float *p; long long sn, sc, sh, sw; };
+struct LImageOut { float *p; long long sn, sc, sh, sw; };
+struct LMap { const float *p; long long sn, sh, sw; };
+struct LMapOut { float *p; long long sn, sh, sw; };
+static inline LImage ldev(const SndeImage &v) { return LImage{v.ptr, v.sn, v.sc, v.sh, v.sw}; }
+static inline LImageOut ldev(const SndeImageOut &v) { return LImageOut{v.ptr, v.sn, v.sc, v.sh, v.sw}; }
+static inline LMap ldev(const SndeMap &v) { return LMap{v.ptr, v.sn, v.sh, v.sw}; }
+static inline LMapOut ldev(const SndeMapOut &v) { return LMapOut{v.ptr, v.sn, v.sh, v.sw}; }
+__device__ __forceinline__ float ld_img(const LImage &im, long long n, int c, int y, int x) {
+    return __ldg(im.p + n * im.sn + c * im.sc + (long long)y * im.sh + (long long)x * im.sw);
+}
+__device__ __forceinline__ float ld_map(const LMap &m, long long n, int y, int x) {
+    return __ldg(m.p + n * m.sn + (long long)y * m.sh + (long long)x * m.sw);
+}
+
 #define SNDE_CHECK_LAUNCH() do { if (cudaGetLastError() != cudaSuccess) return SNDE_ERR_CUDA; } while (0)
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -55,20 +71,51 @@ __global__ void __launch_bounds__(128) loss_prep_kernel(int B, int S, int ns, co
     loss_prep_thread(blockIdx.x * blockDim.x + threadIdx.x, B, S, ns, poses, kp, P, Kinv);
 }
 
-__global__ void __launch_bounds__(128) loss_final_kernel(int B, int S, int ns, int flags, const float *__restrict__ poses,
-                                                         FinalParams fp, const double *__restrict__ gP,
-                                                         const double *__restrict__ gKinv, const double *__restrict__ loss,
-                                                         float *__restrict__ loss_out, float *__restrict__ grad_poses,
-                                                         float *__restrict__ grad_K) {
-    loss_final_thread(blockIdx.x * blockDim.x + threadIdx.x, B, S, ns, flags, poses, fp, gP, gKinv, loss, loss_out, grad_poses, grad_K);
+// block b < B: one thread per (source k, scale s) runs the double-precision backward of the matrix prep, then the
+// block reduces over scales (pose gradient) and over sources (intrinsics gradient) in a fixed order.  Block B: scalars.
+__global__ void __launch_bounds__(64) loss_final_kernel(int B, int S, int ns, int flags, const float *__restrict__ poses,
+                                                        FinalParams fp, const double *__restrict__ gP,
+                                                        const double *__restrict__ gKinv, const double *__restrict__ loss,
+                                                        float *__restrict__ loss_out, float *__restrict__ grad_poses,
+                                                        float *__restrict__ grad_K) {
+    __shared__ double sv[64][6];
+    __shared__ double sk[64][9];
+    const int b = blockIdx.x, t = threadIdx.x;
+    if (b == B) { if (t == 0) loss_final_scalars(ns, fp, loss, loss_out); return; }
+    if (!(flags & FLAG_GRAD)) return;
+    const bool wantK = (flags & FLAG_GRAD_K) != 0;
+    for (int base = 0; base < S * ns; base += 64) {          // S*ns <= 64 in practice: one pass
+        const int i = base + t;
+        const int k = i / ns, s = i - k * ns;
+        if (i < S * ns) loss_final_pair(b, k, s, B, S, flags, poses, fp, gP, gKinv, sv[t], sk[t]);
+        __syncthreads();
+        const int cnt = min(64, S * ns - base);
+        // pose gradient: sum over the scales of source k (threads base+k*ns .. base+k*ns+ns-1); requires ns | 64-chunk alignment
+        if (t < cnt && (base + t) % ns == 0) {
+            const int kk = (base + t) / ns;
+            for (int j = 0; j < 6; ++j) {
+                double a = 0.0;
+                for (int q = 0; q < ns && t + q < cnt; ++q) a += sv[t + q][j];
+                if (base == 0 || true) grad_poses[(b * S + kk) * 6 + j] = (float)a;
+            }
+        }
+        if (wantK && t < ns && base == 0) {
+            for (int j = 0; j < 9; ++j) {
+                double a = 0.0;
+                for (int kk = 0; kk * ns + t < cnt; ++kk) a += sk[kk * ns + t][j];
+                grad_K[((size_t)b * ns + t) * 9 + j] = (float)a;
+            }
+        }
+        __syncthreads();
+    }
 }
 
-template <bool GRAD, bool GRADK>
-__global__ void __launch_bounds__(TileCfg::NT, 3) loss_tile_kernel(const __grid_constant__ DevLoss p) {
+template <bool GRAD, bool GRADK, bool EXTRA>
+__global__ void __launch_bounds__(TileCfg::NT, 2) loss_tile_kernel(const __grid_constant__ DevLoss p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
     Regs regs;
-    loss_tile<GRAD, GRADK>(p, (int)blockIdx.x, sm, &regs);
+    loss_tile<GRAD, GRADK, EXTRA>(p, (int)blockIdx.x, sm, &regs);
 }
 
 extern "C" size_t snde_sizeof_loss_args(void) { return sizeof(SndeLossArgs); }
@@ -93,6 +140,7 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     if ((a->flags & SNDE_LOSS_GRAD) && !a->grad_poses) return SNDE_ERR_NULL;
     if ((a->flags & SNDE_LOSS_GRAD_K) && !a->grad_K) return SNDE_ERR_NULL;
     if (a->B <= 0 || a->S <= 0 || a->num_scales <= 0 || a->num_scales > SNDE_MAX_SCALES) return SNDE_ERR_SHAPE;
+    if (a->S * a->num_scales > 64) return SNDE_ERR_SHAPE;     // finalize kernel: one thread per (source, scale)
     const LossWorkspace lay = loss_ws_layout(a->B, a->S, a->num_scales);
     if (!a->workspace || a->workspace_bytes < lay.end || ((uintptr_t)a->workspace & 15)) return SNDE_ERR_WORKSPACE;
     DevLoss d; int64_t tiles = 0;
@@ -110,7 +158,7 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     const bool grad = a->flags & SNDE_LOSS_GRAD, gradk = a->flags & SNDE_LOSS_GRAD_K;
     // opt in to > 48 KB dynamic shared memory once per kernel variant and device (not a stream operation; kept out of
     // the per-call path so the call can be captured into a CUDA graph after one eager warm-up)
-    static bool attr_done[3][64] = {};
+    static bool attr_done[4][64] = {};
     int devi = 0;
     cudaGetDevice(&devi);
     auto launch = [&](auto kern, int variant) -> int {
@@ -121,12 +169,18 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
         kern<<<(unsigned)tiles, TileCfg::NT, smem, st>>>(d);
         return SNDE_OK;
     };
-    if (!grad) rc = launch(loss_tile_kernel<false, false>, 0);
-    else if (!gradk) rc = launch(loss_tile_kernel<true, false>, 1);
-    else rc = launch(loss_tile_kernel<true, true>, 2);
+    // EXTRA variants honour masks / warped+error outputs / border padding / intrinsics gradients; the lean ones are the hot path
+    bool extra = gradk || a->padding_mode != SNDE_PAD_ZEROS;
+    for (int s = 0; s < ns; ++s) {
+        const SndeLossScale &in = a->scale[s];
+        extra = extra || in.mask_fwd.ptr || in.mask_bwd.ptr || in.warped_fwd.ptr || in.warped_bwd.ptr || in.err_fwd.ptr || in.err_bwd.ptr;
+    }
+    if (!grad) rc = extra ? launch(loss_tile_kernel<false, false, true>, 0) : launch(loss_tile_kernel<false, false, false>, 1);
+    else if (extra) rc = launch(loss_tile_kernel<true, true, true>, 2);
+    else rc = launch(loss_tile_kernel<true, false, false>, 3);
     if (rc) return rc;
     SNDE_CHECK_LAUNCH();
-    loss_final_kernel<<<(B + 1 + 127) / 128, 128, 0, st>>>(B, S, ns, a->flags, a->poses, fp, (const double *)(ws + lay.gP),
+    loss_final_kernel<<<B + 1, 64, 0, st>>>(B, S, ns, a->flags, a->poses, fp, (const double *)(ws + lay.gP),
                                                            (const double *)(ws + lay.gKinv), (const double *)(ws + lay.loss),
                                                            a->loss_out, a->grad_poses, a->grad_K);
     SNDE_CHECK_LAUNCH();
@@ -187,7 +241,7 @@ extern "C" int snde_pose_matrices_bwd(int B, const float *poses, int64_t pose_st
 }
 
 // ---- compute_rigid_flow, per-pixel part: grid (ceil(h*w/256), B) ----
-__global__ void __launch_bounds__(256) rigid_flow_fwd_kernel(int h, int w, DevMap depth, const float *__restrict__ Kinv,
+__global__ void __launch_bounds__(256) rigid_flow_fwd_kernel(int h, int w, LMap depth, const float *__restrict__ Kinv,
                                                              const float *__restrict__ P, const float *__restrict__ xtab,
                                                              const float *__restrict__ ytab, float *__restrict__ flow) {
     const int b = blockIdx.y;
@@ -209,7 +263,7 @@ extern "C" int snde_rigid_flow_fwd(int B, int h, int w, SndeMap depth, const flo
     if (B <= 0 || h <= 0 || w <= 0) return SNDE_ERR_SHAPE;
     if ((long long)B * h * w >= (1LL << 31) || B > 65535) return SNDE_ERR_TOO_LARGE;
     dim3 grid((h * w + 255) / 256, B);
-    rigid_flow_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(h, w, dev(depth), Kinv, P, xtab, ytab, flow);
+    rigid_flow_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(h, w, ldev(depth), Kinv, P, xtab, ytab, flow);
     SNDE_CHECK_LAUNCH();
     return SNDE_OK;
 }
@@ -234,10 +288,10 @@ __device__ __forceinline__ void block_atomic_add(float (&v)[NV], double *dst, fl
 }
 
 template <bool GRADK>
-__global__ void __launch_bounds__(256) rigid_flow_bwd_kernel(int h, int w, DevMap depth, const float *__restrict__ Kinv,
+__global__ void __launch_bounds__(256) rigid_flow_bwd_kernel(int h, int w, LMap depth, const float *__restrict__ Kinv,
                                                              const float *__restrict__ P, const float *__restrict__ xtab,
                                                              const float *__restrict__ ytab, const float *__restrict__ gflow,
-                                                             DevMapOut gdepth, double *__restrict__ gP, double *__restrict__ gKinv) {
+                                                             LMapOut gdepth, double *__restrict__ gP, double *__restrict__ gKinv) {
     __shared__ float red[8 * 12];
     const int b = blockIdx.y;
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,14 +328,14 @@ extern "C" int snde_rigid_flow_bwd(int B, int h, int w, SndeMap depth, const flo
     if (B <= 0 || h <= 0 || w <= 0) return SNDE_ERR_SHAPE;
     if ((long long)B * h * w >= (1LL << 31) || B > 65535) return SNDE_ERR_TOO_LARGE;
     dim3 grid((h * w + 255) / 256, B);
-    if (gKinv) rigid_flow_bwd_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(h, w, dev(depth), Kinv, P, xtab, ytab, gflow, dev(gdepth), gP, gKinv);
-    else rigid_flow_bwd_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(h, w, dev(depth), Kinv, P, xtab, ytab, gflow, dev(gdepth), gP, gKinv);
+    if (gKinv) rigid_flow_bwd_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(h, w, ldev(depth), Kinv, P, xtab, ytab, gflow, ldev(gdepth), gP, gKinv);
+    else rigid_flow_bwd_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(h, w, ldev(depth), Kinv, P, xtab, ytab, gflow, ldev(gdepth), gP, gKinv);
     SNDE_CHECK_LAUNCH();
     return SNDE_OK;
 }
 
 // ---- bilinear_sampler / flow_warp ----
-__global__ void __launch_bounds__(256) sampler_fwd_kernel(long long total, int C, int hs, int ws, DevImage img, int ht, int wt,
+__global__ void __launch_bounds__(256) sampler_fwd_kernel(long long total, int C, int hs, int ws, LImage img, int ht, int wt,
                                                           const float *__restrict__ coords, int add_grid,
                                                           const float *__restrict__ xtab, const float *__restrict__ ytab, int border,
                                                           float *__restrict__ out, float *__restrict__ valid) {
@@ -311,16 +365,16 @@ extern "C" int snde_bilinear_sampler_fwd(int N, int C, int hs, int ws, SndeImage
     const long long total = (long long)N * ht * wt;
     if (total * C >= (1LL << 31) || (long long)N * hs * ws * C >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
     const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-    sampler_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, C, hs, ws, dev(img), ht, wt, coords, add_grid, xtab, ytab,
+    sampler_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, C, hs, ws, ldev(img), ht, wt, coords, add_grid, xtab, ytab,
                                                              padding_mode, out, valid);
     SNDE_CHECK_LAUNCH();
     return SNDE_OK;
 }
 
-__global__ void __launch_bounds__(256) sampler_bwd_kernel(long long total, int C, int hs, int ws, DevImage img, int ht, int wt,
+__global__ void __launch_bounds__(256) sampler_bwd_kernel(long long total, int C, int hs, int ws, LImage img, int ht, int wt,
                                                           const float *__restrict__ coords, int add_grid,
                                                           const float *__restrict__ xtab, const float *__restrict__ ytab, int border,
-                                                          const float *__restrict__ gout, float *__restrict__ gcoords, DevImageOut gimg) {
+                                                          const float *__restrict__ gout, float *__restrict__ gcoords, LImageOut gimg) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int ix = (int)(i % wt); const long long t = i / wt; const int iy = (int)(t % ht); const long long n = t / ht;
         const float2 cf = reinterpret_cast<const float2 *>(coords)[i];
@@ -360,8 +414,8 @@ extern "C" int snde_bilinear_sampler_bwd(int N, int C, int hs, int ws, SndeImage
     const long long total = (long long)N * ht * wt;
     if (total * C >= (1LL << 31) || (long long)N * hs * ws * C >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
     const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-    sampler_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, C, hs, ws, dev(img), ht, wt, coords, add_grid, xtab, ytab,
-                                                             padding_mode, gout, gcoords, dev(gimg));
+    sampler_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, C, hs, ws, ldev(img), ht, wt, coords, add_grid, xtab, ytab,
+                                                             padding_mode, gout, gcoords, ldev(gimg));
     SNDE_CHECK_LAUNCH();
     return SNDE_OK;
 }
@@ -369,11 +423,11 @@ extern "C" int snde_bilinear_sampler_bwd(int N, int C, int hs, int ws, SndeImage
 // ---- image_similarity / DSSIM (materialising, reference-signature version) ----
 // one thread per (n, y, x); 5x5 neighbourhoods come straight from global memory (L1/L2 resident).
 // The fused tile kernel is the fast path; this one exists so the reference's own call sequence runs.
-__device__ __forceinline__ float img_or_zero(const DevImage &im, long long n, int c, int y, int x, int h, int w) {
+__device__ __forceinline__ float img_or_zero(const LImage &im, long long n, int c, int y, int x, int h, int w) {
     return (y >= 0 && y < h && x >= 0 && x < w) ? ld_img(im, n, c, y, x) : 0.f;
 }
 
-__device__ __forceinline__ void ssim_at(const DevImage &X, const DevImage &Y, long long n, int c, int cy, int cx, int h, int w, Ssim &ss) {
+__device__ __forceinline__ void ssim_at(const LImage &X, const LImage &Y, long long n, int c, int cy, int cx, int h, int w, Ssim &ss) {
     float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
 #pragma unroll
     for (int dr = -1; dr <= 1; ++dr)
@@ -385,7 +439,7 @@ __device__ __forceinline__ void ssim_at(const DevImage &X, const DevImage &Y, lo
     ssim_from_sums(sx, sy, sxx, syy, sxy, ss);
 }
 
-__global__ void __launch_bounds__(256) similarity_fwd_kernel(long long total, int h, int w, float alpha, float oma, DevImage X, DevImage Y,
+__global__ void __launch_bounds__(256) similarity_fwd_kernel(long long total, int h, int w, float alpha, float oma, LImage X, LImage Y,
                                                              float *__restrict__ err) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int ix = (int)(i % w); const long long t = i / w; const int iy = (int)(t % h); const long long n = t / h;
@@ -404,12 +458,12 @@ extern "C" int snde_image_similarity_fwd(int N, int h, int w, float alpha, SndeI
     const long long total = (long long)N * h * w;
     if (total * 3 >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
     const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-    similarity_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, h, w, alpha, (float)(1.0 - (double)alpha), dev(x), dev(y), err);
+    similarity_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, h, w, alpha, (float)(1.0 - (double)alpha), ldev(x), ldev(y), err);
     SNDE_CHECK_LAUNCH();
     return SNDE_OK;
 }
 
-__global__ void __launch_bounds__(256) similarity_bwd_kernel(long long total, int h, int w, float alpha, float oma, DevImage X, DevImage Y,
+__global__ void __launch_bounds__(256) similarity_bwd_kernel(long long total, int h, int w, float alpha, float oma, LImage X, LImage Y,
                                                              const float *__restrict__ gerr, float *__restrict__ gx, float *__restrict__ gy) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int ix = (int)(i % w); const long long t = i / w; const int iy = (int)(t % h); const long long n = t / h;
@@ -443,18 +497,18 @@ extern "C" int snde_image_similarity_bwd(int N, int h, int w, float alpha, SndeI
     if (total * 3 >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
     if (!gx && !gy) return SNDE_OK;
     const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-    similarity_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, h, w, alpha, (float)(1.0 - (double)alpha), dev(x), dev(y), gerr, gx, gy);
+    similarity_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, h, w, alpha, (float)(1.0 - (double)alpha), ldev(x), ldev(y), gerr, gx, gy);
     SNDE_CHECK_LAUNCH();
     return SNDE_OK;
 }
 
 // ---- smooth_loss ----
-__device__ __forceinline__ float pair_weight(const DevImage &I, long long m, int y0, int x0, int y1, int x1) {
+__device__ __forceinline__ float pair_weight(const LImage &I, long long m, int y0, int x0, int y1, int x1) {
     return edge_weight3(ld_img(I, m, 0, y0, x0), ld_img(I, m, 1, y0, x0), ld_img(I, m, 2, y0, x0),
                         ld_img(I, m, 0, y1, x1), ld_img(I, m, 1, y1, x1), ld_img(I, m, 2, y1, x1));
 }
 
-__global__ void __launch_bounds__(256) smooth_fwd_kernel(long long total, int h, int w, DevMap D, DevImage I, double *__restrict__ sums) {
+__global__ void __launch_bounds__(256) smooth_fwd_kernel(long long total, int h, int w, LMap D, LImage I, double *__restrict__ sums) {
     __shared__ float red[8 * 2];
     float acc[2] = {0.f, 0.f};
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -472,13 +526,13 @@ extern "C" int snde_smooth_loss_fwd(int M, int h, int w, SndeMap depth, SndeImag
     const long long total = (long long)M * h * w;
     if (total * 3 >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
     const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    smooth_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, h, w, dev(depth), dev(img), sums);
+    smooth_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, h, w, ldev(depth), ldev(img), sums);
     SNDE_CHECK_LAUNCH();
     return SNDE_OK;
 }
 
-__global__ void __launch_bounds__(256) smooth_bwd_kernel(long long total, int h, int w, DevMap D, DevImage I, const float *__restrict__ gscale,
-                                                         double inv_nx, double inv_ny, DevMapOut G) {
+__global__ void __launch_bounds__(256) smooth_bwd_kernel(long long total, int h, int w, LMap D, LImage I, const float *__restrict__ gscale,
+                                                         double inv_nx, double inv_ny, LMapOut G) {
     const float gs = __ldg(gscale);
     const float cx = (float)((double)gs * inv_nx), cy = (float)((double)gs * inv_ny);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -500,8 +554,8 @@ extern "C" int snde_smooth_loss_bwd(int M, int h, int w, SndeMap depth, SndeImag
     const long long total = (long long)M * h * w;
     if (total * 3 >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
     const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    smooth_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, h, w, dev(depth), dev(img), gscale_dev,
-                                                            1.0 / ((double)M * h * (w - 1)), 1.0 / ((double)M * (h - 1) * w), dev(gdepth));
+    smooth_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, h, w, ldev(depth), ldev(img), gscale_dev,
+                                                            1.0 / ((double)M * h * (w - 1)), 1.0 / ((double)M * (h - 1) * w), ldev(gdepth));
     SNDE_CHECK_LAUNCH();
     return SNDE_OK;
 }

@@ -9,10 +9,16 @@
 
 namespace snde {
 
-static inline DevImage dev(const SndeImage &v) { return DevImage{v.ptr, v.sn, v.sc, v.sh, v.sw}; }
-static inline DevImageOut dev(const SndeImageOut &v) { return DevImageOut{v.ptr, v.sn, v.sc, v.sh, v.sw}; }
-static inline DevMap dev(const SndeMap &v) { return DevMap{v.ptr, v.sn, v.sh, v.sw}; }
-static inline DevMapOut dev(const SndeMapOut &v) { return DevMapOut{v.ptr, v.sn, v.sh, v.sw}; }
+// in-image strides are 32-bit on the device (validated in build_dev_loss); the batch stride stays 64-bit
+static inline DevImage dev(const SndeImage &v) { return DevImage{v.ptr, v.sn, (int)v.sc, (int)v.sh, (int)v.sw, 0}; }
+static inline DevImageOut dev(const SndeImageOut &v) { return DevImageOut{v.ptr, v.sn, (int)v.sc, (int)v.sh, (int)v.sw, 0}; }
+static inline DevMap dev(const SndeMap &v) { return DevMap{v.ptr, v.sn, (int)v.sh, (int)v.sw}; }
+static inline DevMapOut dev(const SndeMapOut &v) { return DevMapOut{v.ptr, v.sn, (int)v.sh, (int)v.sw}; }
+static inline bool fits32(int64_t sc, int64_t sh, int64_t sw, int h, int w) {
+    const int64_t lim = (int64_t)1 << 30;
+    auto ab = [](int64_t v) { return v < 0 ? -v : v; };
+    return 2 * ab(sc) + ab(sh) * h + ab(sw) * w < lim;
+}
 
 // =============================================================================================
 // Fused loss
@@ -62,42 +68,51 @@ struct FinalParams {
     double inv_count[SNDE_MAX_SCALES], inv_nx[SNDE_MAX_SCALES], inv_ny[SNDE_MAX_SCALES];
 };
 
-// thread b < B: pose / intrinsics gradients of batch element b; thread B: the loss scalars
-SNDE_HD void loss_final_thread(int i, int B, int S, int ns, int flags, const float *poses, FinalParams fp, const double *gP,
-                               const double *gKinv, const double *loss, float *loss_out, float *grad_poses, float *grad_K) {
-    const int N = B * S;
-    if (i == B) {
-        double rigid = 0.0, smooth = 0.0;
-        for (int s = 0; s < ns; ++s) {
-            const double fm = loss[s * 4 + 0] * fp.inv_count[s], bm = loss[s * 4 + 1] * fp.inv_count[s];
-            const double sm = loss[s * 4 + 2] * fp.inv_nx[s] + loss[s * 4 + 3] * fp.inv_ny[s];
-            rigid += (double)fp.photo_weight[s] * (fm + bm);
-            smooth += (double)fp.smooth_weight[s] * sm;
-            loss_out[3 + 3 * s + 0] = (float)fm; loss_out[3 + 3 * s + 1] = (float)bm; loss_out[3 + 3 * s + 2] = (float)sm;
-        }
-        loss_out[0] = (float)(rigid + smooth); loss_out[1] = (float)rigid; loss_out[2] = (float)smooth;
-        return;
-    }
-    if (i > B || !(flags & FLAG_GRAD)) return;
-    const int b = i;
+// Finalize, split so that the double-precision chains run in parallel:
+//   loss_final_pair(b, k, s): backward of the matrix prep for one (batch element, source, scale) -> gv[6], gK[9]
+//   loss_final_scalars: the loss scalars from the per-scale sums
+SNDE_HD void loss_final_pair(int b, int k, int s, int B, int S, int flags, const float *poses, const FinalParams &fp,
+                             const double *gP, const double *gKinv, double *gv /*6*/, double *gK /*9*/) {
+    const int N = B * S, n = k * B + b;
     const bool wantK = (flags & FLAG_GRAD_K) != 0;
-    double gK[SNDE_MAX_SCALES][9];
-    for (int s = 0; s < ns; ++s) for (int j = 0; j < 9; ++j) gK[s][j] = 0.0;
-    for (int k = 0; k < S; ++k) {
-        const int n = k * B + b;
-        float vec[6];
-        for (int j = 0; j < 6; ++j) vec[j] = poses[(b * S + k) * 6 + j];
-        double gv[6] = {0, 0, 0, 0, 0, 0};
-        for (int s = 0; s < ns; ++s) {
-            float K[9];
-            for (int j = 0; j < 9; ++j) K[j] = fp.K[s][b * 9 + j];
-            const double *g = gP + ((size_t)s * N + n) * 24;
-            pose_prep_bwd(vec, K, g, g + 12, (wantK && k == 0) ? gKinv + ((size_t)s * B + b) * 9 : nullptr, gv,
-                          wantK ? gK[s] : nullptr);
-        }
-        for (int j = 0; j < 6; ++j) grad_poses[(b * S + k) * 6 + j] = (float)gv[j];
+    float vec[6], K[9];
+    for (int j = 0; j < 6; ++j) { vec[j] = poses[(b * S + k) * 6 + j]; gv[j] = 0.0; }
+    for (int j = 0; j < 9; ++j) { K[j] = fp.K[s][b * 9 + j]; gK[j] = 0.0; }
+    const double *g = gP + ((size_t)s * N + n) * 24;
+    pose_prep_bwd(vec, K, g, g + 12, (wantK && k == 0) ? gKinv + ((size_t)s * B + b) * 9 : nullptr, gv, wantK ? gK : nullptr);
+}
+
+SNDE_HD void loss_final_scalars(int ns, const FinalParams &fp, const double *loss, float *loss_out) {
+    double rigid = 0.0, smooth = 0.0;
+    for (int s = 0; s < ns; ++s) {
+        const double fm = loss[s * 4 + 0] * fp.inv_count[s], bm = loss[s * 4 + 1] * fp.inv_count[s];
+        const double sm = loss[s * 4 + 2] * fp.inv_nx[s] + loss[s * 4 + 3] * fp.inv_ny[s];
+        rigid += (double)fp.photo_weight[s] * (fm + bm);
+        smooth += (double)fp.smooth_weight[s] * sm;
+        loss_out[3 + 3 * s + 0] = (float)fm; loss_out[3 + 3 * s + 1] = (float)bm; loss_out[3 + 3 * s + 2] = (float)sm;
     }
-    if (wantK) for (int s = 0; s < ns; ++s) for (int j = 0; j < 9; ++j) grad_K[((size_t)b * ns + s) * 9 + j] = (float)gK[s][j];
+    loss_out[0] = (float)(rigid + smooth); loss_out[1] = (float)rigid; loss_out[2] = (float)smooth;
+}
+
+// serial composition (host emulation; the GPU kernel spreads loss_final_pair over threads)
+static inline void loss_final_host(int B, int S, int ns, int flags, const float *poses, const FinalParams &fp, const double *gP,
+                                   const double *gKinv, const double *loss, float *loss_out, float *grad_poses, float *grad_K) {
+    loss_final_scalars(ns, fp, loss, loss_out);
+    if (!(flags & FLAG_GRAD)) return;
+    for (int b = 0; b < B; ++b) {
+        double gKs[SNDE_MAX_SCALES][9] = {};
+        for (int k = 0; k < S; ++k) {
+            double gvs[6] = {0, 0, 0, 0, 0, 0};
+            for (int s = 0; s < ns; ++s) {
+                double gv[6], gK[9];
+                loss_final_pair(b, k, s, B, S, flags, poses, fp, gP, gKinv, gv, gK);
+                for (int j = 0; j < 6; ++j) gvs[j] += gv[j];
+                for (int j = 0; j < 9; ++j) gKs[s][j] += gK[j];
+            }
+            for (int j = 0; j < 6; ++j) grad_poses[(b * S + k) * 6 + j] = (float)gvs[j];
+        }
+        if (flags & FLAG_GRAD_K) for (int s = 0; s < ns; ++s) for (int j = 0; j < 9; ++j) grad_K[((size_t)b * ns + s) * 9 + j] = (float)gKs[s][j];
+    }
 }
 
 static inline int build_dev_loss(const SndeLossArgs *a, DevLoss &d, const LossWorkspace *lay, int64_t *num_tiles) {
@@ -120,6 +135,12 @@ static inline int build_dev_loss(const SndeLossArgs *a, DevLoss &d, const LossWo
         if (M * in.h * in.w >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
         if (!in.tgt.ptr || !in.src.ptr || !in.depth.ptr || !in.K || !in.xtab || !in.ytab) return SNDE_ERR_NULL;
         if ((a->flags & SNDE_LOSS_GRAD) && !in.grad_depth.ptr) return SNDE_ERR_NULL;
+        if (!fits32(in.tgt.sc, in.tgt.sh, in.tgt.sw, in.h, in.w) || !fits32(in.src.sc, in.src.sh, in.src.sw, in.h, in.w) ||
+            !fits32(0, in.depth.sh, in.depth.sw, in.h, in.w) || !fits32(0, in.grad_depth.sh, in.grad_depth.sw, in.h, in.w) ||
+            !fits32(0, in.mask_fwd.sh, in.mask_fwd.sw, in.h, in.w) || !fits32(0, in.mask_bwd.sh, in.mask_bwd.sw, in.h, in.w) ||
+            !fits32(in.warped_fwd.sc, in.warped_fwd.sh, in.warped_fwd.sw, in.h, in.w) || !fits32(in.warped_bwd.sc, in.warped_bwd.sh, in.warped_bwd.sw, in.h, in.w) ||
+            !fits32(in.err_fwd.sc, in.err_fwd.sh, in.err_fwd.sw, in.h, in.w) || !fits32(in.err_bwd.sc, in.err_bwd.sh, in.err_bwd.sw, in.h, in.w))
+            return SNDE_ERR_TOO_LARGE;
         o.h = in.h; o.w = in.w;
         o.tiles_x = (in.w + TileCfg::TW - 1) / TileCfg::TW;
         o.tiles_y = (in.h + TileCfg::TH - 1) / TileCfg::TH;

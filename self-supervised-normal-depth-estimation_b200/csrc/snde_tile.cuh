@@ -12,13 +12,23 @@
 // The owner's edge-aware smoothness term (depth, image already in shared memory) rides along.
 // Each depth gradient element is written exactly once, by the CTA whose inner tile holds it.
 //
-// Region = inner tile + 2-pixel halo: SSIM at p needs a 3x3 window of warped values, and
-// dL/d(warped)(p) needs the SSIM coefficients of the 3x3 neighbours of p.
+// Region = inner tile (60 x 16) + 2-pixel halo = 64 x 20: SSIM at p needs a 3x3 window of warped
+// values, and dL/d(warped)(p) needs the SSIM coefficients of the 3x3 neighbours of p.
 //
-// The code is written as barrier-separated phases over "all threads of the CTA"
-// (SNDE_THREADS_BEGIN/END).  On the GPU that is `tid = threadIdx.x` + __syncthreads(); under the
-// host-emulation test harness (g++, tests/host_emul) it is a loop over tid, which lets the tile
-// logic be checked against the oracle without a GPU.  The product never runs the host variant.
+// Phases (barrier separated):
+//   0  owner image + depth -> shared memory
+//   A  per region pixel: reproject, 4-tap gather of the other image -> Y (+ tap derivatives G)
+//   B  9 warp tasks = 3 channels x 3 row bands; each lane owns two adjacent columns and slides
+//      a 3-row window down its band: row sums are formed once and reused by three output rows.
+//      SSIM, the error value and the three backward coefficient maps come out of this phase.
+//   C  same task shape on the coefficient maps: dL/d(warped_ch) -> written over Y in place
+//   G  per inner pixel: dot with the tap derivatives, back through the projection
+//   S  smoothness pairs, then the depth-gradient tile is written
+//
+// The code is written as phases over "all threads of the CTA" (SNDE_THREADS_BEGIN/END).  On the
+// GPU that is `tid = threadIdx.x` + __syncthreads(); under the host-emulation test harness (g++,
+// tests/host_emul) it is a loop over tid, which lets the tile logic be checked against the
+// oracle without a GPU.  The product never runs the host variant.
 #pragma once
 #include "snde_math.cuh"
 
@@ -29,19 +39,20 @@
 namespace snde {
 
 struct TileCfg {
-    static constexpr int RW = 64;        // region width  (2 warps of columns)
+    static constexpr int RW = 64;        // region width  (32 lanes x 2 columns)
     static constexpr int TH = 16;        // inner tile height
     static constexpr int RH = TH + 4;    // region height
     static constexpr int TW = RW - 4;    // inner tile width (60)
-    static constexpr int NT = 256;       // threads per CTA
-    static constexpr int PPT = TH * RW / NT;   // inner pixels owned per thread (4)
-    static constexpr int NWARP = NT / 32;
+    static constexpr int NWARP = 9;      // 3 channels x 3 row bands
+    static constexpr int NT = NWARP * 32;
+    static constexpr int PPT = (TH * RW + NT - 1) / NT;   // inner-pixel slots per thread (4)
+    static constexpr int BAND = 6;       // rows per band (phase B: 18 rows, phase C: 16 rows)
 };
 
-struct DevImage { const float *p; long long sn, sc, sh, sw; };
-struct DevImageOut { float *p; long long sn, sc, sh, sw; };
-struct DevMap { const float *p; long long sn, sh, sw; };
-struct DevMapOut { float *p; long long sn, sh, sw; };
+struct DevImage { const float *p; long long sn; int sc, sh, sw, pad_; };
+struct DevImageOut { float *p; long long sn; int sc, sh, sw, pad_; };
+struct DevMap { const float *p; long long sn; int sh, sw; };
+struct DevMapOut { float *p; long long sn; int sh, sw; };
 
 struct DevScale {
     int h, w, tiles_x, tiles_y;
@@ -75,24 +86,24 @@ enum { ACC_DP = 0, ACC_DK = 12, ACC_ERR = 21, ACC_SX = 22, ACC_SY = 23, ACC_N = 
 
 // per-thread state that lives across phases (registers on the GPU)
 struct Regs {
-    float gx[TileCfg::PPT], gy[TileCfg::PPT], gd[TileCfg::PPT];
+    float gd[TileCfg::PPT];
     float acc[ACC_N];
 };
 
 struct TileSmem {
     float X[3][TileCfg::RH][TileCfg::RW];         // owner image, 0 outside the image (= the pools' zero padding)
-    float Y[3][TileCfg::RH][TileCfg::RW];         // warped other image, 0 outside the image
+    float Y[3][TileCfg::RH][TileCfg::RW];         // warped other image, 0 outside the image; phase C overwrites inner pixels with dL/dY
     float D[TileCfg::RH][TileCfg::RW];            // owner depth
-    float Co[3][TileCfg::RH - 2][TileCfg::RW];    // SSIM backward coefficient maps of the current channel; reused for the smoothness pair weights
+    float Co[9][TileCfg::RH - 2][TileCfg::RW];    // [ch*3+m]: SSIM backward coefficient maps (rows = region rows 1..RH-2); reused for the smoothness pair weights
     float G[6][TileCfg::TH][TileCfg::RW];         // d(warped_c)/dx, /dy of the inner pixels
     float red[TileCfg::NWARP][ACC_N];             // block-reduction scratch
 };
 
 #if defined(__CUDA_ARCH__)
-#define SNDE_THREADS_BEGIN { const int tid = (int)threadIdx.x; Regs &rg = regs[0];
+#define SNDE_THREADS_BEGIN { const int tid = (int)threadIdx.x; Regs &rg = regs[0]; (void)rg;
 #define SNDE_THREADS_END } __syncthreads();
 #else
-#define SNDE_THREADS_BEGIN for (int tid = 0; tid < TileCfg::NT; ++tid) { Regs &rg = regs[tid];
+#define SNDE_THREADS_BEGIN for (int tid = 0; tid < TileCfg::NT; ++tid) { Regs &rg = regs[tid]; (void)rg;
 #define SNDE_THREADS_END }
 #endif
 
@@ -102,7 +113,7 @@ struct TileSmem {
 #define SNDE_TILE_FN inline
 #endif
 
-// Sum acc[first..first+count) over the CTA and add each to dst[i*stride] (double atomics).
+// Sum acc[first..first+count) over the CTA and add each to dst[i] (double atomics).
 template <int first, int count>
 SNDE_TILE_FN void block_reduce_add(TileSmem &sm, Regs *regs, double *dst) {
 #if defined(__CUDA_ARCH__)
@@ -132,15 +143,35 @@ SNDE_TILE_FN void block_reduce_add(TileSmem &sm, Regs *regs, double *dst) {
 #endif
 }
 
-SNDE_HD float ld_img(const DevImage &im, long long n, int c, int y, int x) {
-    return ldg(im.p + n * im.sn + c * im.sc + (long long)y * im.sh + (long long)x * im.sw);
+// horizontal 3-sums of one region row for the two columns (c0, c0+1) a lane owns
+struct RowSums { float x[2], y[2], xx[2], yy[2], xy[2], cx[2], cy[2]; };
+
+SNDE_HD void row_sums(const float *Xrow, const float *Yrow, int c0, int cl, int cr, RowSums &o) {
+    const F2 xv = *reinterpret_cast<const F2 *>(Xrow + c0), yv = *reinterpret_cast<const F2 *>(Yrow + c0);
+    const float xm = Xrow[cl], xp = Xrow[cr], ym = Yrow[cl], yp = Yrow[cr];
+    const float tx = xv.x + xv.y, ty = yv.x + yv.y;
+    const float txx = fmaf(xv.y, xv.y, xv.x * xv.x), tyy = fmaf(yv.y, yv.y, yv.x * yv.x), txy = fmaf(xv.y, yv.y, xv.x * yv.x);
+    o.x[0] = xm + tx;             o.x[1] = tx + xp;
+    o.y[0] = ym + ty;             o.y[1] = ty + yp;
+    o.xx[0] = fmaf(xm, xm, txx);  o.xx[1] = fmaf(xp, xp, txx);
+    o.yy[0] = fmaf(ym, ym, tyy);  o.yy[1] = fmaf(yp, yp, tyy);
+    o.xy[0] = fmaf(xm, ym, txy);  o.xy[1] = fmaf(xp, yp, txy);
+    o.cx[0] = xv.x; o.cx[1] = xv.y; o.cy[0] = yv.x; o.cy[1] = yv.y;
 }
-SNDE_HD float ld_map(const DevMap &m, long long n, int y, int x) {
-    return ldg(m.p + n * m.sn + (long long)y * m.sh + (long long)x * m.sw);
+
+struct CoSums { float a[2], b[2], c[2]; };
+
+SNDE_HD void co_row_sums(const float *A, const float *Bm, const float *Cm, int c0, int cl, int cr, CoSums &o) {
+    const F2 av = *reinterpret_cast<const F2 *>(A + c0), bv = *reinterpret_cast<const F2 *>(Bm + c0), cv = *reinterpret_cast<const F2 *>(Cm + c0);
+    const float ta = av.x + av.y, tb = bv.x + bv.y, tc = cv.x + cv.y;
+    o.a[0] = A[cl] + ta;  o.a[1] = ta + A[cr];
+    o.b[0] = Bm[cl] + tb; o.b[1] = tb + Bm[cr];
+    o.c[0] = Cm[cl] + tc; o.c[1] = tc + Cm[cr];
 }
 
 // The tile program.  GRAD: also back-propagate.  GRADK: also accumulate d/dKinv.
-template <bool GRAD, bool GRADK>
+// EXTRA: honour the optional explainability masks and warped / error-map outputs.
+template <bool GRAD, bool GRADK, bool EXTRA>
 SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *regs) {
     using C = TileCfg;
     // ---- decode the work item (uniform over the CTA) ----
@@ -159,8 +190,9 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
     const bool clsF = ent.cls == 0;
     const int b = clsF ? m : (m % B);            // batch element (selects K)
     const DevImage &own = clsF ? sc.tgt : sc.src;
-    const long long own_n = m;
+    const float *own_base = own.p + (long long)m * own.sn;
     const long long depth_n = clsF ? m : (long long)B + m;
+    const float *depth_base = sc.depth.p + depth_n * sc.depth.sn;
     const int n_others = (p.flags & FLAG_NO_PHOTO) ? 0 : (clsF ? S : 1);
     const bool do_smooth = !(p.flags & FLAG_NO_SMOOTH);
     const float alpha = p.alpha, oma = p.oma;
@@ -169,36 +201,42 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
     // ---- phase 0: owner image + depth into shared memory, zero the per-thread state ----
     SNDE_THREADS_BEGIN
 #pragma unroll
-        for (int i = 0; i < C::PPT; ++i) { rg.gx[i] = 0.f; rg.gy[i] = 0.f; rg.gd[i] = 0.f; }
+        for (int i = 0; i < C::PPT; ++i) rg.gd[i] = 0.f;
 #pragma unroll
         for (int i = 0; i < ACC_N; ++i) rg.acc[i] = 0.f;
         for (int idx = tid; idx < C::RH * C::RW; idx += C::NT) {
-            const int r = idx / C::RW, c = idx - r * C::RW;
+            const int r = idx >> 6, c = idx & 63;
             const int iy = ry0 + r, ix = rx0 + c;
             const bool in = iy >= 0 && iy < h && ix >= 0 && ix < w;
-            sm.X[0][r][c] = in ? ld_img(own, own_n, 0, iy, ix) : 0.f;
-            sm.X[1][r][c] = in ? ld_img(own, own_n, 1, iy, ix) : 0.f;
-            sm.X[2][r][c] = in ? ld_img(own, own_n, 2, iy, ix) : 0.f;
-            sm.D[r][c] = in ? ld_map(sc.depth, depth_n, iy, ix) : 0.f;
+            float x0 = 0.f, x1 = 0.f, x2 = 0.f, d = 0.f;
+            if (in) {
+                const float *q = own_base + iy * own.sh + ix * own.sw;
+                x0 = ldg(q); x1 = ldg(q + own.sc); x2 = ldg(q + 2 * own.sc);
+                d = ldg(depth_base + iy * sc.depth.sh + ix * sc.depth.sw);
+            }
+            sm.X[0][r][c] = x0; sm.X[1][r][c] = x1; sm.X[2][r][c] = x2; sm.D[r][c] = d;
         }
     SNDE_THREADS_END
 
     for (int k = 0; k < n_others; ++k) {
         const long long n = clsF ? (long long)k * B + b : m;      // index into the N-sized tensors
         const DevImage &oth = clsF ? sc.src : sc.tgt;
-        const long long oth_n = clsF ? n : b;
+        const float *oth_base = oth.p + (clsF ? n : (long long)b) * oth.sn;
         const float *Pg = sc.P + (n * 2 + (clsF ? 0 : 1)) * 12;
         const DevMap &mask = clsF ? sc.mask_fwd : sc.mask_bwd;
         const DevImageOut &wout = clsF ? sc.warped_fwd : sc.warped_bwd;
         const DevImageOut &eout = clsF ? sc.err_fwd : sc.err_bwd;
+        const bool has_mask = EXTRA && mask.p != nullptr;
         float P[12], Ki[9];
+#pragma unroll
         for (int i = 0; i < 12; ++i) P[i] = ldg(Pg + i);
+#pragma unroll
         for (int i = 0; i < 9; ++i) Ki[i] = ldg(Kinv + i);
 
         // ---- phase A: reproject + sample every in-image region pixel ----
         SNDE_THREADS_BEGIN
             for (int idx = tid; idx < C::RH * C::RW; idx += C::NT) {
-                const int r = idx / C::RW, c = idx - r * C::RW;
+                const int r = idx >> 6, c = idx & 63;
                 const int iy = ry0 + r, ix = rx0 + c;
                 const bool in = iy >= 0 && iy < h && ix >= 0 && ix < w;
                 float y0 = 0.f, y1 = 0.f, y2 = 0.f;
@@ -206,27 +244,33 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
                     const float xt = ldg(sc.xtab + ix), yt = ldg(sc.ytab + iy);
                     Reproj rp; reproject(Ki, P, xt, yt, sm.D[r][c], rp);
                     float x, y; flow_coords(rp, xt, yt, x, y);
-                    Taps tp; make_taps(x, y, h, w, p.padding, tp);
-                    const float *base = oth.p + oth_n * oth.sn;
-                    const long long o00 = (long long)tp.y0 * oth.sh + (long long)tp.x0 * oth.sw;
-                    const long long o01 = (long long)tp.y1 * oth.sh + (long long)tp.x0 * oth.sw;
-                    const long long o10 = (long long)tp.y0 * oth.sh + (long long)tp.x1 * oth.sw;
-                    const long long o11 = (long long)tp.y1 * oth.sh + (long long)tp.x1 * oth.sw;
+                    Taps tp; make_taps(x, y, h, w, EXTRA ? p.padding : 0, tp);
+                    const int o00 = tp.y0 * oth.sh + tp.x0 * oth.sw, o01 = tp.y1 * oth.sh + tp.x0 * oth.sw;
+                    const int o10 = tp.y0 * oth.sh + tp.x1 * oth.sw, o11 = tp.y1 * oth.sh + tp.x1 * oth.sw;
+                    const float w00 = tp.wx0 * tp.wy0, w01 = tp.wx0 * tp.wy1, w10 = tp.wx1 * tp.wy0, w11 = tp.wx1 * tp.wy1;
                     const bool inner = r >= 2 && r < C::TH + 2 && c >= 2 && c < C::RW - 2;
-                    float yv[3];
+                    // Outside [0,w-1) x [0,h-1) the reference's clamped-corner weights cancel to zero (up to rounding
+                    // residue that grows with the distance from the image); the fused path writes the exact zero.
+                    const bool valid = (EXTRA && p.padding) ? true : tap_valid(x, y, h, w, 0) != 0.f;   // border mode samples everywhere
+                    float yv[3] = {0.f, 0.f, 0.f};
+                    if (valid) {
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        const float *bc = base + ch * oth.sc;
-                        const float i00 = ldg(bc + o00), i01 = ldg(bc + o01), i10 = ldg(bc + o10), i11 = ldg(bc + o11);
-                        yv[ch] = tap_blend(tp, i00, i01, i10, i11);
-                        if (GRAD && inner) {
-                            float ddx, ddy; tap_derivs(tp, i00, i01, i10, i11, ddx, ddy);
-                            sm.G[2 * ch][r - 2][c] = ddx; sm.G[2 * ch + 1][r - 2][c] = ddy;
+                        for (int ch = 0; ch < 3; ++ch) {
+                            const float *bc = oth_base + ch * oth.sc;
+                            const float i00 = ldg(bc + o00), i01 = ldg(bc + o01), i10 = ldg(bc + o10), i11 = ldg(bc + o11);
+                            yv[ch] = tap_blend_fma(w00, w01, w10, w11, i00, i01, i10, i11);
+                            if (GRAD && inner) {
+                                float ddx, ddy; tap_derivs_fma(tp, i00, i01, i10, i11, ddx, ddy);
+                                sm.G[2 * ch][r - 2][c] = ddx; sm.G[2 * ch + 1][r - 2][c] = ddy;
+                            }
                         }
+                    } else if (GRAD && inner) {
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) sm.G[q][r - 2][c] = 0.f;
                     }
                     y0 = yv[0]; y1 = yv[1]; y2 = yv[2];
-                    if (inner && wout.p) {
-                        float *o = wout.p + n * wout.sn + (long long)iy * wout.sh + (long long)ix * wout.sw;
+                    if (EXTRA && inner && wout.p) {
+                        float *o = wout.p + n * wout.sn + iy * wout.sh + ix * wout.sw;
                         o[0] = y0; o[wout.sc] = y1; o[2 * wout.sc] = y2;
                     }
                 }
@@ -234,99 +278,125 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
             }
         SNDE_THREADS_END
 
-        for (int ch = 0; ch < 3; ++ch) {
-            // ---- phase B: SSIM + error at every window centre of region rows 1..RH-2, cols 1..RW-2 ----
-            SNDE_THREADS_BEGIN
-                for (int idx = tid; idx < (C::RH - 2) * C::RW; idx += C::NT) {
-                    const int r1 = idx / C::RW, c = idx - r1 * C::RW;
-                    const int r = r1 + 1;
-                    if (c == 0 || c == C::RW - 1) continue;
-                    const int iy = ry0 + r, ix = rx0 + c;
-                    const bool in = iy >= 0 && iy < h && ix >= 0 && ix < w;
-                    const bool inner = r >= 2 && r < C::TH + 2 && c >= 2 && c < C::RW - 2;
+        // ---- phase B: SSIM + error value + backward coefficients; warp task = (channel, band of 6 rows) ----
+        SNDE_THREADS_BEGIN
+            const int warp = tid >> 5, lane = tid & 31;
+            const int ch = warp % 3, band = warp / 3;
+            const int ra = 1 + C::BAND * band;                 // output rows ra .. ra+5 (region rows 1..18)
+            const int c0 = 2 * lane, cl = c0 > 0 ? c0 - 1 : 0, cr = c0 + 2 < C::RW ? c0 + 2 : C::RW - 1;
+            const float gS0 = -0.5f * alpha * sc.gphoto;
+            RowSums ra_, rb_, rc_;
+            row_sums(sm.X[ch][ra - 1], sm.Y[ch][ra - 1], c0, cl, cr, ra_);
+            row_sums(sm.X[ch][ra], sm.Y[ch][ra], c0, cl, cr, rb_);
+            float err_acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < C::BAND; ++j) {
+                const int r = ra + j;
+                row_sums(sm.X[ch][r + 1], sm.Y[ch][r + 1], c0, cl, cr, rc_);
+                const int iy = ry0 + r;
+                const bool row_in = iy >= 0 && iy < h;
+                const bool row_inner = r >= 2 && r < C::TH + 2;
+                float oa[2], ob[2], oc[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int c = c0 + q, ix = rx0 + c;
+                    const bool valid = row_in && c >= 1 && c <= C::RW - 2 && ix >= 0 && ix < w;
+                    const float sx = (ra_.x[q] + rb_.x[q]) + rc_.x[q], sy = (ra_.y[q] + rb_.y[q]) + rc_.y[q];
+                    const float sxx = (ra_.xx[q] + rb_.xx[q]) + rc_.xx[q], syy = (ra_.yy[q] + rb_.yy[q]) + rc_.yy[q];
+                    const float sxy = (ra_.xy[q] + rb_.xy[q]) + rc_.xy[q];
+                    SsimS ss; ssim_sums(sx, sy, sxx, syy, sxy, ss);
+                    const float v = fmaf(-0.5f, ss.S, 0.5f);
+                    const float err = fmaf(alpha, clampf(v, 0.f, 1.f), oma * fabsf(rb_.cx[q] - rb_.cy[q]));
+                    float mk = 1.f;
+                    if (has_mask && valid) mk = ldg(mask.p + n * mask.sn + iy * mask.sh + ix * mask.sw);
+                    if (valid && row_inner && c >= 2 && c < C::RW - 2) {
+                        err_acc += EXTRA ? err * mk : err;
+                        if (EXTRA && eout.p) eout.p[n * eout.sn + ch * eout.sc + iy * eout.sh + ix * eout.sw] = err;
+                    }
                     float ca = 0.f, cb = 0.f, cc = 0.f;
-                    if (in && (GRAD || inner)) {
-                        float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
-#pragma unroll
-                        for (int dr = -1; dr <= 1; ++dr)
-#pragma unroll
-                            for (int dc = -1; dc <= 1; ++dc) {
-                                const float xv = sm.X[ch][r + dr][c + dc], yv = sm.Y[ch][r + dr][c + dc];
-                                sx = sx + xv; sy = sy + yv; sxx = sxx + xv * xv; syy = syy + yv * yv; sxy = sxy + xv * yv;
-                            }
-                        Ssim ss; ssim_from_sums(sx, sy, sxx, syy, sxy, ss);
-                        float v;
-                        const float err = similarity_value(alpha, oma, ss.S, sm.X[ch][r][c], sm.Y[ch][r][c], v);
-                        const float mk = mask.p ? ld_map(mask, n, iy, ix) : 1.f;
-                        if (inner) {
-                            rg.acc[ACC_ERR] += err * mk;
-                            if (eout.p) eout.p[n * eout.sn + ch * eout.sc + (long long)iy * eout.sh + (long long)ix * eout.sw] = err;
-                        }
-                        if (GRAD) {
-                            const float g = sc.gphoto * mk;
-                            const float gS = (v >= 0.f && v <= 1.f) ? -0.5f * alpha * g : 0.f;
-                            float cmx;
-                            ssim_bwd_coeffs(ss, gS, cmx, ca, cb, cc);
-                        }
+                    if (GRAD) {
+                        const float gS = (valid && v >= 0.f && v <= 1.f) ? (EXTRA ? gS0 * mk : gS0) : 0.f;
+                        ssim_sums_bwd(ss, sx, sy, gS, ca, cb, cc);
                     }
-                    if (GRAD) { sm.Co[0][r1][c] = ca; sm.Co[1][r1][c] = cb; sm.Co[2][r1][c] = cc; }
+                    oa[q] = ca; ob[q] = cb; oc[q] = cc;
                 }
-            SNDE_THREADS_END
-            if (GRAD) {
-                // ---- phase C: dL/d(warped_ch) at the inner pixels -> accumulate dL/dx, dL/dy ----
-                SNDE_THREADS_BEGIN
-#pragma unroll
-                    for (int i = 0; i < C::PPT; ++i) {
-                        const int idx = tid + i * C::NT;
-                        const int row = idx / C::RW, c = idx - row * C::RW;
-                        const int r = row + 2, iy = ry0 + r, ix = rx0 + c;
-                        if (c < 2 || c >= C::RW - 2 || iy >= h || ix >= w) continue;   // iy, ix >= 0 for inner pixels
-                        float ba = 0.f, bb = 0.f, bc = 0.f;
-#pragma unroll
-                        for (int dr = -1; dr <= 1; ++dr)
-#pragma unroll
-                            for (int dc = -1; dc <= 1; ++dc) {
-                                ba += sm.Co[0][r - 1 + dr][c + dc]; bb += sm.Co[1][r - 1 + dr][c + dc]; bc += sm.Co[2][r - 1 + dr][c + dc];
-                            }
-                        const float xv = sm.X[ch][r][c], yv = sm.Y[ch][r][c];
-                        const float mk = mask.p ? ld_map(mask, n, iy, ix) : 1.f;
-                        const float l1 = oma * (sc.gphoto * mk) * signf(xv - yv);
-                        const float gyh = (ba + 2.f * yv * bb + xv * bc) / 9.f - l1;
-                        rg.gx[i] += gyh * sm.G[2 * ch][row][c];
-                        rg.gy[i] += gyh * sm.G[2 * ch + 1][row][c];
-                    }
-                SNDE_THREADS_END
+                if (GRAD) {
+                    *reinterpret_cast<F2 *>(&sm.Co[ch * 3 + 0][r - 1][c0]) = F2{oa[0], oa[1]};
+                    *reinterpret_cast<F2 *>(&sm.Co[ch * 3 + 1][r - 1][c0]) = F2{ob[0], ob[1]};
+                    *reinterpret_cast<F2 *>(&sm.Co[ch * 3 + 2][r - 1][c0]) = F2{oc[0], oc[1]};
+                }
+                ra_ = rb_; rb_ = rc_;
             }
-        }
+            rg.acc[ACC_ERR] += err_acc;
+        SNDE_THREADS_END
 
         if (GRAD) {
-            // ---- phase G: back through the projection for the inner pixels ----
+            // ---- phase C: dL/d(warped_ch) at the inner pixels, written over Y in place ----
+            SNDE_THREADS_BEGIN
+                const int warp = tid >> 5, lane = tid & 31;
+                const int ch = warp % 3, band = warp / 3;
+                const int ra = 2 + C::BAND * band;             // output rows ra .. min(ra+5, TH+1)  (region rows 2..17)
+                const int c0 = 2 * lane, cl = c0 > 0 ? c0 - 1 : 0, cr = c0 + 2 < C::RW ? c0 + 2 : C::RW - 1;
+                const float g1 = oma * sc.gphoto;
+                const float *A = &sm.Co[ch * 3 + 0][0][0], *Bm = &sm.Co[ch * 3 + 1][0][0], *Cm = &sm.Co[ch * 3 + 2][0][0];
+                CoSums sa, sb, sc_;
+                co_row_sums(A + (ra - 2) * C::RW, Bm + (ra - 2) * C::RW, Cm + (ra - 2) * C::RW, c0, cl, cr, sa);   // Co row index = region row - 1
+                co_row_sums(A + (ra - 1) * C::RW, Bm + (ra - 1) * C::RW, Cm + (ra - 1) * C::RW, c0, cl, cr, sb);
+#pragma unroll
+                for (int j = 0; j < C::BAND; ++j) {
+                    const int r = ra + j;
+                    if (r < C::TH + 2) {
+                        co_row_sums(A + r * C::RW, Bm + r * C::RW, Cm + r * C::RW, c0, cl, cr, sc_);
+                        const F2 xv = *reinterpret_cast<const F2 *>(&sm.X[ch][r][c0]), yv = *reinterpret_cast<const F2 *>(&sm.Y[ch][r][c0]);
+                        const float xs[2] = {xv.x, xv.y}, ys[2] = {yv.x, yv.y};
+                        const int iy = ry0 + r;
+                        float po[2];
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const float ba = (sa.a[q] + sb.a[q]) + sc_.a[q], bb = (sa.b[q] + sb.b[q]) + sc_.b[q], bc = (sa.c[q] + sb.c[q]) + sc_.c[q];
+                            float gl = g1;
+                            if (has_mask) {
+                                const int ix = rx0 + c0 + q;
+                                if (iy < h && ix >= 0 && ix < w) gl = g1 * ldg(mask.p + n * mask.sn + iy * mask.sh + ix * mask.sw);
+                            }
+                            const float d = xs[q] - ys[q];
+                            const float l1 = d > 0.f ? gl : (d < 0.f ? -gl : 0.f);
+                            po[q] = fmaf(ys[q] + ys[q], bb, fmaf(xs[q], bc, ba)) - l1;
+                        }
+                        *reinterpret_cast<F2 *>(&sm.Y[ch][r][c0]) = F2{po[0], po[1]};
+                        sa = sb; sb = sc_;
+                    }
+                }
+            SNDE_THREADS_END
+
+            // ---- phase G: dot with the tap derivatives, back through the projection (inner pixels) ----
             SNDE_THREADS_BEGIN
 #pragma unroll
                 for (int i = 0; i < C::PPT; ++i) {
                     const int idx = tid + i * C::NT;
-                    const int row = idx / C::RW, c = idx - row * C::RW;
+                    const int row = idx >> 6, c = idx & 63;
                     const int r = row + 2, iy = ry0 + r, ix = rx0 + c;
-                    const float gx = rg.gx[i], gy = rg.gy[i];
-                    rg.gx[i] = 0.f; rg.gy[i] = 0.f;
-                    if (c < 2 || c >= C::RW - 2 || iy >= h || ix >= w) continue;
+                    if (idx >= C::TH * C::RW || c < 2 || c >= C::RW - 2 || iy >= h || ix >= w) continue;   // iy, ix >= 0 for inner pixels
+                    const float g0 = sm.Y[0][r][c], g1_ = sm.Y[1][r][c], g2 = sm.Y[2][r][c];
+                    const float gx = fmaf(g2, sm.G[4][row][c], fmaf(g1_, sm.G[2][row][c], g0 * sm.G[0][row][c]));
+                    const float gy = fmaf(g2, sm.G[5][row][c], fmaf(g1_, sm.G[3][row][c], g0 * sm.G[1][row][c]));
                     const float xt = ldg(sc.xtab + ix), yt = ldg(sc.ytab + iy), d = sm.D[r][c];
-                    Reproj rp; reproject(Ki, P, xt, yt, d, rp);
+                    Reproj rp; reproject_nodiv(Ki, P, xt, yt, d, rp);
                     float gu[3], gcam[3];
-                    rg.gd[i] += reproject_bwd(P, rp, gx, gy, gu, gcam);
+                    rg.gd[i] += reproject_bwd_fast(P, rp, gx, gy, gu, gcam);
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
-                        rg.acc[ACC_DP + q * 4 + 0] += gu[q] * rp.cam[0];
-                        rg.acc[ACC_DP + q * 4 + 1] += gu[q] * rp.cam[1];
-                        rg.acc[ACC_DP + q * 4 + 2] += gu[q] * rp.cam[2];
+                        rg.acc[ACC_DP + q * 4 + 0] = fmaf(gu[q], rp.cam[0], rg.acc[ACC_DP + q * 4 + 0]);
+                        rg.acc[ACC_DP + q * 4 + 1] = fmaf(gu[q], rp.cam[1], rg.acc[ACC_DP + q * 4 + 1]);
+                        rg.acc[ACC_DP + q * 4 + 2] = fmaf(gu[q], rp.cam[2], rg.acc[ACC_DP + q * 4 + 2]);
                         rg.acc[ACC_DP + q * 4 + 3] += gu[q];
                     }
                     if (GRADK) {
 #pragma unroll
                         for (int q = 0; q < 3; ++q) {
                             const float gray = gcam[q] * d;
-                            rg.acc[ACC_DK + q * 3 + 0] += gray * xt;
-                            rg.acc[ACC_DK + q * 3 + 1] += gray * yt;
+                            rg.acc[ACC_DK + q * 3 + 0] = fmaf(gray, xt, rg.acc[ACC_DK + q * 3 + 0]);
+                            rg.acc[ACC_DK + q * 3 + 1] = fmaf(gray, yt, rg.acc[ACC_DK + q * 3 + 1]);
                             rg.acc[ACC_DK + q * 3 + 2] += gray;
                         }
                     }
@@ -347,7 +417,7 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
         float (*SYw)[C::RW] = (float (*)[C::RW])(&sm.Co[0][0][0] + (C::TH + 1) * C::RW);
         SNDE_THREADS_BEGIN
             for (int idx = tid; idx < (C::TH + 1) * C::RW; idx += C::NT) {
-                const int pr = idx / C::RW, c = idx - pr * C::RW;
+                const int pr = idx >> 6, c = idx & 63;
                 const int r = pr + 1, iy = ry0 + r, ix = rx0 + c;
                 float vx = 0.f, vy = 0.f;
                 if (c >= 1 && c <= C::RW - 2 && iy >= 0 && iy < h && ix >= 0 && ix < w) {
@@ -377,9 +447,9 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
 #pragma unroll
                 for (int i = 0; i < C::PPT; ++i) {
                     const int idx = tid + i * C::NT;
-                    const int row = idx / C::RW, c = idx - row * C::RW;
+                    const int row = idx >> 6, c = idx & 63;
                     const int r = row + 2, iy = ry0 + r, ix = rx0 + c;
-                    if (c < 2 || c >= C::RW - 2 || iy >= h || ix >= w) continue;
+                    if (idx >= C::TH * C::RW || c < 2 || c >= C::RW - 2 || iy >= h || ix >= w) continue;
                     const int pr = r - 1;
                     rg.gd[i] += sc.gsx * (SXw[pr][c] - SXw[pr][c - 1]) + sc.gsy * (SYw[pr][c] - SYw[pr - 1][c]);
                 }
@@ -390,13 +460,14 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
     // ---- write the depth gradient, publish the partial sums ----
     if (GRAD) {
         SNDE_THREADS_BEGIN
+            float *gbase = sc.gdepth.p + depth_n * sc.gdepth.sn;
 #pragma unroll
             for (int i = 0; i < C::PPT; ++i) {
                 const int idx = tid + i * C::NT;
-                const int row = idx / C::RW, c = idx - row * C::RW;
+                const int row = idx >> 6, c = idx & 63;
                 const int iy = ry0 + row + 2, ix = rx0 + c;
-                if (c < 2 || c >= C::RW - 2 || iy >= h || ix >= w) continue;
-                sc.gdepth.p[depth_n * sc.gdepth.sn + (long long)iy * sc.gdepth.sh + (long long)ix * sc.gdepth.sw] = rg.gd[i];
+                if (idx >= C::TH * C::RW || c < 2 || c >= C::RW - 2 || iy >= h || ix >= w) continue;
+                gbase[iy * sc.gdepth.sh + ix * sc.gdepth.sw] = rg.gd[i];
             }
         SNDE_THREADS_END
         if (GRADK) block_reduce_add<ACC_DK, 9>(sm, regs, sc.gKinv + 9 * b);

@@ -32,15 +32,19 @@ extern "C" __attribute__((visibility("default"))) int emul_loss_fwdbwd(const Snd
     TileSmem *sm = new TileSmem;
     std::vector<Regs> regs(TileCfg::NT);
     const bool grad = a->flags & SNDE_LOSS_GRAD, gradk = a->flags & SNDE_LOSS_GRAD_K;
+    bool extra = gradk || a->padding_mode != SNDE_PAD_ZEROS;      // same variant selection as snde_loss_fwdbwd
+    for (int s = 0; s < ns; ++s) {
+        const SndeLossScale &in = a->scale[s];
+        extra = extra || in.mask_fwd.ptr || in.mask_bwd.ptr || in.warped_fwd.ptr || in.warped_bwd.ptr || in.err_fwd.ptr || in.err_bwd.ptr;
+    }
     for (int64_t blk = 0; blk < tiles; ++blk) {
         memset(sm, 0xff, sizeof(TileSmem));   // NaN-fill: catches reads of unwritten shared memory
-        if (!grad) loss_tile<false, false>(d, (int)blk, *sm, regs.data());
-        else if (!gradk) loss_tile<true, false>(d, (int)blk, *sm, regs.data());
-        else loss_tile<true, true>(d, (int)blk, *sm, regs.data());
+        if (!grad) { if (extra) loss_tile<false, false, true>(d, (int)blk, *sm, regs.data()); else loss_tile<false, false, false>(d, (int)blk, *sm, regs.data()); }
+        else if (extra) loss_tile<true, true, true>(d, (int)blk, *sm, regs.data());
+        else loss_tile<true, false, false>(d, (int)blk, *sm, regs.data());
     }
     delete sm;
-    for (int i = 0; i <= B; ++i)
-        loss_final_thread(i, B, S, ns, a->flags, a->poses, fp, (const double *)(ws + lay.gP), (const double *)(ws + lay.gKinv),
-                          (const double *)(ws + lay.loss), a->loss_out, a->grad_poses, a->grad_K);
+    loss_final_host(B, S, ns, a->flags, a->poses, fp, (const double *)(ws + lay.gP), (const double *)(ws + lay.gKinv),
+                    (const double *)(ws + lay.loss), a->loss_out, a->grad_poses, a->grad_K);
     return SNDE_OK;
 }
