@@ -37,6 +37,7 @@ extern "C" {
 
 #define SNDE_VERSION 100      /* 0.1.0 */
 #define SNDE_MAX_SCALES 6
+#define SNDE_MAX_SOURCES 8     /* source views per target in the fused loss */
 
 typedef enum SndeStatus {
     SNDE_OK = 0,

@@ -118,6 +118,7 @@ static inline void loss_final_host(int B, int S, int ns, int flags, const float 
 static inline int build_dev_loss(const SndeLossArgs *a, DevLoss &d, const LossWorkspace *lay, int64_t *num_tiles) {
     if (!a) return SNDE_ERR_NULL;
     if (a->B <= 0 || a->S <= 0 || a->num_scales <= 0 || a->num_scales > SNDE_MAX_SCALES) return SNDE_ERR_SHAPE;
+    if (a->S > TileCfg::MAX_S) return SNDE_ERR_SHAPE;        // SNDE_MAX_SOURCES
     if (a->padding_mode != SNDE_PAD_ZEROS && a->padding_mode != SNDE_PAD_BORDER) return SNDE_ERR_ARG;
     if (a->flags & ~15) return SNDE_ERR_ARG;
     if ((a->flags & SNDE_LOSS_GRAD_K) && !(a->flags & SNDE_LOSS_GRAD)) return SNDE_ERR_ARG;

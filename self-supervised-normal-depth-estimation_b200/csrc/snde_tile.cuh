@@ -47,6 +47,7 @@ struct TileCfg {
     static constexpr int NT = NWARP * 32;
     static constexpr int PPT = (TH * RW + NT - 1) / NT;   // inner-pixel slots per thread (4)
     static constexpr int BAND = 6;       // rows per band (phase B: 18 rows, phase C: 16 rows)
+    static constexpr int MAX_S = 8;      // most source views per target (SNDE_MAX_SOURCES)
 };
 
 struct DevImage { const float *p; long long sn; int sc, sh, sw, pad_; };
@@ -82,12 +83,14 @@ struct DevLoss {
 };
 
 enum { FLAG_GRAD = 1, FLAG_GRAD_K = 2, FLAG_NO_PHOTO = 4, FLAG_NO_SMOOTH = 8 };   // == SNDE_LOSS_* in include/snde.h
-enum { ACC_DP = 0, ACC_DK = 12, ACC_ERR = 21, ACC_SX = 22, ACC_SY = 23, ACC_N = 24 };
+// acc[0..11] = dP of the current other image; tail[0..8] = dKinv, tail[9] = err, tail[10], tail[11] = smoothness sums
+enum { T_DK = 0, T_ERR = 9, T_SX = 10, T_SY = 11 };
 
 // per-thread state that lives across phases (registers on the GPU)
 struct Regs {
     float gd[TileCfg::PPT];
-    float acc[ACC_N];
+    float dP[12];
+    float tail[12];
 };
 
 struct TileSmem {
@@ -96,7 +99,8 @@ struct TileSmem {
     float D[TileCfg::RH][TileCfg::RW];            // owner depth
     float Co[9][TileCfg::RH - 2][TileCfg::RW];    // [ch*3+m]: SSIM backward coefficient maps (rows = region rows 1..RH-2); reused for the smoothness pair weights
     float G[6][TileCfg::TH][TileCfg::RW];         // d(warped_c)/dx, /dy of the inner pixels
-    float red[TileCfg::NWARP][ACC_N];             // block-reduction scratch
+    float red[TileCfg::MAX_S + 1][TileCfg::NWARP][16];   // per-warp partial sums: slot k = dP of other k; last used slot = dKinv, err, smooth
+    float PK[2][24];                              // P (12) and Kinv (9) of the current / next other image
 };
 
 #if defined(__CUDA_ARCH__)
@@ -113,33 +117,32 @@ struct TileSmem {
 #define SNDE_TILE_FN inline
 #endif
 
-// Sum acc[first..first+count) over the CTA and add each to dst[i] (double atomics).
-template <int first, int count>
-SNDE_TILE_FN void block_reduce_add(TileSmem &sm, Regs *regs, double *dst) {
+// Warp-level sum of up to 16 per-lane values into dst[0..15] (dst = this warp's row of sm.red).  On the GPU a
+// transposing butterfly: every xor step halves the number of live values, 16 shuffles in all instead of 5 per value.
+SNDE_TILE_FN void warp_sum16(const float *v12, float *dst, int lane) {
 #if defined(__CUDA_ARCH__)
-    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float v[16];
 #pragma unroll
-    for (int i = 0; i < count; ++i) {
-        float v = regs[0].acc[first + i];
+    for (int i = 0; i < 12; ++i) v[i] = v12[i];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) sm.red[warp][i] = v;
+    for (int i = 12; i < 16; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int half = 8; half >= 1; half >>= 1) {
+        const int mask = half * 2;                      // lane bit consumed at this step: 16, 8, 4, 2
+        const bool upper = (lane & mask) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+        }
     }
-    __syncthreads();
-    if (tid < count) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < TileCfg::NWARP; ++w) s += (double)sm.red[w][tid];
-        if (s != 0.0) atomicAdd(dst + tid, s);
-    }
-    __syncthreads();
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    if ((lane & 1) == 0) dst[((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = v[0];
 #else
-    (void)sm;
-    for (int i = 0; i < count; ++i) {
-        double s = 0.0;
-        for (int t = 0; t < TileCfg::NT; ++t) s += (double)regs[t].acc[first + i];
-        dst[i] += s;
-    }
+    // host emulation: called once per thread; lane 0 zeroes the row, every lane adds its values
+    if (lane == 0) for (int i = 0; i < 16; ++i) dst[i] = 0.f;
+    for (int i = 0; i < 12; ++i) dst[i] += v12[i];
 #endif
 }
 
@@ -203,7 +206,11 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
 #pragma unroll
         for (int i = 0; i < C::PPT; ++i) rg.gd[i] = 0.f;
 #pragma unroll
-        for (int i = 0; i < ACC_N; ++i) rg.acc[i] = 0.f;
+        for (int i = 0; i < 12; ++i) { rg.dP[i] = 0.f; rg.tail[i] = 0.f; }
+        if (n_others > 0 && tid < 21) {           // stage P / Kinv of the first other image
+            const long long n0 = clsF ? (long long)b : m;
+            sm.PK[0][tid] = tid < 12 ? ldg(sc.P + (n0 * 2 + (clsF ? 0 : 1)) * 12 + tid) : ldg(Kinv + tid - 12);
+        }
         for (int idx = tid; idx < C::RH * C::RW; idx += C::NT) {
             const int r = idx >> 6, c = idx & 63;
             const int iy = ry0 + r, ix = rx0 + c;
@@ -222,19 +229,23 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
         const long long n = clsF ? (long long)k * B + b : m;      // index into the N-sized tensors
         const DevImage &oth = clsF ? sc.src : sc.tgt;
         const float *oth_base = oth.p + (clsF ? n : (long long)b) * oth.sn;
-        const float *Pg = sc.P + (n * 2 + (clsF ? 0 : 1)) * 12;
         const DevMap &mask = clsF ? sc.mask_fwd : sc.mask_bwd;
         const DevImageOut &wout = clsF ? sc.warped_fwd : sc.warped_bwd;
         const DevImageOut &eout = clsF ? sc.err_fwd : sc.err_bwd;
         const bool has_mask = EXTRA && mask.p != nullptr;
-        float P[12], Ki[9];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) P[i] = ldg(Pg + i);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Ki[i] = ldg(Kinv + i);
+        const float *PKs = sm.PK[k & 1];
 
         // ---- phase A: reproject + sample every in-image region pixel ----
         SNDE_THREADS_BEGIN
+            float P[12], Ki[9];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) P[i] = PKs[i];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Ki[i] = PKs[12 + i];
+            if (k + 1 < n_others && tid < 21) {       // stage the next other image's matrices (read after two more barriers)
+                const long long n1 = (long long)(k + 1) * B + b;
+                sm.PK[(k + 1) & 1][tid] = tid < 12 ? ldg(sc.P + (n1 * 2) * 12 + tid) : ldg(Kinv + tid - 12);
+            }
             for (int idx = tid; idx < C::RH * C::RW; idx += C::NT) {
                 const int r = idx >> 6, c = idx & 63;
                 const int iy = ry0 + r, ix = rx0 + c;
@@ -244,7 +255,9 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
                     const float xt = ldg(sc.xtab + ix), yt = ldg(sc.ytab + iy);
                     Reproj rp; reproject(Ki, P, xt, yt, sm.D[r][c], rp);
                     float x, y; flow_coords(rp, xt, yt, x, y);
-                    Taps tp; make_taps(x, y, h, w, EXTRA ? p.padding : 0, tp);
+                    Taps tp;
+                    if (EXTRA && p.padding) make_taps(x, y, h, w, p.padding, tp);
+                    else make_taps_valid(x, y, tp);          // only used when the coordinate is valid (no clamp is active there)
                     const int o00 = tp.y0 * oth.sh + tp.x0 * oth.sw, o01 = tp.y1 * oth.sh + tp.x0 * oth.sw;
                     const int o10 = tp.y0 * oth.sh + tp.x1 * oth.sw, o11 = tp.y1 * oth.sh + tp.x1 * oth.sw;
                     const float w00 = tp.wx0 * tp.wy0, w01 = tp.wx0 * tp.wy1, w10 = tp.wx1 * tp.wy0, w11 = tp.wx1 * tp.wy1;
@@ -327,7 +340,7 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
                 }
                 ra_ = rb_; rb_ = rc_;
             }
-            rg.acc[ACC_ERR] += err_acc;
+            rg.tail[T_ERR] += err_acc;
         SNDE_THREADS_END
 
         if (GRAD) {
@@ -371,6 +384,13 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
 
             // ---- phase G: dot with the tap derivatives, back through the projection (inner pixels) ----
             SNDE_THREADS_BEGIN
+                float P[12], Ki[9];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) P[i] = PKs[i];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Ki[i] = PKs[12 + i];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) rg.dP[i] = 0.f;
 #pragma unroll
                 for (int i = 0; i < C::PPT; ++i) {
                     const int idx = tid + i * C::NT;
@@ -386,27 +406,22 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
                     rg.gd[i] += reproject_bwd_fast(P, rp, gx, gy, gu, gcam);
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
-                        rg.acc[ACC_DP + q * 4 + 0] = fmaf(gu[q], rp.cam[0], rg.acc[ACC_DP + q * 4 + 0]);
-                        rg.acc[ACC_DP + q * 4 + 1] = fmaf(gu[q], rp.cam[1], rg.acc[ACC_DP + q * 4 + 1]);
-                        rg.acc[ACC_DP + q * 4 + 2] = fmaf(gu[q], rp.cam[2], rg.acc[ACC_DP + q * 4 + 2]);
-                        rg.acc[ACC_DP + q * 4 + 3] += gu[q];
+                        rg.dP[q * 4 + 0] = fmaf(gu[q], rp.cam[0], rg.dP[q * 4 + 0]);
+                        rg.dP[q * 4 + 1] = fmaf(gu[q], rp.cam[1], rg.dP[q * 4 + 1]);
+                        rg.dP[q * 4 + 2] = fmaf(gu[q], rp.cam[2], rg.dP[q * 4 + 2]);
+                        rg.dP[q * 4 + 3] += gu[q];
                     }
                     if (GRADK) {
 #pragma unroll
                         for (int q = 0; q < 3; ++q) {
                             const float gray = gcam[q] * d;
-                            rg.acc[ACC_DK + q * 3 + 0] = fmaf(gray, xt, rg.acc[ACC_DK + q * 3 + 0]);
-                            rg.acc[ACC_DK + q * 3 + 1] = fmaf(gray, yt, rg.acc[ACC_DK + q * 3 + 1]);
-                            rg.acc[ACC_DK + q * 3 + 2] += gray;
+                            rg.tail[T_DK + q * 3 + 0] = fmaf(gray, xt, rg.tail[T_DK + q * 3 + 0]);
+                            rg.tail[T_DK + q * 3 + 1] = fmaf(gray, yt, rg.tail[T_DK + q * 3 + 1]);
+                            rg.tail[T_DK + q * 3 + 2] += gray;
                         }
                     }
                 }
-            SNDE_THREADS_END
-            block_reduce_add<ACC_DP, 12>(sm, regs, sc.gP + (n * 2 + (clsF ? 0 : 1)) * 12);
-            SNDE_THREADS_BEGIN
-#pragma unroll
-                for (int i = 0; i < 12; ++i) rg.acc[ACC_DP + i] = 0.f;
-                (void)tid;
+                warp_sum16(rg.dP, sm.red[k][tid >> 5], tid & 31);     // combined across warps at the end of the tile
             SNDE_THREADS_END
         }
     }
@@ -424,18 +439,18 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
                     const bool inner = r >= 2 && r < C::TH + 2 && c >= 2 && c < C::RW - 2;
                     const float d = sm.D[r][c];
                     if (ix + 1 < w) {
-                        const float wgt = edge_weight3(sm.X[0][r][c], sm.X[1][r][c], sm.X[2][r][c],
+                        const float wgt = edge_weight3_fast(sm.X[0][r][c], sm.X[1][r][c], sm.X[2][r][c],
                                                        sm.X[0][r][c + 1], sm.X[1][r][c + 1], sm.X[2][r][c + 1]);
                         const float v = (d - sm.D[r][c + 1]) * wgt;
-                        vx = signf(v) * wgt;
-                        if (inner) rg.acc[ACC_SX] += fabsf(v);
+                        vx = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
+                        if (inner) rg.tail[T_SX] += fabsf(v);
                     }
                     if (iy + 1 < h) {
-                        const float wgt = edge_weight3(sm.X[0][r][c], sm.X[1][r][c], sm.X[2][r][c],
+                        const float wgt = edge_weight3_fast(sm.X[0][r][c], sm.X[1][r][c], sm.X[2][r][c],
                                                        sm.X[0][r + 1][c], sm.X[1][r + 1][c], sm.X[2][r + 1][c]);
                         const float v = (d - sm.D[r + 1][c]) * wgt;
-                        vy = signf(v) * wgt;
-                        if (inner) rg.acc[ACC_SY] += fabsf(v);
+                        vy = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
+                        if (inner) rg.tail[T_SY] += fabsf(v);
                     }
                 }
                 SXw[pr][c] = vx; SYw[pr][c] = vy;
@@ -470,11 +485,34 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
                 gbase[iy * sc.gdepth.sh + ix * sc.gdepth.sw] = rg.gd[i];
             }
         SNDE_THREADS_END
-        if (GRADK) block_reduce_add<ACC_DK, 9>(sm, regs, sc.gKinv + 9 * b);
     }
-    // acc[ERR] -> loss[0|1]; acc[SX], acc[SY] -> loss[2], loss[3]
-    block_reduce_add<ACC_ERR, 1>(sm, regs, sc.loss + (clsF ? 0 : 1));
-    block_reduce_add<ACC_SX, 2>(sm, regs, sc.loss + 2);
+    // ---- publish: per-warp partials -> shared memory -> one double atomicAdd per value per CTA ----
+    const int nslots = (GRAD ? n_others : 0) + 1;
+    SNDE_THREADS_BEGIN
+        warp_sum16(rg.tail, sm.red[nslots - 1][tid >> 5], tid & 31);
+    SNDE_THREADS_END
+    SNDE_THREADS_BEGIN
+        if (tid < 16 * nslots) {
+            const int slot = tid >> 4, i = tid & 15;
+            double sum = 0.0;
+#pragma unroll
+            for (int wq = 0; wq < C::NWARP; ++wq) sum += (double)sm.red[slot][wq][i];
+            double *dst = nullptr;
+            if (slot < nslots - 1) {
+                const long long nk = clsF ? (long long)slot * B + b : m;
+                if (i < 12) dst = sc.gP + (nk * 2 + (clsF ? 0 : 1)) * 12 + i;
+            } else if (i < 9) { if (GRADK) dst = sc.gKinv + 9 * b + i; }
+            else if (i == T_ERR) dst = sc.loss + (clsF ? 0 : 1);
+            else if (i == T_SX || i == T_SY) dst = sc.loss + 2 + (i - T_SX);
+            if (dst && sum != 0.0) {
+#if defined(__CUDA_ARCH__)
+                atomicAdd(dst, sum);
+#else
+                *dst += sum;
+#endif
+            }
+        }
+    SNDE_THREADS_END
 }
 
 }  // namespace snde
