@@ -15,7 +15,7 @@ def ranges(fname, markers):
             raise SystemExit("marker not found: " + pat)
     pts.sort()
     return pts
-tile = ranges("snde_tile.cuh", [("reduce", "void block_reduce_add"), ("B.row_sums", "struct RowSums"), ("C.co_row_sums", "struct CoSums"),
+tile = ranges("snde_tile.cuh", [("reduce", "void warp_sum16"), ("B.row_sums", "struct RowSums"), ("C.co_row_sums", "struct CoSums"),
                                 ("decode", "The tile program."), ("0.load", "---- phase 0"), ("A", "for (int k = 0; k < n_others"),
                                 ("B", "---- phase B"), ("C", "---- phase C"), ("G", "---- phase G"), ("S", "if (do_smooth)"),
                                 ("W.write", "---- write the depth gradient")])

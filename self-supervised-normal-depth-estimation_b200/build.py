@@ -2,8 +2,9 @@
 
     python -m snde_b200.build            # or: __graft_entry__.build()
 
--fmad=false: the arithmetic order of csrc/snde_math.cuh is part of the parity contract
-(fused multiply-adds only where written as fmaf()); no --use_fast_math.
+Arithmetic order is part of the parity contract (csrc/snde_math.cuh): the reference-signature kernels
+(snde_ops.cu) are built with -fmad=false; the fused kernel (snde_fused.cu) with -fmad=true, its exact-order
+chains written out with fmaf()/__fmul_rn()/__fadd_rn().  No --use_fast_math anywhere.
 """
 from __future__ import annotations
 
@@ -16,7 +17,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libsnde.so")
-SOURCES = ["snde_kernels.cu"]
+# (source, fp-contraction flag): the fused kernel spells out its exact-order arithmetic, the reference-signature
+# kernels follow the reference op by op
+SOURCES = [("snde_fused.cu", "-fmad=true"), ("snde_ops.cu", "-fmad=false")]
 HEADERS = ["snde_math.cuh", "snde_tile.cuh", "snde_loss_setup.cuh"]
 
 
@@ -31,22 +34,29 @@ def is_fresh() -> bool:
     if not os.path.exists(LIB):
         return False
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(INCLUDE, "snde.h")]
+    deps = [os.path.join(CSRC, f) for f in [s for s, _ in SOURCES] + HEADERS] + [os.path.join(INCLUDE, "snde.h")]
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if is_fresh() and not force:
         return LIB
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-fmad=false", "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",
-           "-Xptxas", "-v" if verbose else "-O3", "-I", INCLUDE, "-I", CSRC,
-           "-DSNDE_BUILDING=1", "-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose:
-        print(res.stderr)
+    common = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "-Xptxas", "-v" if verbose else "-O3",
+              "-I", INCLUDE, "-I", CSRC, "-DSNDE_BUILDING=1"]
+    objs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    for src, fmad in SOURCES:
+        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        res = subprocess.run(common + [fmad, "-c", "-o", obj, os.path.join(CSRC, src)], capture_output=True, text=True)
+        if verbose:
+            print(res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stderr[-4000:])
+        objs.append(obj)
+    res = subprocess.run([nvcc_path(), "-shared", "-o", LIB] + objs, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stderr[-4000:])
+        raise RuntimeError("link failed:\n" + res.stderr[-4000:])
     return LIB
 
 

@@ -1,12 +1,12 @@
-// snde_kernels.cu -- sm_100a kernels + the C ABI declared in include/snde.h.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false (see build.py).
+// snde_ops.cu -- reference-signature kernels of the C ABI (include/snde.h): pose matrices, compute_rigid_flow,
+// bilinear_sampler / flow_warp, image_similarity / DSSIM, smooth_loss.  Each materialises its output like the
+// reference op it replaces.  Built with -fmad=false: these follow the reference's arithmetic op by op.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
 
 #include "snde.h"
-#include "snde_tile.cuh"
-#include "snde_loss_setup.cuh"
+#include "snde_math.cuh"
 
 using namespace snde;
 
@@ -29,163 +29,6 @@ __device__ __forceinline__ float ld_map(const LMap &m, long long n, int y, int x
 #define SNDE_CHECK_LAUNCH() do { if (cudaGetLastError() != cudaSuccess) return SNDE_ERR_CUDA; } while (0)
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
-
-// =============================================================================================
-// small helpers
-// =============================================================================================
-extern "C" int snde_version(void) { return SNDE_VERSION; }
-
-extern "C" const char *snde_strerror(int status) {
-    switch (status) {
-        case SNDE_OK: return "ok";
-        case SNDE_ERR_NULL: return "snde: required pointer is NULL";
-        case SNDE_ERR_SHAPE: return "snde: bad shape (non-positive dimension, C != 3, or h,w < 2 for smoothness)";
-        case SNDE_ERR_TOO_LARGE: return "snde: tensor too large (N*h*w must stay below 2^31)";
-        case SNDE_ERR_WORKSPACE: return "snde: workspace missing, too small or not 16-byte aligned";
-        case SNDE_ERR_ARG: return "snde: bad argument (enum, flag or scalar out of range)";
-        case SNDE_ERR_CUDA: return "snde: CUDA launch failed";
-        default: return "snde: unknown status";
-    }
-}
-
-// reference: utils/utils_edited.py:307-317 -- (linspace(-1,1,n)+1)*0.5*(n-1); torch.linspace rounds
-// start + step*i (first half) / end - step*(n-1-i) (second half) once, i.e. as an FMA.
-extern "C" int snde_fill_grid_table(int n, float *out) {
-    if (!out) return SNDE_ERR_NULL;
-    if (n <= 0) return SNDE_ERR_SHAPE;
-    if (n == 1) { out[0] = 0.f; return SNDE_OK; }
-    const float step = 2.f / (float)(n - 1);
-    const int half = n / 2;
-    for (int i = 0; i < n; ++i) {
-        volatile float lin = (i < half) ? fmaf(step, (float)i, -1.f) : fmaf(-step, (float)(n - i - 1), 1.f);
-        volatile float t = lin + 1.f;
-        t = t * 0.5f;
-        out[i] = t * (float)(n - 1);
-    }
-    return SNDE_OK;
-}
-
-
-__global__ void __launch_bounds__(128) loss_prep_kernel(int B, int S, int ns, const float *__restrict__ poses, PrepParams kp,
-                                                        float *__restrict__ P, float *__restrict__ Kinv) {
-    loss_prep_thread(blockIdx.x * blockDim.x + threadIdx.x, B, S, ns, poses, kp, P, Kinv);
-}
-
-// block b < B: one thread per (source k, scale s) runs the double-precision backward of the matrix prep, then the
-// block reduces over scales (pose gradient) and over sources (intrinsics gradient) in a fixed order.  Block B: scalars.
-__global__ void __launch_bounds__(64) loss_final_kernel(int B, int S, int ns, int flags, const float *__restrict__ poses,
-                                                        FinalParams fp, const double *__restrict__ gP,
-                                                        const double *__restrict__ gKinv, const double *__restrict__ loss,
-                                                        float *__restrict__ loss_out, float *__restrict__ grad_poses,
-                                                        float *__restrict__ grad_K) {
-    __shared__ double sv[64][6];
-    __shared__ double sk[64][9];
-    const int b = blockIdx.x, t = threadIdx.x;
-    if (b == B) { if (t == 0) loss_final_scalars(ns, fp, loss, loss_out); return; }
-    if (!(flags & FLAG_GRAD)) return;
-    const bool wantK = (flags & FLAG_GRAD_K) != 0;
-    for (int base = 0; base < S * ns; base += 64) {          // S*ns <= 64 in practice: one pass
-        const int i = base + t;
-        const int k = i / ns, s = i - k * ns;
-        if (i < S * ns) loss_final_pair(b, k, s, B, S, flags, poses, fp, gP, gKinv, sv[t], sk[t]);
-        __syncthreads();
-        const int cnt = min(64, S * ns - base);
-        // pose gradient: sum over the scales of source k (threads base+k*ns .. base+k*ns+ns-1); requires ns | 64-chunk alignment
-        if (t < cnt && (base + t) % ns == 0) {
-            const int kk = (base + t) / ns;
-            for (int j = 0; j < 6; ++j) {
-                double a = 0.0;
-                for (int q = 0; q < ns && t + q < cnt; ++q) a += sv[t + q][j];
-                if (base == 0 || true) grad_poses[(b * S + kk) * 6 + j] = (float)a;
-            }
-        }
-        if (wantK && t < ns && base == 0) {
-            for (int j = 0; j < 9; ++j) {
-                double a = 0.0;
-                for (int kk = 0; kk * ns + t < cnt; ++kk) a += sk[kk * ns + t][j];
-                grad_K[((size_t)b * ns + t) * 9 + j] = (float)a;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-template <bool GRAD, bool GRADK, bool EXTRA>
-__global__ void __launch_bounds__(TileCfg::NT, 2) loss_tile_kernel(const __grid_constant__ DevLoss p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
-    Regs regs;
-    loss_tile<GRAD, GRADK, EXTRA>(p, (int)blockIdx.x, sm, &regs);
-}
-
-extern "C" size_t snde_sizeof_loss_args(void) { return sizeof(SndeLossArgs); }
-
-extern "C" size_t snde_loss_workspace_bytes(int B, int S, int num_scales) {
-    if (B <= 0 || S <= 0 || num_scales <= 0) return 0;
-    return loss_ws_layout(B, S, num_scales).end;
-}
-
-extern "C" int64_t snde_loss_num_tiles(const SndeLossArgs *args) {
-    DevLoss d; int64_t n = 0;
-    SndeLossArgs tmp;
-    if (!args) return SNDE_ERR_NULL;
-    tmp = *args;
-    int rc = build_dev_loss(&tmp, d, nullptr, &n);
-    return rc ? rc : n;
-}
-
-extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
-    if (!a) return SNDE_ERR_NULL;
-    if (!a->poses || !a->loss_out) return SNDE_ERR_NULL;
-    if ((a->flags & SNDE_LOSS_GRAD) && !a->grad_poses) return SNDE_ERR_NULL;
-    if ((a->flags & SNDE_LOSS_GRAD_K) && !a->grad_K) return SNDE_ERR_NULL;
-    if (a->B <= 0 || a->S <= 0 || a->num_scales <= 0 || a->num_scales > SNDE_MAX_SCALES) return SNDE_ERR_SHAPE;
-    if (a->S * a->num_scales > 64) return SNDE_ERR_SHAPE;     // finalize kernel: one thread per (source, scale)
-    const LossWorkspace lay = loss_ws_layout(a->B, a->S, a->num_scales);
-    if (!a->workspace || a->workspace_bytes < lay.end || ((uintptr_t)a->workspace & 15)) return SNDE_ERR_WORKSPACE;
-    DevLoss d; int64_t tiles = 0;
-    int rc = build_dev_loss(a, d, &lay, &tiles);
-    if (rc) return rc;
-    cudaStream_t st = as_stream(stream_);
-    const int B = a->B, S = a->S, ns = a->num_scales, N = B * S;
-    unsigned char *ws = (unsigned char *)a->workspace;
-    if (cudaMemsetAsync(ws + lay.gP, 0, lay.end - lay.gP, st) != cudaSuccess) return SNDE_ERR_CUDA;
-    PrepParams kp; FinalParams fp;
-    build_prep_final(a, kp, fp);
-    loss_prep_kernel<<<(ns * N + 127) / 128, 128, 0, st>>>(B, S, ns, a->poses, kp, (float *)(ws + lay.P), (float *)(ws + lay.Kinv));
-    SNDE_CHECK_LAUNCH();
-    const size_t smem = sizeof(TileSmem);
-    const bool grad = a->flags & SNDE_LOSS_GRAD, gradk = a->flags & SNDE_LOSS_GRAD_K;
-    // opt in to > 48 KB dynamic shared memory once per kernel variant and device (not a stream operation; kept out of
-    // the per-call path so the call can be captured into a CUDA graph after one eager warm-up)
-    static bool attr_done[4][64] = {};
-    int devi = 0;
-    cudaGetDevice(&devi);
-    auto launch = [&](auto kern, int variant) -> int {
-        if (devi < 0 || devi >= 64 || !attr_done[variant][devi]) {
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SNDE_ERR_CUDA;
-            if (devi >= 0 && devi < 64) attr_done[variant][devi] = true;
-        }
-        kern<<<(unsigned)tiles, TileCfg::NT, smem, st>>>(d);
-        return SNDE_OK;
-    };
-    // EXTRA variants honour masks / warped+error outputs / border padding / intrinsics gradients; the lean ones are the hot path
-    bool extra = gradk || a->padding_mode != SNDE_PAD_ZEROS;
-    for (int s = 0; s < ns; ++s) {
-        const SndeLossScale &in = a->scale[s];
-        extra = extra || in.mask_fwd.ptr || in.mask_bwd.ptr || in.warped_fwd.ptr || in.warped_bwd.ptr || in.err_fwd.ptr || in.err_bwd.ptr;
-    }
-    if (!grad) rc = extra ? launch(loss_tile_kernel<false, false, true>, 0) : launch(loss_tile_kernel<false, false, false>, 1);
-    else if (extra) rc = launch(loss_tile_kernel<true, true, true>, 2);
-    else rc = launch(loss_tile_kernel<true, false, false>, 3);
-    if (rc) return rc;
-    SNDE_CHECK_LAUNCH();
-    loss_final_kernel<<<B + 1, 64, 0, st>>>(B, S, ns, a->flags, a->poses, fp, (const double *)(ws + lay.gP),
-                                                           (const double *)(ws + lay.gKinv), (const double *)(ws + lay.loss),
-                                                           a->loss_out, a->grad_poses, a->grad_K);
-    SNDE_CHECK_LAUNCH();
-    return SNDE_OK;
-}
 
 // =============================================================================================
 // Reference-signature pieces

@@ -111,6 +111,14 @@ struct TileSmem {
 #define SNDE_THREADS_END }
 #endif
 
+// Pin a pointer in a register pair: stops the compiler from re-deriving it from (struct field + 64-bit offset) at
+// every use, so that base[int_offset] costs one IMAD.WIDE instead of a four-instruction 64-bit add-and-shift.
+#if defined(__CUDA_ARCH__)
+#define SNDE_PIN_PTR(p) asm volatile("" : "+l"(p))
+#else
+#define SNDE_PIN_PTR(p) ((void)0)
+#endif
+
 #if defined(__CUDACC__)
 #define SNDE_TILE_FN __device__ __forceinline__
 #else
@@ -211,15 +219,18 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
             const long long n0 = clsF ? (long long)b : m;
             sm.PK[0][tid] = tid < 12 ? ldg(sc.P + (n0 * 2 + (clsF ? 0 : 1)) * 12 + tid) : ldg(Kinv + tid - 12);
         }
+        const float *ob = own_base, *db = depth_base;
+        SNDE_PIN_PTR(ob); SNDE_PIN_PTR(db);
+        const int osc = own.sc, osh = own.sh, osw = own.sw, dsh = sc.depth.sh, dsw = sc.depth.sw;
         for (int idx = tid; idx < C::RH * C::RW; idx += C::NT) {
             const int r = idx >> 6, c = idx & 63;
             const int iy = ry0 + r, ix = rx0 + c;
             const bool in = iy >= 0 && iy < h && ix >= 0 && ix < w;
             float x0 = 0.f, x1 = 0.f, x2 = 0.f, d = 0.f;
             if (in) {
-                const float *q = own_base + iy * own.sh + ix * own.sw;
-                x0 = ldg(q); x1 = ldg(q + own.sc); x2 = ldg(q + 2 * own.sc);
-                d = ldg(depth_base + iy * sc.depth.sh + ix * sc.depth.sw);
+                const int q = iy * osh + ix * osw;
+                x0 = ldg(ob + q); x1 = ldg(ob + (q + osc)); x2 = ldg(ob + (q + 2 * osc));
+                d = ldg(db + (iy * dsh + ix * dsw));
             }
             sm.X[0][r][c] = x0; sm.X[1][r][c] = x1; sm.X[2][r][c] = x2; sm.D[r][c] = d;
         }
@@ -234,6 +245,7 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
         const DevImageOut &eout = clsF ? sc.err_fwd : sc.err_bwd;
         const bool has_mask = EXTRA && mask.p != nullptr;
         const float *PKs = sm.PK[k & 1];
+        const int oth_sc = oth.sc, oth_sh = oth.sh, oth_sw = oth.sw;
 
         // ---- phase A: reproject + sample every in-image region pixel ----
         SNDE_THREADS_BEGIN
@@ -246,20 +258,22 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
                 const long long n1 = (long long)(k + 1) * B + b;
                 sm.PK[(k + 1) & 1][tid] = tid < 12 ? ldg(sc.P + (n1 * 2) * 12 + tid) : ldg(Kinv + tid - 12);
             }
+            const float *obase = oth_base, *xtab = sc.xtab, *ytab = sc.ytab;
+            SNDE_PIN_PTR(obase); SNDE_PIN_PTR(xtab); SNDE_PIN_PTR(ytab);
             for (int idx = tid; idx < C::RH * C::RW; idx += C::NT) {
                 const int r = idx >> 6, c = idx & 63;
                 const int iy = ry0 + r, ix = rx0 + c;
                 const bool in = iy >= 0 && iy < h && ix >= 0 && ix < w;
                 float y0 = 0.f, y1 = 0.f, y2 = 0.f;
                 if (in) {
-                    const float xt = ldg(sc.xtab + ix), yt = ldg(sc.ytab + iy);
-                    Reproj rp; reproject(Ki, P, xt, yt, sm.D[r][c], rp);
+                    const float xt = ldg(xtab + ix), yt = ldg(ytab + iy);
+                    Reproj rp; reproject_fast(Ki, P, xt, yt, sm.D[r][c], rp);
                     float x, y; flow_coords(rp, xt, yt, x, y);
                     Taps tp;
                     if (EXTRA && p.padding) make_taps(x, y, h, w, p.padding, tp);
                     else make_taps_valid(x, y, tp);          // only used when the coordinate is valid (no clamp is active there)
-                    const int o00 = tp.y0 * oth.sh + tp.x0 * oth.sw, o01 = tp.y1 * oth.sh + tp.x0 * oth.sw;
-                    const int o10 = tp.y0 * oth.sh + tp.x1 * oth.sw, o11 = tp.y1 * oth.sh + tp.x1 * oth.sw;
+                    const int o00 = tp.y0 * oth_sh + tp.x0 * oth_sw, o01 = tp.y1 * oth_sh + tp.x0 * oth_sw;
+                    const int o10 = tp.y0 * oth_sh + tp.x1 * oth_sw, o11 = tp.y1 * oth_sh + tp.x1 * oth_sw;
                     const float w00 = tp.wx0 * tp.wy0, w01 = tp.wx0 * tp.wy1, w10 = tp.wx1 * tp.wy0, w11 = tp.wx1 * tp.wy1;
                     const bool inner = r >= 2 && r < C::TH + 2 && c >= 2 && c < C::RW - 2;
                     // Outside [0,w-1) x [0,h-1) the reference's clamped-corner weights cancel to zero (up to rounding
@@ -269,8 +283,9 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
                     if (valid) {
 #pragma unroll
                         for (int ch = 0; ch < 3; ++ch) {
-                            const float *bc = oth_base + ch * oth.sc;
-                            const float i00 = ldg(bc + o00), i01 = ldg(bc + o01), i10 = ldg(bc + o10), i11 = ldg(bc + o11);
+                            const int oc = ch * oth_sc;      // 32-bit offsets: one IMAD.WIDE per gather
+                            const float i00 = ldg(obase + (o00 + oc)), i01 = ldg(obase + (o01 + oc));
+                            const float i10 = ldg(obase + (o10 + oc)), i11 = ldg(obase + (o11 + oc));
                             yv[ch] = tap_blend_fma(w00, w01, w10, w11, i00, i01, i10, i11);
                             if (GRAD && inner) {
                                 float ddx, ddy; tap_derivs_fma(tp, i00, i01, i10, i11, ddx, ddy);
@@ -391,6 +406,8 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
                 for (int i = 0; i < 9; ++i) Ki[i] = PKs[12 + i];
 #pragma unroll
                 for (int i = 0; i < 12; ++i) rg.dP[i] = 0.f;
+                const float *xtab = sc.xtab, *ytab = sc.ytab;
+                SNDE_PIN_PTR(xtab); SNDE_PIN_PTR(ytab);
 #pragma unroll
                 for (int i = 0; i < C::PPT; ++i) {
                     const int idx = tid + i * C::NT;
@@ -400,7 +417,7 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
                     const float g0 = sm.Y[0][r][c], g1_ = sm.Y[1][r][c], g2 = sm.Y[2][r][c];
                     const float gx = fmaf(g2, sm.G[4][row][c], fmaf(g1_, sm.G[2][row][c], g0 * sm.G[0][row][c]));
                     const float gy = fmaf(g2, sm.G[5][row][c], fmaf(g1_, sm.G[3][row][c], g0 * sm.G[1][row][c]));
-                    const float xt = ldg(sc.xtab + ix), yt = ldg(sc.ytab + iy), d = sm.D[r][c];
+                    const float xt = ldg(xtab + ix), yt = ldg(ytab + iy), d = sm.D[r][c];
                     Reproj rp; reproject_nodiv(Ki, P, xt, yt, d, rp);
                     float gu[3], gcam[3];
                     rg.gd[i] += reproject_bwd_fast(P, rp, gx, gy, gu, gcam);
