@@ -101,6 +101,7 @@ struct TileSmem {
     float G[6][TileCfg::TH][TileCfg::RW];         // d(warped_c)/dx, /dy of the inner pixels
     float red[TileCfg::MAX_S + 1][TileCfg::NWARP][16];   // per-warp partial sums: slot k = dP of other k; last used slot = dKinv, err, smooth
     float PK[2][24];                              // P (12) and Kinv (9) of the current / next other image
+    float xt[TileCfg::RW], yt[TileCfg::RH];       // meshgrid tables of the region's columns / rows
 };
 
 #if defined(__CUDA_ARCH__)
@@ -219,6 +220,8 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
             const long long n0 = clsF ? (long long)b : m;
             sm.PK[0][tid] = tid < 12 ? ldg(sc.P + (n0 * 2 + (clsF ? 0 : 1)) * 12 + tid) : ldg(Kinv + tid - 12);
         }
+        if (tid < C::RW) { const int ix = rx0 + tid; sm.xt[tid] = (ix >= 0 && ix < w) ? ldg(sc.xtab + ix) : 0.f; }
+        else if (tid < C::RW + C::RH) { const int iy = ry0 + tid - C::RW; sm.yt[tid - C::RW] = (iy >= 0 && iy < h) ? ldg(sc.ytab + iy) : 0.f; }
         const float *ob = own_base, *db = depth_base;
         SNDE_PIN_PTR(ob); SNDE_PIN_PTR(db);
         const int osc = own.sc, osh = own.sh, osw = own.sw, dsh = sc.depth.sh, dsw = sc.depth.sw;
@@ -258,51 +261,75 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
                 const long long n1 = (long long)(k + 1) * B + b;
                 sm.PK[(k + 1) & 1][tid] = tid < 12 ? ldg(sc.P + (n1 * 2) * 12 + tid) : ldg(Kinv + tid - 12);
             }
-            const float *obase = oth_base, *xtab = sc.xtab, *ytab = sc.ytab;
-            SNDE_PIN_PTR(obase); SNDE_PIN_PTR(xtab); SNDE_PIN_PTR(ytab);
-            for (int idx = tid; idx < C::RH * C::RW; idx += C::NT) {
-                const int r = idx >> 6, c = idx & 63;
-                const int iy = ry0 + r, ix = rx0 + c;
-                const bool in = iy >= 0 && iy < h && ix >= 0 && ix < w;
-                float y0 = 0.f, y1 = 0.f, y2 = 0.f;
-                if (in) {
-                    const float xt = ldg(xtab + ix), yt = ldg(ytab + iy);
-                    Reproj rp; reproject_fast(Ki, P, xt, yt, sm.D[r][c], rp);
-                    float x, y; flow_coords(rp, xt, yt, x, y);
-                    Taps tp;
-                    if (EXTRA && p.padding) make_taps(x, y, h, w, p.padding, tp);
-                    else make_taps_valid(x, y, tp);          // only used when the coordinate is valid (no clamp is active there)
-                    const int o00 = tp.y0 * oth_sh + tp.x0 * oth_sw, o01 = tp.y1 * oth_sh + tp.x0 * oth_sw;
-                    const int o10 = tp.y0 * oth_sh + tp.x1 * oth_sw, o11 = tp.y1 * oth_sh + tp.x1 * oth_sw;
-                    const float w00 = tp.wx0 * tp.wy0, w01 = tp.wx0 * tp.wy1, w10 = tp.wx1 * tp.wy0, w11 = tp.wx1 * tp.wy1;
-                    const bool inner = r >= 2 && r < C::TH + 2 && c >= 2 && c < C::RW - 2;
-                    // Outside [0,w-1) x [0,h-1) the reference's clamped-corner weights cancel to zero (up to rounding
-                    // residue that grows with the distance from the image); the fused path writes the exact zero.
-                    const bool valid = (EXTRA && p.padding) ? true : tap_valid(x, y, h, w, 0) != 0.f;   // border mode samples everywhere
+            const float *obase = oth_base;
+            SNDE_PIN_PTR(obase);
+            // Two region pixels per iteration: both coordinate chains first, then all 24 gathers back to back (memory-level
+            // parallelism: the gathers are the long-latency part of the tile), then the blends.
+            for (int idx0 = tid; idx0 < C::RH * C::RW; idx0 += 2 * C::NT) {
+                int rr[2], cc[2], o00[2], o01[2], o10[2], o11[2];
+                bool in[2], valid[2], inner[2];
+                Taps tp[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int idx = idx0 + j * C::NT;
+                    const int r = idx >> 6, c = idx & 63;
+                    rr[j] = r; cc[j] = c;
+                    const int iy = ry0 + r, ix = rx0 + c;
+                    in[j] = idx < C::RH * C::RW && iy >= 0 && iy < h && ix >= 0 && ix < w;
+                    valid[j] = false; inner[j] = false;
+                    o00[j] = o01[j] = o10[j] = o11[j] = 0;
+                    if (in[j]) {
+                        const float xt = sm.xt[c], yt = sm.yt[r];
+                        Reproj rp; reproject_fast(Ki, P, xt, yt, sm.D[r][c], rp);
+                        float x, y; flow_coords(rp, xt, yt, x, y);
+                        // Outside [0,w-1) x [0,h-1) the reference's clamped-corner weights cancel to zero (up to rounding
+                        // residue that grows with the distance from the image); the fused path writes the exact zero.
+                        if (EXTRA && p.padding) { make_taps(x, y, h, w, p.padding, tp[j]); valid[j] = true; }   // border mode samples everywhere
+                        else { make_taps_valid(x, y, tp[j]); valid[j] = tap_valid(x, y, h, w, 0) != 0.f; }
+                        inner[j] = r >= 2 && r < C::TH + 2 && c >= 2 && c < C::RW - 2;
+                        if (valid[j]) {
+                            o00[j] = tp[j].y0 * oth_sh + tp[j].x0 * oth_sw; o01[j] = tp[j].y1 * oth_sh + tp[j].x0 * oth_sw;
+                            o10[j] = tp[j].y0 * oth_sh + tp[j].x1 * oth_sw; o11[j] = tp[j].y1 * oth_sh + tp[j].x1 * oth_sw;
+                        }
+                    }
+                }
+                float v[2][12];
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const int oc = ch * oth_sc;          // 32-bit offsets: one IMAD.WIDE per gather
+                        v[j][4 * ch + 0] = valid[j] ? ldg(obase + (o00[j] + oc)) : 0.f;
+                        v[j][4 * ch + 1] = valid[j] ? ldg(obase + (o01[j] + oc)) : 0.f;
+                        v[j][4 * ch + 2] = valid[j] ? ldg(obase + (o10[j] + oc)) : 0.f;
+                        v[j][4 * ch + 3] = valid[j] ? ldg(obase + (o11[j] + oc)) : 0.f;
+                    }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (idx0 + j * C::NT >= C::RH * C::RW) continue;
+                    const int r = rr[j], c = cc[j];
                     float yv[3] = {0.f, 0.f, 0.f};
-                    if (valid) {
+                    if (valid[j]) {
+                        const float w00 = tp[j].wx0 * tp[j].wy0, w01 = tp[j].wx0 * tp[j].wy1, w10 = tp[j].wx1 * tp[j].wy0, w11 = tp[j].wx1 * tp[j].wy1;
 #pragma unroll
                         for (int ch = 0; ch < 3; ++ch) {
-                            const int oc = ch * oth_sc;      // 32-bit offsets: one IMAD.WIDE per gather
-                            const float i00 = ldg(obase + (o00 + oc)), i01 = ldg(obase + (o01 + oc));
-                            const float i10 = ldg(obase + (o10 + oc)), i11 = ldg(obase + (o11 + oc));
+                            const float i00 = v[j][4 * ch], i01 = v[j][4 * ch + 1], i10 = v[j][4 * ch + 2], i11 = v[j][4 * ch + 3];
                             yv[ch] = tap_blend_fma(w00, w01, w10, w11, i00, i01, i10, i11);
-                            if (GRAD && inner) {
-                                float ddx, ddy; tap_derivs_fma(tp, i00, i01, i10, i11, ddx, ddy);
+                            if (GRAD && inner[j]) {
+                                float ddx, ddy; tap_derivs_fma(tp[j], i00, i01, i10, i11, ddx, ddy);
                                 sm.G[2 * ch][r - 2][c] = ddx; sm.G[2 * ch + 1][r - 2][c] = ddy;
                             }
                         }
-                    } else if (GRAD && inner) {
+                    } else if (GRAD && inner[j]) {
 #pragma unroll
                         for (int q = 0; q < 6; ++q) sm.G[q][r - 2][c] = 0.f;
                     }
-                    y0 = yv[0]; y1 = yv[1]; y2 = yv[2];
-                    if (EXTRA && inner && wout.p) {
-                        float *o = wout.p + n * wout.sn + iy * wout.sh + ix * wout.sw;
-                        o[0] = y0; o[wout.sc] = y1; o[2 * wout.sc] = y2;
+                    if (EXTRA && inner[j] && wout.p) {
+                        float *o = wout.p + n * wout.sn + (ry0 + r) * wout.sh + (rx0 + c) * wout.sw;
+                        o[0] = yv[0]; o[wout.sc] = yv[1]; o[2 * wout.sc] = yv[2];
                     }
+                    sm.Y[0][r][c] = yv[0]; sm.Y[1][r][c] = yv[1]; sm.Y[2][r][c] = yv[2];
                 }
-                sm.Y[0][r][c] = y0; sm.Y[1][r][c] = y1; sm.Y[2][r][c] = y2;
             }
         SNDE_THREADS_END
 
@@ -406,8 +433,6 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
                 for (int i = 0; i < 9; ++i) Ki[i] = PKs[12 + i];
 #pragma unroll
                 for (int i = 0; i < 12; ++i) rg.dP[i] = 0.f;
-                const float *xtab = sc.xtab, *ytab = sc.ytab;
-                SNDE_PIN_PTR(xtab); SNDE_PIN_PTR(ytab);
 #pragma unroll
                 for (int i = 0; i < C::PPT; ++i) {
                     const int idx = tid + i * C::NT;
@@ -417,7 +442,7 @@ SNDE_TILE_FN void loss_tile(const DevLoss &p, int block_id, TileSmem &sm, Regs *
                     const float g0 = sm.Y[0][r][c], g1_ = sm.Y[1][r][c], g2 = sm.Y[2][r][c];
                     const float gx = fmaf(g2, sm.G[4][row][c], fmaf(g1_, sm.G[2][row][c], g0 * sm.G[0][row][c]));
                     const float gy = fmaf(g2, sm.G[5][row][c], fmaf(g1_, sm.G[3][row][c], g0 * sm.G[1][row][c]));
-                    const float xt = ldg(xtab + ix), yt = ldg(ytab + iy), d = sm.D[r][c];
+                    const float xt = sm.xt[c], yt = sm.yt[r], d = sm.D[r][c];
                     Reproj rp; reproject_nodiv(Ki, P, xt, yt, d, rp);
                     float gu[3], gcam[3];
                     rg.gd[i] += reproject_bwd_fast(P, rp, gx, gy, gu, gcam);
