@@ -1,0 +1,48 @@
+// Micro-benchmark: issue rate of FFMA vs FFMA2 / FADD2 / FMUL2 (packed fp32 pairs, sm_100a) and of SHFL / LDS mixes.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o f32x2 f32x2.cu && ./f32x2
+#include <cstdio>
+#include <cuda_runtime.h>
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack(float a, float b) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack(u64 v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) { u64 d; asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) { u64 d; asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+#define ILP 8
+template <int MODE> __global__ void k(float *out, int iters, float s) {
+    float a[ILP]; u64 p[ILP];
+    for (int i = 0; i < ILP; ++i) { a[i] = threadIdx.x * 1e-3f + i; p[i] = pack(a[i], a[i] + 1.f); }
+    const u64 ps = pack(s, s * 0.5f), pt = pack(1e-3f, 2e-3f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            if (MODE == 0) a[i] = fmaf(a[i], s, 1e-3f);
+            if (MODE == 1) p[i] = ffma2(p[i], ps, pt);
+            if (MODE == 2) p[i] = fadd2(p[i], pt);
+            if (MODE == 3) p[i] = fmul2(p[i], ps);
+            if (MODE == 4) { a[i] = fmaf(a[i], s, 1e-3f); p[i] = ffma2(p[i], ps, pt); }   // mix 1:1
+            if (MODE == 5) a[i] = __shfl_xor_sync(0xffffffffu, a[i], 1) + 1e-3f;        // SHFL + FADD
+            if (MODE == 6) { float r; asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a[i])); a[i] = r; }
+        }
+    }
+    float acc = 0.f;
+    for (int i = 0; i < ILP; ++i) { float x, y; unpack(p[i], x, y); acc += a[i] + x + y; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+template <int MODE> void run(const char *name, int per_iter_inst) {
+    float *out; cudaMalloc(&out, 148 * 8 * 1024 * 4);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 20000, blocks = 148 * 2, threads = 512;
+    k<MODE><<<blocks, threads>>>(out, 100, 0.999f);
+    cudaEventRecord(e0); k<MODE><<<blocks, threads>>>(out, iters, 0.999f); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    double winst = (double)blocks * threads / 32 * iters * ILP * per_iter_inst;
+    int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+    printf("%-28s %8.3f ms  %7.1f G warp-inst/s  = %.2f warp-inst/clk/SM at %d MHz (nominal)\n", name, ms, winst / ms / 1e6,
+           winst / (ms * 1e-3) / 148 / (clk * 1e3), clk / 1000);
+    cudaFree(out);
+}
+int main() {
+    run<0>("FFMA", 1); run<1>("FFMA2", 1); run<2>("FADD2", 1); run<3>("FMUL2", 1); run<4>("FFMA+FFMA2", 2); run<5>("SHFL+FADD", 2); run<6>("MUFU.RCP", 1);
+    return 0;
+}
