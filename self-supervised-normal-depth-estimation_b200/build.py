@@ -20,7 +20,7 @@ LIB = os.path.join(HERE, "libsnde.so")
 # (source, fp-contraction flag): the fused kernel spells out its exact-order arithmetic, the reference-signature
 # kernels follow the reference op by op
 SOURCES = [("snde_fused.cu", "-fmad=true"), ("snde_ops.cu", "-fmad=false")]
-HEADERS = ["snde_math.cuh", "snde_tile.cuh", "snde_loss_setup.cuh"]
+HEADERS = ["snde_math.cuh", "snde_strip.cuh", "snde_loss_setup.cuh"]
 
 
 def nvcc_path() -> str:

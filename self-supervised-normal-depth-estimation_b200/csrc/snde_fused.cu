@@ -6,10 +6,14 @@
 #include <string.h>
 
 #include "snde.h"
-#include "snde_tile.cuh"
+#include "snde_strip.cuh"
 #include "snde_loss_setup.cuh"
 
 using namespace snde;
+
+#ifndef SNDE_STRIP_CTAS_PER_SM
+#define SNDE_STRIP_CTAS_PER_SM 3
+#endif
 
 #define SNDE_CHECK_LAUNCH() do { if (cudaGetLastError() != cudaSuccess) return SNDE_ERR_CUDA; } while (0)
 
@@ -95,12 +99,21 @@ __global__ void __launch_bounds__(64) loss_final_kernel(int B, int S, int ns, in
     }
 }
 
-template <bool GRAD, bool GRADK, bool EXTRA>
-__global__ void __launch_bounds__(TileCfg::NT, 2) loss_tile_kernel(const __grid_constant__ DevLoss p) {
+// Persistent grid: every warp pulls strip tasks from a counter until none is left.  The warps of a CTA share nothing
+// (the shared-memory rows are lane-private), so there is no CTA-wide barrier in the kernel.
+template <bool GRAD, bool GRADK, bool EXTRA, bool FAST>
+__global__ void __launch_bounds__(StripCfg::NT, SNDE_STRIP_CTAS_PER_SM) loss_strip_kernel(const __grid_constant__ DevLoss p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
-    Regs regs;
-    loss_tile<GRAD, GRADK, EXTRA>(p, (int)blockIdx.x, sm, &regs);
+    const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5;
+    StripSmem &sm = reinterpret_cast<StripSmem *>(smem_raw)[warp];
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(p.counter, 1);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= p.total_tasks) break;
+        strip_task<GRAD, GRADK, EXTRA, FAST>(p, task, lane, sm);
+        __syncwarp();
+    }
 }
 
 extern "C" size_t snde_sizeof_loss_args(void) { return sizeof(SndeLossArgs); }
@@ -139,30 +152,45 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     build_prep_final(a, kp, fp);
     loss_prep_kernel<<<(ns * N + 127) / 128, 128, 0, st>>>(B, S, ns, a->poses, kp, (float *)(ws + lay.P), (float *)(ws + lay.Kinv));
     SNDE_CHECK_LAUNCH();
-    const size_t smem = sizeof(TileSmem);
+    const size_t smem = sizeof(StripSmem) * StripCfg::WARPS;
     const bool grad = a->flags & SNDE_LOSS_GRAD, gradk = a->flags & SNDE_LOSS_GRAD_K;
     // opt in to > 48 KB dynamic shared memory once per kernel variant and device (not a stream operation; kept out of
     // the per-call path so the call can be captured into a CUDA graph after one eager warm-up)
-    static bool attr_done[4][64] = {};
+    static bool attr_done[8][64] = {};
+    static int sm_count[64] = {};
     int devi = 0;
     cudaGetDevice(&devi);
+    if (devi < 0 || devi >= 64) return SNDE_ERR_CUDA;
+    if (!sm_count[devi]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, devi) != cudaSuccess || n <= 0) return SNDE_ERR_CUDA;
+        sm_count[devi] = n;
+    }
+    // persistent grid: as many CTAs as fit, but no more warps than tasks
+    long long ctas = (long long)sm_count[devi] * SNDE_STRIP_CTAS_PER_SM;
+    const long long need = (tiles + StripCfg::WARPS - 1) / StripCfg::WARPS;
+    if (ctas > need) ctas = need;
     auto launch = [&](auto kern, int variant) -> int {
-        if (devi < 0 || devi >= 64 || !attr_done[variant][devi]) {
+        if (!attr_done[variant][devi]) {
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SNDE_ERR_CUDA;
-            if (devi >= 0 && devi < 64) attr_done[variant][devi] = true;
+            attr_done[variant][devi] = true;
         }
-        kern<<<(unsigned)tiles, TileCfg::NT, smem, st>>>(d);
+        kern<<<(unsigned)ctas, StripCfg::NT, smem, st>>>(d);
         return SNDE_OK;
     };
-    // EXTRA variants honour masks / warped+error outputs / border padding / intrinsics gradients; the lean ones are the hot path
-    bool extra = gradk || a->padding_mode != SNDE_PAD_ZEROS;
+    // EXTRA variants honour masks / warped+error outputs / border padding / intrinsics gradients; FAST ones need planar,
+    // aligned tensors at every scale.  The lean fast one is the hot path.
+    bool extra = gradk || a->padding_mode != SNDE_PAD_ZEROS, fast = true;
     for (int s = 0; s < ns; ++s) {
         const SndeLossScale &in = a->scale[s];
         extra = extra || in.mask_fwd.ptr || in.mask_bwd.ptr || in.warped_fwd.ptr || in.warped_bwd.ptr || in.err_fwd.ptr || in.err_bwd.ptr;
+        fast = fast && d.sc[s].fast;
     }
-    if (!grad) rc = extra ? launch(loss_tile_kernel<false, false, true>, 0) : launch(loss_tile_kernel<false, false, false>, 1);
-    else if (extra) rc = launch(loss_tile_kernel<true, true, true>, 2);
-    else rc = launch(loss_tile_kernel<true, false, false>, 3);
+    if (!grad) {
+        if (extra) rc = launch(loss_strip_kernel<false, false, true, false>, 0);
+        else rc = fast ? launch(loss_strip_kernel<false, false, false, true>, 1) : launch(loss_strip_kernel<false, false, false, false>, 2);
+    } else if (extra) rc = launch(loss_strip_kernel<true, true, true, false>, 3);
+    else rc = fast ? launch(loss_strip_kernel<true, false, false, true>, 4) : launch(loss_strip_kernel<true, false, false, false>, 5);
     if (rc) return rc;
     SNDE_CHECK_LAUNCH();
     loss_final_kernel<<<B + 1, 64, 0, st>>>(B, S, ns, a->flags, a->poses, fp, (const double *)(ws + lay.gP),

@@ -1,11 +1,11 @@
 // snde_loss_setup.cuh -- host-side setup of the fused loss (argument validation, workspace layout,
-// work table) and the per-thread bodies of its two tiny companion kernels (matrix prep, finalize).
+// task table) and the per-thread bodies of its two tiny companion kernels (matrix prep, finalize).
 // Shared by snde_kernels.cu (the product) and the host-emulation test harness.
 #pragma once
 #include <string.h>
 
 #include "snde.h"
-#include "snde_tile.cuh"
+#include "snde_strip.cuh"
 
 namespace snde {
 
@@ -23,8 +23,8 @@ static inline bool fits32(int64_t sc, int64_t sh, int64_t sw, int h, int w) {
 // =============================================================================================
 // Fused loss
 // =============================================================================================
-struct LossWorkspace {   // offsets in bytes
-    size_t P, Kinv, gP, gKinv, loss, end;
+struct LossWorkspace {   // offsets in bytes; [gP, end) is zeroed at the start of every call
+    size_t P, Kinv, gP, gKinv, loss, counter, end;
 };
 static inline LossWorkspace loss_ws_layout(int B, int S, int ns) {
     LossWorkspace o;
@@ -35,7 +35,8 @@ static inline LossWorkspace loss_ws_layout(int B, int S, int ns) {
     o.gP = up(o.Kinv + sizeof(float) * ns * B * 9);
     o.gKinv = up(o.gP + sizeof(double) * ns * N * 24);
     o.loss = up(o.gKinv + sizeof(double) * ns * B * 9);
-    o.end = up(o.loss + sizeof(double) * ns * 4);
+    o.counter = up(o.loss + sizeof(double) * ns * 4);
+    o.end = up(o.counter + sizeof(int) * 4);
     return o;
 }
 
@@ -115,10 +116,10 @@ static inline void loss_final_host(int B, int S, int ns, int flags, const float 
     }
 }
 
-static inline int build_dev_loss(const SndeLossArgs *a, DevLoss &d, const LossWorkspace *lay, int64_t *num_tiles) {
+static inline int build_dev_loss(const SndeLossArgs *a, DevLoss &d, const LossWorkspace *lay, int64_t *num_tiles, int seg_rows = 0) {
     if (!a) return SNDE_ERR_NULL;
     if (a->B <= 0 || a->S <= 0 || a->num_scales <= 0 || a->num_scales > SNDE_MAX_SCALES) return SNDE_ERR_SHAPE;
-    if (a->S > TileCfg::MAX_S) return SNDE_ERR_SHAPE;        // SNDE_MAX_SOURCES
+    if (a->S > StripCfg::MAX_S) return SNDE_ERR_SHAPE;       // SNDE_MAX_SOURCES
     if (a->padding_mode != SNDE_PAD_ZEROS && a->padding_mode != SNDE_PAD_BORDER) return SNDE_ERR_ARG;
     if (a->flags & ~15) return SNDE_ERR_ARG;
     if ((a->flags & SNDE_LOSS_GRAD_K) && !(a->flags & SNDE_LOSS_GRAD)) return SNDE_ERR_ARG;
@@ -143,8 +144,22 @@ static inline int build_dev_loss(const SndeLossArgs *a, DevLoss &d, const LossWo
             !fits32(in.err_fwd.sc, in.err_fwd.sh, in.err_fwd.sw, in.h, in.w) || !fits32(in.err_bwd.sc, in.err_bwd.sh, in.err_bwd.sw, in.h, in.w))
             return SNDE_ERR_TOO_LARGE;
         o.h = in.h; o.w = in.w;
-        o.tiles_x = (in.w + TileCfg::TW - 1) / TileCfg::TW;
-        o.tiles_y = (in.h + TileCfg::TH - 1) / TileCfg::TH;
+        o.seg_h = seg_rows > 0 ? seg_rows : StripCfg::SEG;
+        if (o.seg_h > in.h) o.seg_h = in.h;
+        o.tiles_x = (in.w + StripCfg::TW - 1) / StripCfg::TW;
+        o.tiles_y = (in.h + o.seg_h - 1) / o.seg_h;
+        // fast path: planar tensors, unit x-stride, even row / plane / batch strides and 8-byte aligned bases, even width:
+        // the lane's pixel pair is then one aligned 64-bit access everywhere
+        {
+            auto even = [](int64_t v) { return (v & 1) == 0; };
+            auto al8 = [](const void *q) { return ((uintptr_t)q & 7) == 0; };
+            bool f = (in.w & 1) == 0;
+            f = f && in.tgt.sw == 1 && even(in.tgt.sh) && even(in.tgt.sc) && even(in.tgt.sn) && al8(in.tgt.ptr);
+            f = f && in.src.sw == 1 && even(in.src.sh) && even(in.src.sc) && even(in.src.sn) && al8(in.src.ptr);
+            f = f && in.depth.sw == 1 && even(in.depth.sh) && even(in.depth.sn) && al8(in.depth.ptr);
+            if (a->flags & SNDE_LOSS_GRAD) f = f && in.grad_depth.sw == 1 && even(in.grad_depth.sh) && even(in.grad_depth.sn) && al8(in.grad_depth.ptr);
+            o.fast = f ? 1 : 0;
+        }
         o.tgt = dev(in.tgt); o.src = dev(in.src); o.depth = dev(in.depth); o.gdepth = dev(in.grad_depth);
         o.xtab = in.xtab; o.ytab = in.ytab;
         if (lay) {
@@ -161,7 +176,8 @@ static inline int build_dev_loss(const SndeLossArgs *a, DevLoss &d, const LossWo
         o.warped_fwd = dev(in.warped_fwd); o.warped_bwd = dev(in.warped_bwd);
         o.err_fwd = dev(in.err_fwd); o.err_bwd = dev(in.err_bwd);
     }
-    // work table: the heavy class-F items (S warps each) first, then the class-R items
+    if (lay) d.counter = (int *)(ws + lay->counter);
+    // work table: the heavy class-F tasks (S passes each) first, then the class-R tasks
     long long total = 0;
     int ne = 0;
     for (int cls = 0; cls < 2; ++cls)
@@ -172,6 +188,7 @@ static inline int build_dev_loss(const SndeLossArgs *a, DevLoss &d, const LossWo
             total += cnt;
         }
     d.num_entries = ne;
+    d.total_tasks = (int)total;
     if (num_tiles) *num_tiles = total;
     return SNDE_OK;
 }

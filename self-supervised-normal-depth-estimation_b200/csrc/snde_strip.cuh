@@ -1,0 +1,708 @@
+// snde_strip.cuh -- the fused loss as a STREAMING STRIP PROGRAM: one warp = one vertical strip of one "owner" image.
+//
+// Work decomposition.  Every image of the step owns exactly one depth map:
+//   class F task: owner = target image b; "others" = its S source images, projected with
+//                 P = K4 @ T_k               (the reference's fwd direction, baseline.py:903-906)
+//   class R task: owner = source image n = k*B + b; other = the target image b, projected with
+//                 P = K4 @ inverse(T_k)      (the bwd direction, baseline.py:909-913)
+// A task is (owner, strip of 60 columns, segment of seg_h rows).  The warp walks DOWN the strip one row per step;
+// lane l owns the two adjacent region columns 2l, 2l+1 (region = the 60 inner columns + a 2-column halo each side).
+// Per step t, all in registers / lane-private shared memory, no CTA barrier anywhere:
+//   A  row t  : reproject the lane's two pixels with the owner's depth, 4-tap gather of the other image -> warped row
+//               (+ the tap derivatives, kept for phase G two steps later)
+//   B  row t-1: SSIM over the 3x3 window from rolling row sums (horizontal neighbours by shuffle, vertical by two
+//               carried rows), error value, and the three backward coefficient maps of that row
+//   C  row t-2: 3x3 box sums of the coefficient maps (same rolling scheme) -> dL/d(warped)
+//   G  row t-2: dot with the tap derivatives, back through the projection -> d/d(depth), d/dP, d/dKinv
+//   S  row t-2: (first pass only) the owner's edge-aware smoothness pairs and their depth gradient
+// Each depth-gradient element is written by exactly one lane (passes over the S others of a class-F owner add to
+// it in a fixed order), so the gradient is deterministic; only the per-sample 3x4 / 3x3 sums and the loss scalars
+// go through (double-precision) atomics.
+//
+// The code is per-lane ("SIMT") code.  On the GPU the neighbour exchange is __shfl_*_sync; under the host-emulation
+// test harness (g++, tests/host_emul) the 32 lanes are fibers and the exchange goes through a slot array, which lets
+// the strip logic be checked against the oracle without a GPU.  The product never runs the host variant.
+#pragma once
+#include "snde_math.cuh"
+
+#ifndef SNDE_MAX_SCALES
+#define SNDE_MAX_SCALES 6
+#endif
+
+namespace snde {
+
+struct StripCfg {
+    static constexpr int RW = 64;        // region columns of a strip (32 lanes x 2 columns)
+    static constexpr int TW = RW - 4;    // inner columns (60)
+    static constexpr int SEG = 32;       // default rows per segment
+    static constexpr int RING = 4;       // rows kept in the lane-private ring (rows t, t-1, t-2 are live)
+    static constexpr int WARPS = 4;      // warps per CTA (independent of each other)
+    static constexpr int NT = WARPS * 32;
+    static constexpr int MAX_S = 8;      // most source views per target (SNDE_MAX_SOURCES)
+};
+
+struct DevImage { const float *p; long long sn; int sc, sh, sw, pad_; };
+struct DevImageOut { float *p; long long sn; int sc, sh, sw, pad_; };
+struct DevMap { const float *p; long long sn; int sh, sw; };
+struct DevMapOut { float *p; long long sn; int sh, sw; };
+
+struct DevScale {
+    int h, w, tiles_x, tiles_y;      // tiles_x = strips per row, tiles_y = segments per column
+    int seg_h, fast;                 // rows per segment; fast != 0: every tensor of this scale is planar, unit x-stride, 8-byte aligned rows
+    DevImage tgt, src;
+    DevMap depth;
+    DevMapOut gdepth;
+    const float *xtab, *ytab;
+    const float *P;        // workspace [N][2][12]  (dir 0: K4@T, dir 1: K4@inv(T))
+    const float *Kinv;     // workspace [B][9]
+    double *gP;            // workspace [N][2][12]
+    double *gKinv;         // workspace [B][9]
+    double *loss;          // workspace [4]: sum fwd err, sum bwd err, sum |dx wx|, sum |dy wy|
+    float gphoto;          // photo_weight / (N*h*w*3): upstream gradient of every error-map element
+    float gsx, gsy;        // smooth_weight / (M*h*(w-1)),  / (M*(h-1)*w)
+    int pad_;
+    DevMap mask_fwd, mask_bwd;
+    DevImageOut warped_fwd, warped_bwd, err_fwd, err_bwd;
+};
+
+struct DevEntry { int begin, count, scale, cls; };   // cls 0 = F tasks, 1 = R tasks
+
+struct DevLoss {
+    int B, S, num_scales, flags, padding, num_entries;
+    float alpha, oma;
+    int total_tasks, pad_;
+    int *counter;                    // workspace: next task to hand out (zeroed per call)
+    DevEntry entry[2 * SNDE_MAX_SCALES];
+    DevScale sc[SNDE_MAX_SCALES];
+};
+
+enum { FLAG_GRAD = 1, FLAG_GRAD_K = 2, FLAG_NO_PHOTO = 4, FLAG_NO_SMOOTH = 8 };   // == SNDE_LOSS_* in include/snde.h
+
+// lane-private rows (a register-file extension: no lane ever reads another lane's slot)
+struct StripSmem {
+    F2 X[StripCfg::RING][3][32];     // owner image rows, 0 outside the image (= the pools' zero padding)
+    F2 Y[StripCfg::RING][3][32];     // warped other image rows, 0 outside the image
+    F2 D[StripCfg::RING][32];        // owner depth rows
+    F2 G[StripCfg::RING][6][32];     // d(warped_c)/dx, /dy
+};
+
+#if defined(__CUDACC__)
+#define SNDE_STRIP_FN __device__ __forceinline__
+#else
+#define SNDE_STRIP_FN inline
+#endif
+
+// ---------------------------------------------------------------------------------------------------------------
+// warp primitives
+// ---------------------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+// from_left[i] = to_right[i] of lane-1, from_right[i] = to_left[i] of lane+1 (own value at the warp's edges)
+template <int N>
+SNDE_STRIP_FN void neighbor_exchange(int, const float (&to_right)[N], const float (&to_left)[N], float (&from_left)[N], float (&from_right)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        from_left[i] = __shfl_up_sync(0xffffffffu, to_right[i], 1);
+        from_right[i] = __shfl_down_sync(0xffffffffu, to_left[i], 1);
+    }
+}
+template <int N>
+SNDE_STRIP_FN void take_from_right(int, const float (&to_left)[N], float (&from_right)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) from_right[i] = __shfl_down_sync(0xffffffffu, to_left[i], 1);
+}
+template <int N>
+SNDE_STRIP_FN void take_from_left(int, const float (&to_right)[N], float (&from_left)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) from_left[i] = __shfl_up_sync(0xffffffffu, to_right[i], 1);
+}
+// sum over the warp of N per-lane values; the totals come back in every lane
+template <int N>
+SNDE_STRIP_FN void warp_sum(int, float (&v)[N]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+}
+SNDE_STRIP_FN void atomic_add_double(double *dst, double v) { atomicAdd(dst, v); }
+#else
+// host emulation (tests/host_emul/emul.cpp): 32 fibers; slots are double-buffered, one yield per exchange
+float *host_warp_slots(int lane, int parity);       // 64 floats per lane and parity
+void host_warp_yield();
+int &host_warp_parity(int lane);
+template <int N>
+SNDE_STRIP_FN void neighbor_exchange(int lane, const float (&to_right)[N], const float (&to_left)[N], float (&from_left)[N], float (&from_right)[N]) {
+    static_assert(2 * N <= 64, "slot array too small");
+    const int par = host_warp_parity(lane);
+    float *mine = host_warp_slots(lane, par);
+    for (int i = 0; i < N; ++i) { mine[i] = to_right[i]; mine[N + i] = to_left[i]; }
+    host_warp_yield();
+    const float *l = host_warp_slots(lane > 0 ? lane - 1 : lane, par), *r = host_warp_slots(lane < 31 ? lane + 1 : lane, par);
+    for (int i = 0; i < N; ++i) { from_left[i] = l[i]; from_right[i] = r[N + i]; }
+    host_warp_parity(lane) = par ^ 1;
+}
+template <int N>
+SNDE_STRIP_FN void take_from_right(int lane, const float (&to_left)[N], float (&from_right)[N]) {
+    float zr[N], fl[N];
+    for (int i = 0; i < N; ++i) zr[i] = 0.f;
+    neighbor_exchange<N>(lane, zr, to_left, fl, from_right);
+}
+template <int N>
+SNDE_STRIP_FN void take_from_left(int lane, const float (&to_right)[N], float (&from_left)[N]) {
+    float zl[N], fr[N];
+    for (int i = 0; i < N; ++i) zl[i] = 0.f;
+    neighbor_exchange<N>(lane, to_right, zl, from_left, fr);
+}
+template <int N>
+SNDE_STRIP_FN void warp_sum(int lane, float (&v)[N]) {
+    static_assert(N <= 64, "slot array too small");
+    const int par = host_warp_parity(lane);
+    float *mine = host_warp_slots(lane, par);
+    for (int i = 0; i < N; ++i) mine[i] = v[i];
+    host_warp_yield();
+    for (int i = 0; i < N; ++i) {
+        float part[32];
+        for (int l = 0; l < 32; ++l) part[l] = host_warp_slots(l, par)[i];
+        for (int o = 16; o > 0; o >>= 1) for (int l = 0; l < o; ++l) part[l] += part[l + o];   // same pairing as the xor butterfly
+        v[i] = part[0];
+    }
+    host_warp_parity(lane) = par ^ 1;
+}
+SNDE_STRIP_FN void atomic_add_double(double *dst, double v) { *dst += v; }
+#endif
+
+#if defined(__CUDA_ARCH__)
+SNDE_STRIP_FN F2 ldg2(const float *p) { const float2 v = __ldg(reinterpret_cast<const float2 *>(p)); return F2{v.x, v.y}; }
+#else
+SNDE_STRIP_FN F2 ldg2(const float *p) { return F2{p[0], p[1]}; }
+#endif
+
+// Pin a pointer in a register pair: stops the compiler from re-deriving it from (struct field + 64-bit offset) at
+// every use, so that base[int_offset] costs one IMAD.WIDE instead of a four-instruction 64-bit add-and-shift.
+#if defined(__CUDA_ARCH__)
+#define SNDE_PIN_PTR(p) asm volatile("" : "+l"(p))
+#else
+#define SNDE_PIN_PTR(p) ((void)0)
+#endif
+
+// horizontal 3-sums of one row for the lane's two columns (same association as the reference-order tile program:
+// left column = left neighbour + (a + b), right column = (a + b) + right neighbour)
+struct HS { F2 x, y, xx, yy, xy; };
+struct CS { F2 a, b, c; };
+
+SNDE_STRIP_FN void hsum_row(const F2 xv, const F2 yv, float xm, float xp, float ym, float yp, HS &o) {
+    const float tx = xv.x + xv.y, ty = yv.x + yv.y;
+    const float txx = fmaf(xv.y, xv.y, xv.x * xv.x), tyy = fmaf(yv.y, yv.y, yv.x * yv.x), txy = fmaf(xv.y, yv.y, xv.x * yv.x);
+    o.x.x = xm + tx;             o.x.y = tx + xp;
+    o.y.x = ym + ty;             o.y.y = ty + yp;
+    o.xx.x = fmaf(xm, xm, txx);  o.xx.y = fmaf(xp, xp, txx);
+    o.yy.x = fmaf(ym, ym, tyy);  o.yy.y = fmaf(yp, yp, tyy);
+    o.xy.x = fmaf(xm, ym, txy);  o.xy.y = fmaf(xp, yp, txy);
+}
+SNDE_STRIP_FN F2 add2(const F2 a, const F2 b) { return F2{a.x + b.x, a.y + b.y}; }
+SNDE_STRIP_FN void hs_add(const HS &a, const HS &b, HS &o) {
+    o.x = add2(a.x, b.x); o.y = add2(a.y, b.y); o.xx = add2(a.xx, b.xx); o.yy = add2(a.yy, b.yy); o.xy = add2(a.xy, b.xy);
+}
+SNDE_STRIP_FN void hs_zero(HS &o) { o.x = o.y = o.xx = o.yy = o.xy = F2{0.f, 0.f}; }
+SNDE_STRIP_FN void cs_zero(CS &o) { o.a = o.b = o.c = F2{0.f, 0.f}; }
+
+// per-task constants and accumulators of one lane
+template <bool GRAD, bool GRADK, bool EXTRA, bool FAST>
+struct StripLane {
+    using C = StripCfg;
+    const DevLoss &p;
+    const DevScale &sc;
+    StripSmem &sm;
+    int lane, h, w, y0, y1, rx0, ix0;
+    bool clsF, do_smooth, do_photo;
+    bool in[2], colB[2], colI[2];
+    float xt[2];
+    float alpha, oma;
+    // owner
+    const float *own_base; int own_sc, own_sh, own_sw;
+    const float *dep_base; int dep_sh, dep_sw;
+    float *gd_base; int gd_sh, gd_sw;
+    // current other image
+    const float *oth_base; int oth_sc, oth_sh, oth_sw;
+    long long n;              // index of the current pair in the N-sized tensors
+    const float *mask_base; int mask_sh, mask_sw;
+    float *wout_base; int wout_sc, wout_sh, wout_sw;
+    float *eout_base; int eout_sc, eout_sh, eout_sw;
+    float P[12], Ki[9];
+    // accumulators
+    float dP[12], dK[9], err_acc, sx_acc, sy_acc;
+    // rolling state
+    HS s1[3];                 // H(t-2) + H(t-1)
+    CS c1[3];                 // Hc(t-3) + Hc(t-2)
+    F2 sy_prev;               // signed smoothness weights of the vertical pairs starting one row above
+
+    SNDE_STRIP_FN StripLane(const DevLoss &p_, const DevScale &sc_, StripSmem &sm_, int lane_) : p(p_), sc(sc_), sm(sm_), lane(lane_) {}
+
+    // ---- owner row iy (image + depth) for the lane's two columns; zeros outside the image ----
+    SNDE_STRIP_FN void load_owner_row(int iy, F2 (&x)[3], F2 &d) const {
+        x[0] = x[1] = x[2] = d = F2{0.f, 0.f};
+        if (iy < 0 || iy >= h) return;
+        if (FAST) {
+            if (in[0]) {          // w and ix0 are even: the pair is inside or outside together
+                const int q = iy * own_sh + ix0;
+                x[0] = ldg2(own_base + q); x[1] = ldg2(own_base + (q + own_sc)); x[2] = ldg2(own_base + (q + 2 * own_sc));
+                d = ldg2(dep_base + (iy * dep_sh + ix0));
+            }
+        } else {
+            if (in[0]) {
+                const int q = iy * own_sh + ix0 * own_sw;
+                x[0].x = ldg(own_base + q); x[1].x = ldg(own_base + (q + own_sc)); x[2].x = ldg(own_base + (q + 2 * own_sc));
+                d.x = ldg(dep_base + (iy * dep_sh + ix0 * dep_sw));
+            }
+            if (in[1]) {
+                const int q = iy * own_sh + (ix0 + 1) * own_sw;
+                x[0].y = ldg(own_base + q); x[1].y = ldg(own_base + (q + own_sc)); x[2].y = ldg(own_base + (q + 2 * own_sc));
+                d.y = ldg(dep_base + (iy * dep_sh + (ix0 + 1) * dep_sw));
+            }
+        }
+    }
+
+    // ---- phase A: reproject + sample the lane's two pixels of row iy (in the image) ----
+    SNDE_STRIP_FN void phase_a(int iy, float yt, const F2 d, bool want_g, F2 (&y)[3], F2 (&g)[6]) const {
+        float yv[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, gv[2][6];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) gv[q][i] = 0.f;
+        Taps tp[2];
+        bool valid[2];
+        int o00[2];
+        const float dq[2] = {d.x, d.y};
+        // both coordinate chains first, then all 24 gathers back to back (memory-level parallelism), then the blends
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            valid[q] = false; o00[q] = 0;
+            tp[q].x0 = tp[q].x1 = tp[q].y0 = tp[q].y1 = 0; tp[q].wx0 = tp[q].wx1 = tp[q].wy0 = tp[q].wy1 = 0.f; tp[q].dx = tp[q].dy = 0.f;
+            if (in[q]) {
+                Reproj rp; reproject_fast(Ki, P, xt[q], yt, dq[q], rp);
+                float x, yy; flow_coords(rp, xt[q], yt, x, yy);
+                // Outside [0,w-1) x [0,h-1) the reference's clamped-corner weights cancel to zero (up to rounding
+                // residue that grows with the distance from the image); the fused path writes the exact zero.
+                if (EXTRA && p.padding) { make_taps(x, yy, h, w, p.padding, tp[q]); valid[q] = true; }   // border mode samples everywhere
+                else { make_taps_valid(x, yy, tp[q]); valid[q] = tap_valid(x, yy, h, w, 0) != 0.f; }
+                if (valid[q]) o00[q] = tp[q].y0 * oth_sh + tp[q].x0 * (FAST ? 1 : oth_sw);
+            }
+        }
+        float v[2][12];
+        const float *ob = oth_base;
+        SNDE_PIN_PTR(ob);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            // row / column steps to the second tap (0 when border mode clamped both taps onto the same pixel)
+            const int dyo = (EXTRA && p.padding) ? (tp[q].y1 - tp[q].y0) * oth_sh : oth_sh;
+            const int dxo = (EXTRA && p.padding) ? (tp[q].x1 - tp[q].x0) * (FAST ? 1 : oth_sw) : (FAST ? 1 : oth_sw);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float *q0 = ob + (o00[q] + ch * oth_sc);
+                const float *q1 = q0 + dyo;
+                v[q][4 * ch + 0] = valid[q] ? ldg(q0) : 0.f;          // (y0, x0)
+                v[q][4 * ch + 1] = valid[q] ? ldg(q1) : 0.f;          // (y1, x0)
+                v[q][4 * ch + 2] = valid[q] ? ldg(q0 + dxo) : 0.f;    // (y0, x1)
+                v[q][4 * ch + 3] = valid[q] ? ldg(q1 + dxo) : 0.f;    // (y1, x1)
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (valid[q]) {
+                const float w00 = tp[q].wx0 * tp[q].wy0, w01 = tp[q].wx0 * tp[q].wy1, w10 = tp[q].wx1 * tp[q].wy0, w11 = tp[q].wx1 * tp[q].wy1;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float i00 = v[q][4 * ch], i01 = v[q][4 * ch + 1], i10 = v[q][4 * ch + 2], i11 = v[q][4 * ch + 3];
+                    yv[q][ch] = tap_blend_fma(w00, w01, w10, w11, i00, i01, i10, i11);
+                    if (GRAD && want_g) tap_derivs_fma(tp[q], i00, i01, i10, i11, gv[q][2 * ch], gv[q][2 * ch + 1]);
+                }
+            }
+            if (EXTRA && wout_base && colI[q] && iy >= y0 && iy < y1) {
+                float *o = wout_base + iy * wout_sh + (ix0 + q) * wout_sw;
+                o[0] = yv[q][0]; o[wout_sc] = yv[q][1]; o[2 * wout_sc] = yv[q][2];
+            }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) y[ch] = F2{yv[0][ch], yv[1][ch]};
+#pragma unroll
+        for (int i = 0; i < 6; ++i) g[i] = F2{gv[0][i], gv[1][i]};
+    }
+
+    SNDE_STRIP_FN float mask_at(int iy, int ix) const { return ldg(mask_base + iy * mask_sh + ix * mask_sw); }
+
+    // ---- one step of the stream: row t enters, rows t-1 (B) and t-2 (C, G, S) are finished ----
+    //   s2_in  = H(t-1), s2_out <- H(t);  c2_in = Hc(t-2), c2_out <- Hc(t-1)
+    //   xr, dr : owner row t (prefetched by the caller);  pass k (0 = first pass over this owner)
+    SNDE_STRIP_FN void step(int t, int k, const F2 (&xr)[3], const F2 dr, const HS (&s2_in)[3], HS (&s2_out)[3],
+                            const CS (&c2_in)[3], CS (&c2_out)[3]) {
+        const int slot0 = t & (C::RING - 1), slot1 = (t - 1) & (C::RING - 1), slot2 = (t - 2) & (C::RING - 1);
+        const bool row_in = t >= 0 && t < h;
+        const bool doB = t >= y0;               // row t-1 needs its coefficient maps (rows y0-1 .. y1)
+        const bool doC = t >= y0 + 2;           // row t-2 is an inner row (y0 .. y1-1)
+        const bool has_mask = EXTRA && mask_base != nullptr;
+
+        // ---------------- phase A (row t) ----------------
+        F2 yr[3], gr[6];
+        if (do_photo) {
+            if (row_in) phase_a(t, ldg(sc.ytab + t), dr, t >= y0 && t < y1, yr, gr);
+            else {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) yr[ch] = F2{0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 6; ++i) gr[i] = F2{0.f, 0.f};
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) sm.Y[slot0][ch][lane] = yr[ch];
+            if (GRAD) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) sm.G[slot0][i][lane] = gr[i];
+            }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) sm.X[slot0][ch][lane] = xr[ch];
+        sm.D[slot0][lane] = dr;
+
+        F2 po[3];                                  // dL/d(warped) of row t-2
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) po[ch] = F2{0.f, 0.f};
+        if (do_photo) {
+            // ---------------- horizontal sums of row t ----------------
+            {
+                float to_right[6], to_left[6], from_left[6], from_right[6];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) { to_right[ch] = xr[ch].y; to_right[3 + ch] = yr[ch].y; to_left[ch] = xr[ch].x; to_left[3 + ch] = yr[ch].x; }
+                neighbor_exchange<6>(lane, to_right, to_left, from_left, from_right);
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) hsum_row(xr[ch], yr[ch], from_left[ch], from_right[ch], from_left[3 + ch], from_right[3 + ch], s2_out[ch]);
+            }
+            // ---------------- phase B (row t-1) ----------------
+            CS co[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) cs_zero(co[ch]);
+            const int rb = t - 1;
+            if (doB && rb >= 0 && rb < h) {
+                const bool row_inner = rb >= y0 && rb < y1;
+                const float gS0 = -0.5f * alpha * sc.gphoto;
+                float mk[2] = {1.f, 1.f};
+                if (has_mask) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) if (colB[q]) mk[q] = mask_at(rb, ix0 + q);
+                }
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    HS tot; hs_add(s1[ch], s2_out[ch], tot);
+                    const F2 xc = sm.X[slot1][ch][lane], yc = sm.Y[slot1][ch][lane];
+                    const float sxq[2] = {tot.x.x, tot.x.y}, syq[2] = {tot.y.x, tot.y.y}, sxxq[2] = {tot.xx.x, tot.xx.y};
+                    const float syyq[2] = {tot.yy.x, tot.yy.y}, sxyq[2] = {tot.xy.x, tot.xy.y};
+                    const float xcq[2] = {xc.x, xc.y}, ycq[2] = {yc.x, yc.y};
+                    float ca[2], cb[2], cc[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        SsimS ss; ssim_sums(sxq[q], syq[q], sxxq[q], syyq[q], sxyq[q], ss);
+                        const float v = fmaf(-0.5f, ss.S, 0.5f);
+                        const float err = fmaf(alpha, clampf(v, 0.f, 1.f), oma * fabsf(xcq[q] - ycq[q]));
+                        if (row_inner && colI[q]) {
+                            err_acc += EXTRA ? err * mk[q] : err;
+                            if (EXTRA && eout_base) eout_base[ch * eout_sc + rb * eout_sh + (ix0 + q) * eout_sw] = err;
+                        }
+                        ca[q] = cb[q] = cc[q] = 0.f;
+                        if (GRAD) {
+                            const float gS = (colB[q] && v >= 0.f && v <= 1.f) ? (EXTRA ? gS0 * mk[q] : gS0) : 0.f;
+                            ssim_sums_bwd(ss, sxq[q], syq[q], gS, ca[q], cb[q], cc[q]);
+                        }
+                    }
+                    co[ch].a = F2{ca[0], ca[1]}; co[ch].b = F2{cb[0], cb[1]}; co[ch].c = F2{cc[0], cc[1]};
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) hs_add(s2_in[ch], s2_out[ch], s1[ch]);      // s1 <- H(t-1) + H(t)
+
+            if (GRAD) {
+                // ---------------- horizontal sums of the coefficient row t-1 ----------------
+                {
+                    float to_right[9], to_left[9], from_left[9], from_right[9];
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        to_right[3 * ch] = co[ch].a.y; to_right[3 * ch + 1] = co[ch].b.y; to_right[3 * ch + 2] = co[ch].c.y;
+                        to_left[3 * ch] = co[ch].a.x; to_left[3 * ch + 1] = co[ch].b.x; to_left[3 * ch + 2] = co[ch].c.x;
+                    }
+                    neighbor_exchange<9>(lane, to_right, to_left, from_left, from_right);
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const float ta = co[ch].a.x + co[ch].a.y, tb = co[ch].b.x + co[ch].b.y, tc = co[ch].c.x + co[ch].c.y;
+                        c2_out[ch].a = F2{from_left[3 * ch] + ta, ta + from_right[3 * ch]};
+                        c2_out[ch].b = F2{from_left[3 * ch + 1] + tb, tb + from_right[3 * ch + 1]};
+                        c2_out[ch].c = F2{from_left[3 * ch + 2] + tc, tc + from_right[3 * ch + 2]};
+                    }
+                }
+                // ---------------- phase C (row t-2): dL/d(warped) ----------------
+                if (doC) {
+                    const int rc = t - 2;
+                    const float g1 = oma * sc.gphoto;
+                    float gl[2] = {g1, g1};
+                    if (has_mask) {
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) if (colI[q]) gl[q] = g1 * mask_at(rc, ix0 + q);
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const F2 ba = add2(c1[ch].a, c2_out[ch].a), bb = add2(c1[ch].b, c2_out[ch].b), bc = add2(c1[ch].c, c2_out[ch].c);
+                        const F2 xv = sm.X[slot2][ch][lane], yv = sm.Y[slot2][ch][lane];
+                        const float d0 = xv.x - yv.x, d1 = xv.y - yv.y;
+                        const float l0 = d0 > 0.f ? gl[0] : (d0 < 0.f ? -gl[0] : 0.f), l1 = d1 > 0.f ? gl[1] : (d1 < 0.f ? -gl[1] : 0.f);
+                        po[ch].x = fmaf(yv.x + yv.x, bb.x, fmaf(xv.x, bc.x, ba.x)) - l0;
+                        po[ch].y = fmaf(yv.y + yv.y, bb.y, fmaf(xv.y, bc.y, ba.y)) - l1;
+                    }
+                }
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {                                        // c1 <- Hc(t-2) + Hc(t-1)
+                    c1[ch].a = add2(c2_in[ch].a, c2_out[ch].a); c1[ch].b = add2(c2_in[ch].b, c2_out[ch].b); c1[ch].c = add2(c2_in[ch].c, c2_out[ch].c);
+                }
+            }
+        }
+
+        // ---------------- rows t-2: phase G, smoothness, depth-gradient write ----------------
+        const int r2 = t - 2;
+        float gd[2] = {0.f, 0.f};
+        if (GRAD && do_photo && doC) {
+            const float yt2 = ldg(sc.ytab + r2);
+            const F2 d2 = sm.D[slot2][lane];
+            F2 g[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) g[i] = sm.G[slot2][i][lane];
+            const float dq[2] = {d2.x, d2.y};
+            const float p0[2] = {po[0].x, po[0].y}, p1[2] = {po[1].x, po[1].y}, p2[2] = {po[2].x, po[2].y};
+            const float g0x[2] = {g[0].x, g[0].y}, g0y[2] = {g[1].x, g[1].y}, g1x[2] = {g[2].x, g[2].y}, g1y[2] = {g[3].x, g[3].y};
+            const float g2x[2] = {g[4].x, g[4].y}, g2y[2] = {g[5].x, g[5].y};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (!colI[q]) continue;
+                const float gx = fmaf(p2[q], g2x[q], fmaf(p1[q], g1x[q], p0[q] * g0x[q]));
+                const float gy = fmaf(p2[q], g2y[q], fmaf(p1[q], g1y[q], p0[q] * g0y[q]));
+                Reproj rp; reproject_nodiv(Ki, P, xt[q], yt2, dq[q], rp);
+                float gu[3], gcam[3];
+                gd[q] = reproject_bwd_fast(P, rp, gx, gy, gu, gcam);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    dP[j * 4 + 0] = fmaf(gu[j], rp.cam[0], dP[j * 4 + 0]);
+                    dP[j * 4 + 1] = fmaf(gu[j], rp.cam[1], dP[j * 4 + 1]);
+                    dP[j * 4 + 2] = fmaf(gu[j], rp.cam[2], dP[j * 4 + 2]);
+                    dP[j * 4 + 3] += gu[j];
+                }
+                if (GRADK) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const float gray = gcam[j] * dq[q];
+                        dK[j * 3 + 0] = fmaf(gray, xt[q], dK[j * 3 + 0]);
+                        dK[j * 3 + 1] = fmaf(gray, yt2, dK[j * 3 + 1]);
+                        dK[j * 3 + 2] += gray;
+                    }
+                }
+            }
+        }
+        // smoothness of row t-2 (first pass only).  One step earlier (row y0-1) only the vertical pair weights are
+        // formed: they are the "pair above" of the first inner row.
+        if (do_smooth && k == 0 && t >= y0 + 1) {
+            F2 sxw = F2{0.f, 0.f}, syw = F2{0.f, 0.f};
+            float nb_x[4] = {0.f, 0.f, 0.f, 0.f};          // right neighbour column: image (3) + depth
+            F2 xa[3], da = F2{0.f, 0.f};
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) xa[ch] = F2{0.f, 0.f};
+            const bool r_in = r2 >= 0 && r2 < h;
+            if (r_in) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) xa[ch] = sm.X[slot2][ch][lane];
+                da = sm.D[slot2][lane];
+            }
+            {
+                const float to_left[4] = {xa[0].x, xa[1].x, xa[2].x, da.x};
+                take_from_right<4>(lane, to_left, nb_x);
+            }
+            if (r_in) {
+                const bool inner_row = doC;
+                const float xq[2][3] = {{xa[0].x, xa[1].x, xa[2].x}, {xa[0].y, xa[1].y, xa[2].y}};
+                const float xn[2][3] = {{xa[0].y, xa[1].y, xa[2].y}, {nb_x[0], nb_x[1], nb_x[2]}};
+                const float dq[2] = {da.x, da.y}, dn[2] = {da.y, nb_x[3]};
+                F2 xb[3], db = F2{0.f, 0.f};
+                const bool below = r2 + 1 < h;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) xb[ch] = below ? sm.X[slot1][ch][lane] : F2{0.f, 0.f};
+                if (below) db = sm.D[slot1][lane];
+                const float xd[2][3] = {{xb[0].x, xb[1].x, xb[2].x}, {xb[0].y, xb[1].y, xb[2].y}};
+                const float dd[2] = {db.x, db.y};
+                float vxs[2] = {0.f, 0.f}, vys[2] = {0.f, 0.f};
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (!colB[q]) continue;
+                    if (ix0 + q + 1 < w) {
+                        const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xn[q][0], xn[q][1], xn[q][2]);
+                        const float v = (dq[q] - dn[q]) * wgt;
+                        vxs[q] = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
+                        if (inner_row && colI[q]) sx_acc += fabsf(v);
+                    }
+                    if (below) {
+                        const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xd[q][0], xd[q][1], xd[q][2]);
+                        const float v = (dq[q] - dd[q]) * wgt;
+                        vys[q] = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
+                        if (inner_row && colI[q]) sy_acc += fabsf(v);
+                    }
+                }
+                sxw = F2{vxs[0], vxs[1]}; syw = F2{vys[0], vys[1]};
+            }
+            // the horizontal pair that ENDS at the lane's left column starts in the left neighbour lane
+            float sx_left;
+            {
+                const float to_right[1] = {sxw.y};
+                float from_left[1];
+                take_from_left<1>(lane, to_right, from_left);
+                sx_left = from_left[0];
+            }
+            if (GRAD && doC) {
+                gd[0] += sc.gsx * (sxw.x - sx_left) + sc.gsy * (syw.x - sy_prev.x);
+                gd[1] += sc.gsx * (sxw.y - sxw.x) + sc.gsy * (syw.y - sy_prev.y);
+            }
+            sy_prev = syw;
+        }
+        if (GRAD && doC && in[0]) {
+            // every lane writes only its own inner pixels; later passes over the same owner add to what this lane wrote
+            if (FAST) {
+                if (colI[0]) {     // inner lanes hold two inner pixels (w even)
+                    float *dst = gd_base + (r2 * gd_sh + ix0);
+                    F2 o = F2{gd[0], gd[1]};
+                    if (k > 0) { const F2 old = *reinterpret_cast<const F2 *>(dst); o.x += old.x; o.y += old.y; }
+                    *reinterpret_cast<F2 *>(dst) = o;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (!colI[q]) continue;
+                    float *dst = gd_base + (r2 * gd_sh + (ix0 + q) * gd_sw);
+                    *dst = k > 0 ? *dst + gd[q] : gd[q];
+                }
+            }
+        }
+    }
+};
+
+// The strip program: one task, all passes.  GRAD: also back-propagate.  GRADK: also accumulate d/dKinv.
+// EXTRA: honour the optional explainability masks, warped / error-map outputs and border padding.
+// FAST: planar tensors with unit x-stride and 8-byte aligned rows (64-bit loads / stores of the lane's pixel pair).
+template <bool GRAD, bool GRADK, bool EXTRA, bool FAST>
+SNDE_STRIP_FN void strip_task(const DevLoss &p, int task, int lane, StripSmem &sm) {
+    using C = StripCfg;
+    // ---- decode the task (uniform over the warp) ----
+    int e = 0;
+    while (e + 1 < p.num_entries && task >= p.entry[e + 1].begin) ++e;
+    const DevEntry ent = p.entry[e];
+    const DevScale &sc = p.sc[ent.scale];
+    const int local = task - ent.begin;
+    const int per_owner = sc.tiles_x * sc.tiles_y;
+    const int m = local / per_owner;                 // owner index inside its class
+    const int tt = local - m * per_owner;
+    const int sy = tt / sc.tiles_x, sx = tt - sy * sc.tiles_x;
+    const int B = p.B, S = p.S;
+
+    StripLane<GRAD, GRADK, EXTRA, FAST> L(p, sc, sm, lane);
+    L.h = sc.h; L.w = sc.w;
+    L.y0 = sy * sc.seg_h; L.y1 = L.y0 + sc.seg_h < sc.h ? L.y0 + sc.seg_h : sc.h;
+    L.rx0 = sx * C::TW - 2; L.ix0 = L.rx0 + 2 * lane;
+    L.clsF = ent.cls == 0;
+    L.do_smooth = !(p.flags & FLAG_NO_SMOOTH);
+    L.do_photo = !(p.flags & FLAG_NO_PHOTO);
+    L.alpha = p.alpha; L.oma = p.oma;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int c = 2 * lane + q, ix = L.ix0 + q;
+        L.in[q] = ix >= 0 && ix < L.w;
+        L.colB[q] = L.in[q] && c >= 1 && c <= C::RW - 2;
+        L.colI[q] = L.in[q] && c >= 2 && c <= C::RW - 3;
+        L.xt[q] = L.in[q] ? ldg(sc.xtab + ix) : 0.f;
+    }
+    const bool clsF = L.clsF;
+    const int b = clsF ? m : (m % B);                // batch element (selects K)
+    const DevImage &own = clsF ? sc.tgt : sc.src;
+    L.own_base = own.p + (long long)m * own.sn; L.own_sc = own.sc; L.own_sh = own.sh; L.own_sw = own.sw;
+    const long long depth_n = clsF ? m : (long long)B + m;
+    L.dep_base = sc.depth.p + depth_n * sc.depth.sn; L.dep_sh = sc.depth.sh; L.dep_sw = sc.depth.sw;
+    L.gd_base = GRAD ? sc.gdepth.p + depth_n * sc.gdepth.sn : nullptr; L.gd_sh = sc.gdepth.sh; L.gd_sw = sc.gdepth.sw;
+    SNDE_PIN_PTR(L.own_base); SNDE_PIN_PTR(L.dep_base);
+    const int n_others = L.do_photo ? (clsF ? S : 1) : 0;
+    const int n_pass = n_others > 0 ? n_others : 1;  // smoothness alone still needs one pass over the owner
+    L.sx_acc = 0.f; L.sy_acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) L.dK[i] = 0.f;
+    const float *Kinv = sc.Kinv + 9 * b;
+    const int t_begin = L.y0 - 2 > 0 ? L.y0 - 2 : 0, t_end = L.y1 + 1;     // rows above the image are zero rows == the initial state
+
+    for (int k = 0; k < n_pass; ++k) {
+        const long long n = clsF ? (long long)k * B + b : m;      // index into the N-sized tensors
+        L.n = n;
+        const DevImage &oth = clsF ? sc.src : sc.tgt;
+        L.oth_base = oth.p + (clsF ? n : (long long)b) * oth.sn; L.oth_sc = oth.sc; L.oth_sh = oth.sh; L.oth_sw = oth.sw;
+        if (EXTRA) {
+            const DevMap &mask = clsF ? sc.mask_fwd : sc.mask_bwd;
+            const DevImageOut &wout = clsF ? sc.warped_fwd : sc.warped_bwd;
+            const DevImageOut &eout = clsF ? sc.err_fwd : sc.err_bwd;
+            L.mask_base = mask.p ? mask.p + n * mask.sn : nullptr; L.mask_sh = mask.sh; L.mask_sw = mask.sw;
+            L.wout_base = wout.p ? wout.p + n * wout.sn : nullptr; L.wout_sc = wout.sc; L.wout_sh = wout.sh; L.wout_sw = wout.sw;
+            L.eout_base = eout.p ? eout.p + n * eout.sn : nullptr; L.eout_sc = eout.sc; L.eout_sh = eout.sh; L.eout_sw = eout.sw;
+        } else {
+            L.mask_base = nullptr; L.wout_base = nullptr; L.eout_base = nullptr;
+        }
+        if (n_others > 0) {
+            const float *Pn = sc.P + (n * 2 + (clsF ? 0 : 1)) * 12;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) L.P[i] = ldg(Pn + i);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) L.Ki[i] = ldg(Kinv + i);
+        }
+        L.err_acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) L.dP[i] = 0.f;
+        HS s2a[3], s2b[3];
+        CS c2a[3], c2b[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) { hs_zero(L.s1[ch]); hs_zero(s2a[ch]); hs_zero(s2b[ch]); cs_zero(L.c1[ch]); cs_zero(c2a[ch]); cs_zero(c2b[ch]); }
+        L.sy_prev = F2{0.f, 0.f};
+
+        F2 xr[3], dr, xn[3], dn;
+        L.load_owner_row(t_begin, xr, dr);
+        // two steps per iteration: the carried row (s2 / c2) alternates between two register sets instead of being copied
+        for (int t = t_begin; t <= t_end; t += 2) {
+            L.load_owner_row(t + 1, xn, dn);                    // prefetch: consumed by the second half
+            L.step(t, k, xr, dr, s2a, s2b, c2a, c2b);
+            if (t + 1 <= t_end) {
+                L.load_owner_row(t + 2, xr, dr);
+                L.step(t + 1, k, xn, dn, s2b, s2a, c2b, c2a);
+            }
+        }
+
+        // ---- publish this pass: error sum and d/dP of pair n ----
+        if (n_others > 0) {
+            float v[13];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) v[i] = L.dP[i];
+            v[12] = L.err_acc;
+            warp_sum<13>(lane, v);
+            float mine = 0.f;
+#pragma unroll
+            for (int i = 0; i < 13; ++i) if (lane == i) mine = v[i];
+            if (GRAD && lane < 12 && mine != 0.f) atomic_add_double(sc.gP + (n * 2 + (clsF ? 0 : 1)) * 12 + lane, (double)mine);
+            if (lane == 12 && mine != 0.f) atomic_add_double(sc.loss + (clsF ? 0 : 1), (double)mine);
+        }
+    }
+    // ---- publish the per-owner sums: smoothness, d/dKinv ----
+    {
+        float v[11];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) v[i] = L.dK[i];
+        v[9] = L.sx_acc; v[10] = L.sy_acc;
+        warp_sum<11>(lane, v);
+        float mine = 0.f;
+#pragma unroll
+        for (int i = 0; i < 11; ++i) if (lane == i) mine = v[i];
+        if (GRADK && lane < 9 && mine != 0.f) atomic_add_double(sc.gKinv + 9 * b + lane, (double)mine);
+        if ((lane == 9 || lane == 10) && mine != 0.f) atomic_add_double(sc.loss + 2 + (lane - 9), (double)mine);
+    }
+}
+
+}  // namespace snde

@@ -1,5 +1,5 @@
-"""Host-emulation harness (tests only): runs the fused loss tile program of csrc/snde_tile.cuh on the
-CPU through tests/host_emul/emul.cpp, with numpy arrays behind the very same SndeLossArgs struct."""
+"""Host-emulation harness (tests only): runs the fused loss strip program of csrc/snde_strip.cuh on the
+CPU through tests/host_emul/emul.cpp (32 fibers per warp), with numpy arrays behind the very same SndeLossArgs struct."""
 import ctypes as C
 import os
 import subprocess
@@ -32,7 +32,7 @@ def _map(a):   # numpy (n,h,w)
     return _abi.map_view(a.ctypes.data, [s // 4 for s in a.strides])
 
 
-def run_loss(inp, alpha=0.85, w_rigid=1.0, w_smooth=0.5, flags=1, padding=0, masks=None, want_maps=False):
+def run_loss(inp, alpha=0.85, w_rigid=1.0, w_smooth=0.5, flags=1, padding=0, masks=None, want_maps=False, seg_rows=0):
     """inp: snde_b200.synthetic.LossInputs (CPU torch). Returns dict like oracle.compose.geonet_loss."""
     from snde_b200 import _abi
     lib = C.CDLL(build())
@@ -74,10 +74,10 @@ def run_loss(inp, alpha=0.85, w_rigid=1.0, w_smooth=0.5, flags=1, padding=0, mas
     wsp = (ws.ctypes.data + 15) & ~15
     args = _abi.make_loss_args(B, S, alpha, flags, padding, poses.ctypes.data, scales, loss_out.ctypes.data, gposes.ctypes.data,
                                gK.ctypes.data, wsp, nbytes)
-    rc = lib.emul_loss_fwdbwd(C.byref(args))
-    if rc:
+    rc = lib.emul_loss_fwdbwd(C.byref(args), C.c_int(seg_rows))
+    if rc < 0:
         raise RuntimeError(abi.snde_strerror(rc).decode())
-    res = dict(loss_total=float(loss_out[0]), loss_rigid_warp=float(loss_out[1]), loss_disp_smooth=float(loss_out[2]),
+    res = dict(variant=rc, loss_total=float(loss_out[0]), loss_rigid_warp=float(loss_out[1]), loss_disp_smooth=float(loss_out[2]),
                fwd_mean=loss_out[3::3].copy(), bwd_mean=loss_out[4::3].copy(), smooth=loss_out[5::3].copy(),
                grad_depth=[o["grad_depth"] for o in outs], grad_poses=gposes, grad_K_ms=gK)
     if want_maps:

@@ -1,6 +1,7 @@
-"""The fused loss TILE PROGRAM (csrc/snde_tile.cuh), compiled for the host by tests/host_emul and run on
-numpy buffers, against the oracle.  This checks the device code's logic (work table, halos, zero padding,
-gradient ownership, finalize) in the GPU-less container; the GPU tests then check the real kernels."""
+"""The fused loss STRIP PROGRAM (csrc/snde_strip.cuh), compiled for the host by tests/host_emul (32 fibers per
+warp) and run on numpy buffers, against the oracle.  This checks the device code's logic (task table, halo columns,
+rolling row sums, segment seams, zero padding, gradient ownership, finalize) in the GPU-less container; the GPU
+tests then check the real kernels."""
 import numpy as np
 import pytest
 
@@ -105,3 +106,48 @@ def test_emulated_strided_views():
     assert a["loss_total"] == b["loss_total"]
     for s in range(inp.num_scales):
         assert np.array_equal(a["grad_depth"][s], b["grad_depth"][s])
+
+
+@pytest.mark.parametrize("seg_rows", [5, 8, 13])
+def test_emulated_segment_seams(seg_rows):
+    """Cutting the strips into short row segments (seams every few rows) must not change a single depth-gradient bit:
+    every inner pixel is still produced by exactly one lane from the same rolling sums."""
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**CASES["small_noise_large_motion"])
+    a, b = emul.run_loss(inp, flags=3), emul.run_loss(inp, flags=3, seg_rows=seg_rows)
+    assert abs(a["loss_total"] - b["loss_total"]) < 1e-6 * abs(a["loss_total"])
+    for s in range(inp.num_scales):
+        assert np.array_equal(a["grad_depth"][s], b["grad_depth"][s])
+    assert rel_l2(b["grad_poses"], a["grad_poses"]) < 1e-5
+    assert rel_l2(b["grad_K_ms"], a["grad_K_ms"]) < 1e-5
+
+
+def test_emulated_variants_selected():
+    """planar inputs take the FAST (64-bit pair access) variant, permuted NHWC views and odd widths the generic one"""
+    import torch
+    from snde_b200.synthetic import make_inputs, LossInputs
+    inp = make_inputs(**CASES["small_smooth"])
+    assert emul.run_loss(inp, flags=1)["variant"] == 4
+    assert emul.run_loss(inp, flags=0)["variant"] == 1
+    assert emul.run_loss(inp, flags=3)["variant"] == 3
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    inp2 = LossInputs([nhwc(t) for t in inp.tgt_pyr], [nhwc(t) for t in inp.src_pyr], inp.depth_pyr, inp.poses, inp.K, inp.K_ms)
+    assert emul.run_loss(inp2, flags=1)["variant"] == 5
+
+
+def test_emulated_odd_sizes(oracle32):
+    """odd width / height (generic variant): columns and rows that do not fill a lane pair or a segment"""
+    from oracle.compose import geonet_loss
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(B=1, S=2, H=37, W=67, num_scales=2, seed=11, smooth=True, motion="large")
+    e = emul.run_loss(inp, flags=3, seg_rows=16)
+    assert e["variant"] == 3
+    o = geonet_loss(oracle32, **oracle_inputs(inp))
+    assert abs(e["loss_total"] - o["loss_total"]) < 1e-6 * abs(o["loss_total"])
+    for s in range(inp.num_scales):
+        assert rel_l2(e["grad_depth"][s], o["grad_depth"][s]) < 1e-4
+    assert rel_l2(e["grad_poses"], o["grad_poses"]) < 1e-4
+    e1 = emul.run_loss(inp, flags=1, seg_rows=16)
+    assert e1["variant"] == 5
+    for s in range(inp.num_scales):
+        assert np.array_equal(e1["grad_depth"][s], e["grad_depth"][s])
