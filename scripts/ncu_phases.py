@@ -1,7 +1,9 @@
 #!/usr/bin/env python
-"""Aggregate ncu per-instruction counts of the fused tile kernel by PHASE (source-line ranges found by markers)."""
-import collections, csv, io, re, subprocess, sys, os
+"""Aggregate ncu per-instruction counts of the fused strip kernel by PHASE (source-line ranges found by markers).
+usage: scripts/ncu_phases.py report.ncu-rep [warped_px]"""
+import collections, csv, io, os, subprocess, sys
 rep = sys.argv[1]
+PX = float(sys.argv[2]) if len(sys.argv) > 2 else 9052160.0
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 csrc = os.path.join(root, "self-supervised-normal-depth-estimation_b200", "csrc")
 def ranges(fname, markers):
@@ -15,16 +17,19 @@ def ranges(fname, markers):
             raise SystemExit("marker not found: " + pat)
     pts.sort()
     return pts
-tile = ranges("snde_tile.cuh", [("reduce", "void warp_sum16"), ("B.row_sums", "struct RowSums"), ("C.co_row_sums", "struct CoSums"),
-                                ("decode", "The tile program."), ("0.load", "---- phase 0"), ("A", "for (int k = 0; k < n_others"),
-                                ("B", "---- phase B"), ("C", "---- phase C"), ("G", "---- phase G"), ("S", "if (do_smooth)"),
-                                ("W.write", "---- write the depth gradient")])
+strip = ranges("snde_strip.cuh", [("warp.exchange", "// warp primitives"), ("B.hsum_row", "SNDE_STRIP_FN void hsum_row"), ("BC.add2(rolling sums)", "SNDE_STRIP_FN F2 add2"),
+                                  ("setup.lane", "struct StripLane {"), ("0.load_owner_row", "SNDE_STRIP_FN void load_owner_row"), ("A", "SNDE_STRIP_FN void phase_a"),
+                                  ("step.head", "SNDE_STRIP_FN void step("), ("B.hsum", "horizontal sums of row t -"), ("B", "phase B (row"),
+                                  ("C.hsum", "horizontal sums of the coefficient"), ("C", "phase C (row"), ("G", "rows t-2: phase G"),
+                                  ("S", "smoothness of row t-2"), ("W.write", "GRAD && doC && in[0]"), ("setup.task", "void strip_task("),
+                                  ("publish", "publish this pass")])
 math_ = ranges("snde_math.cuh", [("misc", "namespace snde {"), ("A.reproject", "struct Reproj {"), ("G.reproject_bwd(ieee)", "SNDE_HD float reproject_bwd("),
                                  ("A.taps", "struct Taps {"), ("ref.ssim", "struct Ssim {"), ("B.ssim_sums", "struct SsimS {"),
-                                 ("B.ssim_bwd", "SNDE_HD void ssim_sums_bwd"), ("G.reproject", "SNDE_HD void reproject_nodiv"),
+                                 ("B.ssim_bwd", "SNDE_HD void ssim_sums_bwd"), ("AG.reproject_nodiv", "SNDE_HD void reproject_nodiv(const float *Kinv, const float *P, float xt, float yt, float d, Reproj &o) {"),
+                                 ("G.reproject_bwd", "SNDE_HD float reproject_bwd_fast"),
                                  ("A.blend", "SNDE_HD float tap_blend_fma"), ("S.edge", "SNDE_HD float edge_weight3"), ("pose", "SNDE_HD void mm3")])
 def phase(f, ln):
-    tab = tile if f == "snde_tile.cuh" else math_ if f == "snde_math.cuh" else None
+    tab = strip if f == "snde_strip.cuh" else math_ if f == "snde_math.cuh" else None
     if tab is None: return "other:" + f
     name = "pre"
     for start, nm in tab:
@@ -40,9 +45,9 @@ for r in csv.reader(io.StringIO(txt)):
         except ValueError: continue
         ph = phase(fname, ln); agg[ph] += n; smp[ph] += s
 tot = sum(agg.values()); ts = max(1, sum(smp.values()))
-print(f"total warp-inst {tot}  (x32 / 9052160 px = {tot*32/9052160:.0f} thread-inst per warped px at config2)")
+print(f"total warp-inst {tot}  (x32 / {PX:.0f} px = {tot*32/PX:.0f} thread-inst per warped px)")
 groups = collections.Counter(); gs = collections.Counter()
 for k, v in agg.items(): groups[k.split(".")[0]] += v; gs[k.split(".")[0]] += smp[k]
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1]): print(f"  {100*v/tot:5.1f}% inst  {100*smp[k]/ts:5.1f}% samples  {k}")
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1]): print(f"  {100*v/tot:5.1f}% inst  {100*smp[k]/ts:5.1f}% samples  {k}   ~{v*32/PX:.0f} inst/px")
 print("by phase:")
-for k, v in sorted(groups.items(), key=lambda kv: -kv[1]): print(f"  {100*v/tot:5.1f}% inst  {100*gs[k]/ts:5.1f}% samples  {k}   ~{v*32/9052160:.0f} inst/px")
+for k, v in sorted(groups.items(), key=lambda kv: -kv[1]): print(f"  {100*v/tot:5.1f}% inst  {100*gs[k]/ts:5.1f}% samples  {k}   ~{v*32/PX:.0f} inst/px")

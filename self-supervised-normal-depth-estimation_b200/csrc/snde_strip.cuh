@@ -35,7 +35,7 @@ struct StripCfg {
     static constexpr int RW = 64;        // region columns of a strip (32 lanes x 2 columns)
     static constexpr int TW = RW - 4;    // inner columns (60)
     static constexpr int SEG = 32;       // default rows per segment
-    static constexpr int RING = 4;       // rows kept in the lane-private ring (rows t, t-1, t-2 are live)
+    static constexpr int RING = 3;       // rows kept in the lane-private ring (rows t, t-1, t-2 are live)
     static constexpr int WARPS = 4;      // warps per CTA (independent of each other)
     static constexpr int NT = WARPS * 32;
     static constexpr int MAX_S = 8;      // most source views per target (SNDE_MAX_SOURCES)
@@ -78,12 +78,22 @@ struct DevLoss {
 
 enum { FLAG_GRAD = 1, FLAG_GRAD_K = 2, FLAG_NO_PHOTO = 4, FLAG_NO_SMOOTH = 8 };   // == SNDE_LOSS_* in include/snde.h
 
-// lane-private rows (a register-file extension: no lane ever reads another lane's slot)
+// Lane-private rows and carried sums (a register-file extension: no lane ever reads another lane's slot, so there is
+// no synchronisation on any of this).  Slot-major so that one base address per row reaches every field by an immediate.
+struct alignas(16) F4 { float x, y, z, w; };
+struct RowSlot {
+    F2 X[3][32];                     // owner image row, 0 outside the image (= the pools' zero padding)
+    F2 Y[3][32];                     // warped other image row, 0 outside the image
+    F2 D[32];                        // owner depth row
+    F2 G[6][32];                     // d(warped_c)/dx, /dy
+};
 struct StripSmem {
-    F2 X[StripCfg::RING][3][32];     // owner image rows, 0 outside the image (= the pools' zero padding)
-    F2 Y[StripCfg::RING][3][32];     // warped other image rows, 0 outside the image
-    F2 D[StripCfg::RING][32];        // owner depth rows
-    F2 G[StripCfg::RING][6][32];     // d(warped_c)/dx, /dy
+    RowSlot ring[StripCfg::RING];
+    F4 H2a[3][2][32];                // per channel: H(t-1) = {x.x,x.y,y.x,y.y}, {xx.x,xx.y,yy.x,yy.y}
+    F2 H2b[3][32];                   //              ... {xy.x,xy.y}
+    F4 C2a[3][32];                   // per channel: Hc(t-2) = {a.x,a.y,b.x,b.y}
+    F2 C2b[3][32];                   //              ... {c.x,c.y}
+    F4 PK[6];                        // P (12 floats) and Kinv (9 floats, padded) of the current pass: warp-uniform reads
 };
 
 #if defined(__CUDACC__)
@@ -124,6 +134,7 @@ SNDE_STRIP_FN void warp_sum(int, float (&v)[N]) {
         for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
 }
 SNDE_STRIP_FN void atomic_add_double(double *dst, double v) { atomicAdd(dst, v); }
+SNDE_STRIP_FN void warp_fence(int) { __syncwarp(); }
 #else
 // host emulation (tests/host_emul/emul.cpp): 32 fibers; slots are double-buffered, one yield per exchange
 float *host_warp_slots(int lane, int parity);       // 64 floats per lane and parity
@@ -168,6 +179,7 @@ SNDE_STRIP_FN void warp_sum(int lane, float (&v)[N]) {
     host_warp_parity(lane) = par ^ 1;
 }
 SNDE_STRIP_FN void atomic_add_double(double *dst, double v) { *dst += v; }
+SNDE_STRIP_FN void warp_fence(int) { host_warp_yield(); }
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -212,30 +224,37 @@ struct StripLane {
     const DevLoss &p;
     const DevScale &sc;
     StripSmem &sm;
-    int lane, h, w, y0, y1, rx0, ix0;
-    bool clsF, do_smooth, do_photo;
+    int lane, h, w, y0, y1, ix0;
+    bool do_smooth, do_photo;
     bool in[2], colB[2], colI[2];
+    float mI[2];              // 1 for an inner in-image column, else 0
+    float gSm[2];             // -0.5*alpha*gphoto where the column takes part in phase B, else 0
     float xt[2];
-    float alpha, oma;
+    float alpha, oma, g1;
     // owner
     const float *own_base; int own_sc, own_sh, own_sw;
     const float *dep_base; int dep_sh, dep_sw;
     float *gd_base; int gd_sh, gd_sw;
     // current other image
     const float *oth_base; int oth_sc, oth_sh, oth_sw;
-    long long n;              // index of the current pair in the N-sized tensors
     const float *mask_base; int mask_sh, mask_sw;
     float *wout_base; int wout_sc, wout_sh, wout_sw;
     float *eout_base; int eout_sc, eout_sh, eout_sw;
-    float P[12], Ki[9];
     // accumulators
     float dP[12], dK[9], err_acc, sx_acc, sy_acc;
-    // rolling state
+    // rolling state kept in registers (the other carried row lives in sm.H2 / sm.C2)
     HS s1[3];                 // H(t-2) + H(t-1)
     CS c1[3];                 // Hc(t-3) + Hc(t-2)
     F2 sy_prev;               // signed smoothness weights of the vertical pairs starting one row above
 
     SNDE_STRIP_FN StripLane(const DevLoss &p_, const DevScale &sc_, StripSmem &sm_, int lane_) : p(p_), sc(sc_), sm(sm_), lane(lane_) {}
+
+    SNDE_STRIP_FN void load_PK(float (&P)[12], float (&Ki)[9]) const {
+        const F4 a = sm.PK[0], b = sm.PK[1], c = sm.PK[2], d = sm.PK[3], e = sm.PK[4], f = sm.PK[5];
+        P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w; P[4] = b.x; P[5] = b.y; P[6] = b.z; P[7] = b.w;
+        P[8] = c.x; P[9] = c.y; P[10] = c.z; P[11] = c.w;
+        Ki[0] = d.x; Ki[1] = d.y; Ki[2] = d.z; Ki[3] = d.w; Ki[4] = e.x; Ki[5] = e.y; Ki[6] = e.z; Ki[7] = e.w; Ki[8] = f.x;
+    }
 
     // ---- owner row iy (image + depth) for the lane's two columns; zeros outside the image ----
     SNDE_STRIP_FN void load_owner_row(int iy, F2 (&x)[3], F2 &d) const {
@@ -263,29 +282,30 @@ struct StripLane {
 
     // ---- phase A: reproject + sample the lane's two pixels of row iy (in the image) ----
     SNDE_STRIP_FN void phase_a(int iy, float yt, const F2 d, bool want_g, F2 (&y)[3], F2 (&g)[6]) const {
-        float yv[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, gv[2][6];
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
+        for (int ch = 0; ch < 3; ++ch) y[ch] = F2{0.f, 0.f};
 #pragma unroll
-            for (int i = 0; i < 6; ++i) gv[q][i] = 0.f;
+        for (int i = 0; i < 6; ++i) g[i] = F2{0.f, 0.f};
+        if (FAST ? !in[0] : !(in[0] || in[1])) return;
+        float P[12], Ki[9];
+        load_PK(P, Ki);
         Taps tp[2];
-        bool valid[2];
         int o00[2];
         const float dq[2] = {d.x, d.y};
-        // both coordinate chains first, then all 24 gathers back to back (memory-level parallelism), then the blends
+        // both coordinate chains first, then all 24 gathers back to back (memory-level parallelism), then the blends.
+        // Branch-free per pixel: an invalid pixel samples address 0 of the image with four zero weights.
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            valid[q] = false; o00[q] = 0;
-            tp[q].x0 = tp[q].x1 = tp[q].y0 = tp[q].y1 = 0; tp[q].wx0 = tp[q].wx1 = tp[q].wy0 = tp[q].wy1 = 0.f; tp[q].dx = tp[q].dy = 0.f;
-            if (in[q]) {
-                Reproj rp; reproject_fast(Ki, P, xt[q], yt, dq[q], rp);
-                float x, yy; flow_coords(rp, xt[q], yt, x, yy);
-                // Outside [0,w-1) x [0,h-1) the reference's clamped-corner weights cancel to zero (up to rounding
-                // residue that grows with the distance from the image); the fused path writes the exact zero.
-                if (EXTRA && p.padding) { make_taps(x, yy, h, w, p.padding, tp[q]); valid[q] = true; }   // border mode samples everywhere
-                else { make_taps_valid(x, yy, tp[q]); valid[q] = tap_valid(x, yy, h, w, 0) != 0.f; }
-                if (valid[q]) o00[q] = tp[q].y0 * oth_sh + tp[q].x0 * (FAST ? 1 : oth_sw);
-            }
+            Reproj rp; reproject_fast(Ki, P, xt[q], yt, dq[q], rp);
+            float x, yy; flow_coords(rp, xt[q], yt, x, yy);
+            bool valid;
+            // Outside [0,w-1) x [0,h-1) the reference's clamped-corner weights cancel to zero (up to rounding
+            // residue that grows with the distance from the image); the fused path writes the exact zero.
+            if (EXTRA && p.padding) { make_taps(x, yy, h, w, p.padding, tp[q]); valid = true; }   // border mode samples everywhere
+            else { make_taps_valid(x, yy, tp[q]); valid = tap_valid(x, yy, h, w, 0) != 0.f; }
+            valid = valid && (FAST || in[q]);
+            o00[q] = valid ? tp[q].y0 * oth_sh + tp[q].x0 * (FAST ? 1 : oth_sw) : 0;
+            if (!valid) { tp[q].wx0 = tp[q].wx1 = tp[q].wy0 = tp[q].wy1 = 0.f; tp[q].x1 = tp[q].x0; tp[q].y1 = tp[q].y0; }
         }
         float v[2][12];
         const float *ob = oth_base;
@@ -299,21 +319,27 @@ struct StripLane {
             for (int ch = 0; ch < 3; ++ch) {
                 const float *q0 = ob + (o00[q] + ch * oth_sc);
                 const float *q1 = q0 + dyo;
-                v[q][4 * ch + 0] = valid[q] ? ldg(q0) : 0.f;          // (y0, x0)
-                v[q][4 * ch + 1] = valid[q] ? ldg(q1) : 0.f;          // (y1, x0)
-                v[q][4 * ch + 2] = valid[q] ? ldg(q0 + dxo) : 0.f;    // (y0, x1)
-                v[q][4 * ch + 3] = valid[q] ? ldg(q1 + dxo) : 0.f;    // (y1, x1)
+                v[q][4 * ch + 0] = ldg(q0);          // (y0, x0)
+                v[q][4 * ch + 1] = ldg(q1);          // (y1, x0)
+                v[q][4 * ch + 2] = ldg(q0 + dxo);    // (y0, x1)
+                v[q][4 * ch + 3] = ldg(q1 + dxo);    // (y1, x1)
             }
         }
+        float yv[2][3], gv[2][6];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            if (valid[q]) {
-                const float w00 = tp[q].wx0 * tp[q].wy0, w01 = tp[q].wx0 * tp[q].wy1, w10 = tp[q].wx1 * tp[q].wy0, w11 = tp[q].wx1 * tp[q].wy1;
+            const float w00 = tp[q].wx0 * tp[q].wy0, w01 = tp[q].wx0 * tp[q].wy1, w10 = tp[q].wx1 * tp[q].wy0, w11 = tp[q].wx1 * tp[q].wy1;
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const float i00 = v[q][4 * ch], i01 = v[q][4 * ch + 1], i10 = v[q][4 * ch + 2], i11 = v[q][4 * ch + 3];
-                    yv[q][ch] = tap_blend_fma(w00, w01, w10, w11, i00, i01, i10, i11);
-                    if (GRAD && want_g) tap_derivs_fma(tp[q], i00, i01, i10, i11, gv[q][2 * ch], gv[q][2 * ch + 1]);
+            for (int ch = 0; ch < 3; ++ch) {
+                const float i00 = v[q][4 * ch], i01 = v[q][4 * ch + 1], i10 = v[q][4 * ch + 2], i11 = v[q][4 * ch + 3];
+                yv[q][ch] = tap_blend_fma(w00, w01, w10, w11, i00, i01, i10, i11);
+                gv[q][2 * ch] = gv[q][2 * ch + 1] = 0.f;
+                if (GRAD && want_g) {
+                    if (EXTRA) tap_derivs_fma(tp[q], i00, i01, i10, i11, gv[q][2 * ch], gv[q][2 * ch + 1]);
+                    else {     // dx = dy = 1 without border clamping
+                        gv[q][2 * ch] = fmaf(tp[q].wy1, i11 - i01, tp[q].wy0 * (i10 - i00));
+                        gv[q][2 * ch + 1] = fmaf(tp[q].wx1, i11 - i10, tp[q].wx0 * (i01 - i00));
+                    }
                 }
             }
             if (EXTRA && wout_base && colI[q] && iy >= y0 && iy < y1) {
@@ -330,67 +356,65 @@ struct StripLane {
     SNDE_STRIP_FN float mask_at(int iy, int ix) const { return ldg(mask_base + iy * mask_sh + ix * mask_sw); }
 
     // ---- one step of the stream: row t enters, rows t-1 (B) and t-2 (C, G, S) are finished ----
-    //   s2_in  = H(t-1), s2_out <- H(t);  c2_in = Hc(t-2), c2_out <- Hc(t-1)
-    //   xr, dr : owner row t (prefetched by the caller);  pass k (0 = first pass over this owner)
-    SNDE_STRIP_FN void step(int t, int k, const F2 (&xr)[3], const F2 dr, const HS (&s2_in)[3], HS (&s2_out)[3],
-                            const CS (&c2_in)[3], CS (&c2_out)[3]) {
-        const int slot0 = t & (C::RING - 1), slot1 = (t - 1) & (C::RING - 1), slot2 = (t - 2) & (C::RING - 1);
+    //   r0, r1, r2 : ring slots of rows t, t-1, t-2;  xr, dr : owner row t (prefetched by the caller)
+    //   pass k (0 = first pass over this owner)
+    SNDE_STRIP_FN void step(int t, int k, RowSlot &r0, const RowSlot &r1, const RowSlot &r2, const F2 (&xr)[3], const F2 dr) {
         const bool row_in = t >= 0 && t < h;
         const bool doB = t >= y0;               // row t-1 needs its coefficient maps (rows y0-1 .. y1)
         const bool doC = t >= y0 + 2;           // row t-2 is an inner row (y0 .. y1-1)
         const bool has_mask = EXTRA && mask_base != nullptr;
 
         // ---------------- phase A (row t) ----------------
-        F2 yr[3], gr[6];
+        F2 yr[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) yr[ch] = F2{0.f, 0.f};
         if (do_photo) {
-            if (row_in) phase_a(t, ldg(sc.ytab + t), dr, t >= y0 && t < y1, yr, gr);
-            else {
+            F2 gr[6];
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) yr[ch] = F2{0.f, 0.f};
+            for (int i = 0; i < 6; ++i) gr[i] = F2{0.f, 0.f};
+            const bool want_g = t >= y0 && t < y1;
+            if (row_in) phase_a(t, ldg(sc.ytab + t), dr, want_g, yr, gr);
 #pragma unroll
-                for (int i = 0; i < 6; ++i) gr[i] = F2{0.f, 0.f};
-            }
+            for (int ch = 0; ch < 3; ++ch) r0.Y[ch][lane] = yr[ch];
+            if (GRAD && want_g) {
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) sm.Y[slot0][ch][lane] = yr[ch];
-            if (GRAD) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) sm.G[slot0][i][lane] = gr[i];
+                for (int i = 0; i < 6; ++i) r0.G[i][lane] = gr[i];
             }
         }
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) sm.X[slot0][ch][lane] = xr[ch];
-        sm.D[slot0][lane] = dr;
+        for (int ch = 0; ch < 3; ++ch) r0.X[ch][lane] = xr[ch];
+        r0.D[lane] = dr;
 
         F2 po[3];                                  // dL/d(warped) of row t-2
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) po[ch] = F2{0.f, 0.f};
         if (do_photo) {
-            // ---------------- horizontal sums of row t ----------------
-            {
-                float to_right[6], to_left[6], from_left[6], from_right[6];
+            const int rb = t - 1, rc = t - 2;
+            const bool rowB = doB && rb >= 0 && rb < h;
+            const bool row_inner = rb >= y0 && rb < y1;
+            float mk[2] = {1.f, 1.f}, gl[2] = {g1, g1};
+            if (has_mask) {
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) { to_right[ch] = xr[ch].y; to_right[3 + ch] = yr[ch].y; to_left[ch] = xr[ch].x; to_left[3 + ch] = yr[ch].x; }
-                neighbor_exchange<6>(lane, to_right, to_left, from_left, from_right);
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) hsum_row(xr[ch], yr[ch], from_left[ch], from_right[ch], from_left[3 + ch], from_right[3 + ch], s2_out[ch]);
-            }
-            // ---------------- phase B (row t-1) ----------------
-            CS co[3];
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) cs_zero(co[ch]);
-            const int rb = t - 1;
-            if (doB && rb >= 0 && rb < h) {
-                const bool row_inner = rb >= y0 && rb < y1;
-                const float gS0 = -0.5f * alpha * sc.gphoto;
-                float mk[2] = {1.f, 1.f};
-                if (has_mask) {
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) if (colB[q]) mk[q] = mask_at(rb, ix0 + q);
+                for (int q = 0; q < 2; ++q) {
+                    if (rowB && colB[q]) mk[q] = mask_at(rb, ix0 + q);
+                    if (GRAD && doC && colI[q]) gl[q] = g1 * mask_at(rc, ix0 + q);
                 }
+            }
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    HS tot; hs_add(s1[ch], s2_out[ch], tot);
-                    const F2 xc = sm.X[slot1][ch][lane], yc = sm.Y[slot1][ch][lane];
+            for (int ch = 0; ch < 3; ++ch) {
+                // ---------------- horizontal sums of row t ----------------
+                HS H;
+                {
+                    const float to_right[2] = {xr[ch].y, yr[ch].y}, to_left[2] = {xr[ch].x, yr[ch].x};
+                    float from_left[2], from_right[2];
+                    neighbor_exchange<2>(lane, to_right, to_left, from_left, from_right);
+                    hsum_row(xr[ch], yr[ch], from_left[0], from_right[0], from_left[1], from_right[1], H);
+                }
+                // ---------------- phase B (row t-1) ----------------
+                CS co; cs_zero(co);
+                if (rowB) {
+                    HS tot; hs_add(s1[ch], H, tot);
+                    const F2 xc = r1.X[ch][lane], yc = r1.Y[ch][lane];
                     const float sxq[2] = {tot.x.x, tot.x.y}, syq[2] = {tot.y.x, tot.y.y}, sxxq[2] = {tot.xx.x, tot.xx.y};
                     const float syyq[2] = {tot.yy.x, tot.yy.y}, sxyq[2] = {tot.xy.x, tot.xy.y};
                     const float xcq[2] = {xc.x, xc.y}, ycq[2] = {yc.x, yc.y};
@@ -398,84 +422,82 @@ struct StripLane {
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         SsimS ss; ssim_sums(sxq[q], syq[q], sxxq[q], syyq[q], sxyq[q], ss);
-                        const float v = fmaf(-0.5f, ss.S, 0.5f);
-                        const float err = fmaf(alpha, clampf(v, 0.f, 1.f), oma * fabsf(xcq[q] - ycq[q]));
-                        if (row_inner && colI[q]) {
-                            err_acc += EXTRA ? err * mk[q] : err;
-                            if (EXTRA && eout_base) eout_base[ch * eout_sc + rb * eout_sh + (ix0 + q) * eout_sw] = err;
+                        const float v = fmaf(-0.5f, ss.S, 0.5f), vc = clampf(v, 0.f, 1.f);
+                        const float err = fmaf(alpha, vc, oma * fabsf(xcq[q] - ycq[q]));
+                        if (row_inner) {
+                            err_acc = fmaf(EXTRA ? err * mk[q] : err, mI[q], err_acc);
+                            if (EXTRA && eout_base && colI[q]) eout_base[ch * eout_sc + rb * eout_sh + (ix0 + q) * eout_sw] = err;
                         }
                         ca[q] = cb[q] = cc[q] = 0.f;
                         if (GRAD) {
-                            const float gS = (colB[q] && v >= 0.f && v <= 1.f) ? (EXTRA ? gS0 * mk[q] : gS0) : 0.f;
+                            const float gS = (v == vc) ? (EXTRA ? gSm[q] * mk[q] : gSm[q]) : 0.f;     // the clamp passes gradient inside [0,1] only
                             ssim_sums_bwd(ss, sxq[q], syq[q], gS, ca[q], cb[q], cc[q]);
                         }
                     }
-                    co[ch].a = F2{ca[0], ca[1]}; co[ch].b = F2{cb[0], cb[1]}; co[ch].c = F2{cc[0], cc[1]};
+                    co.a = F2{ca[0], ca[1]}; co.b = F2{cb[0], cb[1]}; co.c = F2{cc[0], cc[1]};
                 }
-            }
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) hs_add(s2_in[ch], s2_out[ch], s1[ch]);      // s1 <- H(t-1) + H(t)
-
-            if (GRAD) {
-                // ---------------- horizontal sums of the coefficient row t-1 ----------------
+                // roll: s1 <- H(t-1) + H(t); H(t) replaces H(t-1) in the lane's shared slot
                 {
-                    float to_right[9], to_left[9], from_left[9], from_right[9];
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        to_right[3 * ch] = co[ch].a.y; to_right[3 * ch + 1] = co[ch].b.y; to_right[3 * ch + 2] = co[ch].c.y;
-                        to_left[3 * ch] = co[ch].a.x; to_left[3 * ch + 1] = co[ch].b.x; to_left[3 * ch + 2] = co[ch].c.x;
-                    }
-                    neighbor_exchange<9>(lane, to_right, to_left, from_left, from_right);
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        const float ta = co[ch].a.x + co[ch].a.y, tb = co[ch].b.x + co[ch].b.y, tc = co[ch].c.x + co[ch].c.y;
-                        c2_out[ch].a = F2{from_left[3 * ch] + ta, ta + from_right[3 * ch]};
-                        c2_out[ch].b = F2{from_left[3 * ch + 1] + tb, tb + from_right[3 * ch + 1]};
-                        c2_out[ch].c = F2{from_left[3 * ch + 2] + tc, tc + from_right[3 * ch + 2]};
-                    }
+                    const F4 pa = sm.H2a[ch][0][lane], pb = sm.H2a[ch][1][lane];
+                    const F2 pc = sm.H2b[ch][lane];
+                    s1[ch].x = add2(F2{pa.x, pa.y}, H.x); s1[ch].y = add2(F2{pa.z, pa.w}, H.y);
+                    s1[ch].xx = add2(F2{pb.x, pb.y}, H.xx); s1[ch].yy = add2(F2{pb.z, pb.w}, H.yy);
+                    s1[ch].xy = add2(pc, H.xy);
+                    sm.H2a[ch][0][lane] = F4{H.x.x, H.x.y, H.y.x, H.y.y};
+                    sm.H2a[ch][1][lane] = F4{H.xx.x, H.xx.y, H.yy.x, H.yy.y};
+                    sm.H2b[ch][lane] = H.xy;
                 }
-                // ---------------- phase C (row t-2): dL/d(warped) ----------------
-                if (doC) {
-                    const int rc = t - 2;
-                    const float g1 = oma * sc.gphoto;
-                    float gl[2] = {g1, g1};
-                    if (has_mask) {
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) if (colI[q]) gl[q] = g1 * mask_at(rc, ix0 + q);
+                if (GRAD) {
+                    // ---------------- horizontal sums of the coefficient row t-1 ----------------
+                    CS Hc;
+                    {
+                        const float to_right[3] = {co.a.y, co.b.y, co.c.y}, to_left[3] = {co.a.x, co.b.x, co.c.x};
+                        float from_left[3], from_right[3];
+                        neighbor_exchange<3>(lane, to_right, to_left, from_left, from_right);
+                        const float ta = co.a.x + co.a.y, tb = co.b.x + co.b.y, tc = co.c.x + co.c.y;
+                        Hc.a = F2{from_left[0] + ta, ta + from_right[0]};
+                        Hc.b = F2{from_left[1] + tb, tb + from_right[1]};
+                        Hc.c = F2{from_left[2] + tc, tc + from_right[2]};
                     }
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        const F2 ba = add2(c1[ch].a, c2_out[ch].a), bb = add2(c1[ch].b, c2_out[ch].b), bc = add2(c1[ch].c, c2_out[ch].c);
-                        const F2 xv = sm.X[slot2][ch][lane], yv = sm.Y[slot2][ch][lane];
+                    // ---------------- phase C (row t-2): dL/d(warped) ----------------
+                    if (doC) {
+                        const F2 ba = add2(c1[ch].a, Hc.a), bb = add2(c1[ch].b, Hc.b), bc = add2(c1[ch].c, Hc.c);
+                        const F2 xv = r2.X[ch][lane], yv = r2.Y[ch][lane];
                         const float d0 = xv.x - yv.x, d1 = xv.y - yv.y;
                         const float l0 = d0 > 0.f ? gl[0] : (d0 < 0.f ? -gl[0] : 0.f), l1 = d1 > 0.f ? gl[1] : (d1 < 0.f ? -gl[1] : 0.f);
                         po[ch].x = fmaf(yv.x + yv.x, bb.x, fmaf(xv.x, bc.x, ba.x)) - l0;
                         po[ch].y = fmaf(yv.y + yv.y, bb.y, fmaf(xv.y, bc.y, ba.y)) - l1;
                     }
-                }
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {                                        // c1 <- Hc(t-2) + Hc(t-1)
-                    c1[ch].a = add2(c2_in[ch].a, c2_out[ch].a); c1[ch].b = add2(c2_in[ch].b, c2_out[ch].b); c1[ch].c = add2(c2_in[ch].c, c2_out[ch].c);
+                    // roll: c1 <- Hc(t-2) + Hc(t-1)
+                    {
+                        const F4 pa = sm.C2a[ch][lane];
+                        const F2 pc = sm.C2b[ch][lane];
+                        c1[ch].a = add2(F2{pa.x, pa.y}, Hc.a); c1[ch].b = add2(F2{pa.z, pa.w}, Hc.b); c1[ch].c = add2(pc, Hc.c);
+                        sm.C2a[ch][lane] = F4{Hc.a.x, Hc.a.y, Hc.b.x, Hc.b.y};
+                        sm.C2b[ch][lane] = Hc.c;
+                    }
                 }
             }
         }
 
         // ---------------- rows t-2: phase G, smoothness, depth-gradient write ----------------
-        const int r2 = t - 2;
+        const int r2i = t - 2;
         float gd[2] = {0.f, 0.f};
-        if (GRAD && do_photo && doC) {
-            const float yt2 = ldg(sc.ytab + r2);
-            const F2 d2 = sm.D[slot2][lane];
+        if (GRAD && do_photo && doC && (FAST ? colI[0] : (colI[0] || colI[1]))) {
+            float P[12], Ki[9];
+            load_PK(P, Ki);
+            const float yt2 = ldg(sc.ytab + r2i);
+            const F2 d2 = r2.D[lane];
             F2 g[6];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) g[i] = sm.G[slot2][i][lane];
+            for (int i = 0; i < 6; ++i) g[i] = r2.G[i][lane];
             const float dq[2] = {d2.x, d2.y};
             const float p0[2] = {po[0].x, po[0].y}, p1[2] = {po[1].x, po[1].y}, p2[2] = {po[2].x, po[2].y};
             const float g0x[2] = {g[0].x, g[0].y}, g0y[2] = {g[1].x, g[1].y}, g1x[2] = {g[2].x, g[2].y}, g1y[2] = {g[3].x, g[3].y};
             const float g2x[2] = {g[4].x, g[4].y}, g2y[2] = {g[5].x, g[5].y};
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                if (!colI[q]) continue;
+                if (!FAST && !colI[q]) continue;
                 const float gx = fmaf(p2[q], g2x[q], fmaf(p1[q], g1x[q], p0[q] * g0x[q]));
                 const float gy = fmaf(p2[q], g2y[q], fmaf(p1[q], g1y[q], p0[q] * g0y[q]));
                 Reproj rp; reproject_nodiv(Ki, P, xt[q], yt2, dq[q], rp);
@@ -507,11 +529,11 @@ struct StripLane {
             F2 xa[3], da = F2{0.f, 0.f};
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) xa[ch] = F2{0.f, 0.f};
-            const bool r_in = r2 >= 0 && r2 < h;
+            const bool r_in = r2i >= 0 && r2i < h;
             if (r_in) {
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) xa[ch] = sm.X[slot2][ch][lane];
-                da = sm.D[slot2][lane];
+                for (int ch = 0; ch < 3; ++ch) xa[ch] = r2.X[ch][lane];
+                da = r2.D[lane];
             }
             {
                 const float to_left[4] = {xa[0].x, xa[1].x, xa[2].x, da.x};
@@ -523,27 +545,31 @@ struct StripLane {
                 const float xn[2][3] = {{xa[0].y, xa[1].y, xa[2].y}, {nb_x[0], nb_x[1], nb_x[2]}};
                 const float dq[2] = {da.x, da.y}, dn[2] = {da.y, nb_x[3]};
                 F2 xb[3], db = F2{0.f, 0.f};
-                const bool below = r2 + 1 < h;
+                const bool below = r2i + 1 < h;
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) xb[ch] = below ? sm.X[slot1][ch][lane] : F2{0.f, 0.f};
-                if (below) db = sm.D[slot1][lane];
+                for (int ch = 0; ch < 3; ++ch) xb[ch] = below ? r1.X[ch][lane] : F2{0.f, 0.f};
+                if (below) db = r1.D[lane];
                 const float xd[2][3] = {{xb[0].x, xb[1].x, xb[2].x}, {xb[0].y, xb[1].y, xb[2].y}};
                 const float dd[2] = {db.x, db.y};
                 float vxs[2] = {0.f, 0.f}, vys[2] = {0.f, 0.f};
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    if (!colB[q]) continue;
-                    if (ix0 + q + 1 < w) {
+                    const float mi = inner_row ? mI[q] : 0.f;
+                    {
                         const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xn[q][0], xn[q][1], xn[q][2]);
                         const float v = (dq[q] - dn[q]) * wgt;
-                        vxs[q] = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
-                        if (inner_row && colI[q]) sx_acc += fabsf(v);
+                        const float sgn = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
+                        const bool ok = colB[q] && ix0 + q + 1 < w;
+                        vxs[q] = ok ? sgn : 0.f;
+                        sx_acc = fmaf(ok ? fabsf(v) : 0.f, mi, sx_acc);
                     }
-                    if (below) {
+                    {
                         const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xd[q][0], xd[q][1], xd[q][2]);
                         const float v = (dq[q] - dd[q]) * wgt;
-                        vys[q] = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
-                        if (inner_row && colI[q]) sy_acc += fabsf(v);
+                        const float sgn = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
+                        const bool ok = colB[q] && below;
+                        vys[q] = ok ? sgn : 0.f;
+                        sy_acc = fmaf(ok ? fabsf(v) : 0.f, mi, sy_acc);
                     }
                 }
                 sxw = F2{vxs[0], vxs[1]}; syw = F2{vys[0], vys[1]};
@@ -566,7 +592,7 @@ struct StripLane {
             // every lane writes only its own inner pixels; later passes over the same owner add to what this lane wrote
             if (FAST) {
                 if (colI[0]) {     // inner lanes hold two inner pixels (w even)
-                    float *dst = gd_base + (r2 * gd_sh + ix0);
+                    float *dst = gd_base + (r2i * gd_sh + ix0);
                     F2 o = F2{gd[0], gd[1]};
                     if (k > 0) { const F2 old = *reinterpret_cast<const F2 *>(dst); o.x += old.x; o.y += old.y; }
                     *reinterpret_cast<F2 *>(dst) = o;
@@ -575,7 +601,7 @@ struct StripLane {
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     if (!colI[q]) continue;
-                    float *dst = gd_base + (r2 * gd_sh + (ix0 + q) * gd_sw);
+                    float *dst = gd_base + (r2i * gd_sh + (ix0 + q) * gd_sw);
                     *dst = k > 0 ? *dst + gd[q] : gd[q];
                 }
             }
@@ -604,20 +630,22 @@ SNDE_STRIP_FN void strip_task(const DevLoss &p, int task, int lane, StripSmem &s
     StripLane<GRAD, GRADK, EXTRA, FAST> L(p, sc, sm, lane);
     L.h = sc.h; L.w = sc.w;
     L.y0 = sy * sc.seg_h; L.y1 = L.y0 + sc.seg_h < sc.h ? L.y0 + sc.seg_h : sc.h;
-    L.rx0 = sx * C::TW - 2; L.ix0 = L.rx0 + 2 * lane;
-    L.clsF = ent.cls == 0;
+    L.ix0 = sx * C::TW - 2 + 2 * lane;
+    const bool clsF = ent.cls == 0;
     L.do_smooth = !(p.flags & FLAG_NO_SMOOTH);
     L.do_photo = !(p.flags & FLAG_NO_PHOTO);
     L.alpha = p.alpha; L.oma = p.oma;
+    L.g1 = p.oma * sc.gphoto;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const int c = 2 * lane + q, ix = L.ix0 + q;
         L.in[q] = ix >= 0 && ix < L.w;
         L.colB[q] = L.in[q] && c >= 1 && c <= C::RW - 2;
         L.colI[q] = L.in[q] && c >= 2 && c <= C::RW - 3;
+        L.mI[q] = L.colI[q] ? 1.f : 0.f;
+        L.gSm[q] = L.colB[q] ? -0.5f * p.alpha * sc.gphoto : 0.f;
         L.xt[q] = L.in[q] ? ldg(sc.xtab + ix) : 0.f;
     }
-    const bool clsF = L.clsF;
     const int b = clsF ? m : (m % B);                // batch element (selects K)
     const DevImage &own = clsF ? sc.tgt : sc.src;
     L.own_base = own.p + (long long)m * own.sn; L.own_sc = own.sc; L.own_sh = own.sh; L.own_sw = own.sw;
@@ -635,7 +663,6 @@ SNDE_STRIP_FN void strip_task(const DevLoss &p, int task, int lane, StripSmem &s
 
     for (int k = 0; k < n_pass; ++k) {
         const long long n = clsF ? (long long)k * B + b : m;      // index into the N-sized tensors
-        L.n = n;
         const DevImage &oth = clsF ? sc.src : sc.tgt;
         L.oth_base = oth.p + (clsF ? n : (long long)b) * oth.sn; L.oth_sc = oth.sc; L.oth_sh = oth.sh; L.oth_sw = oth.sw;
         if (EXTRA) {
@@ -648,32 +675,36 @@ SNDE_STRIP_FN void strip_task(const DevLoss &p, int task, int lane, StripSmem &s
         } else {
             L.mask_base = nullptr; L.wout_base = nullptr; L.eout_base = nullptr;
         }
-        if (n_others > 0) {
+        warp_fence(lane);                 // every lane is done with the previous pass's matrices
+        if (n_others > 0 && lane < 24) {
             const float *Pn = sc.P + (n * 2 + (clsF ? 0 : 1)) * 12;
-#pragma unroll
-            for (int i = 0; i < 12; ++i) L.P[i] = ldg(Pn + i);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) L.Ki[i] = ldg(Kinv + i);
+            float *pk = reinterpret_cast<float *>(sm.PK);
+            pk[lane] = lane < 12 ? ldg(Pn + lane) : (lane < 21 ? ldg(Kinv + (lane - 12)) : 0.f);
         }
+        // carried rows start as zero rows
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            hs_zero(L.s1[ch]); cs_zero(L.c1[ch]);
+            sm.H2a[ch][0][lane] = F4{0.f, 0.f, 0.f, 0.f}; sm.H2a[ch][1][lane] = F4{0.f, 0.f, 0.f, 0.f}; sm.H2b[ch][lane] = F2{0.f, 0.f};
+            sm.C2a[ch][lane] = F4{0.f, 0.f, 0.f, 0.f}; sm.C2b[ch][lane] = F2{0.f, 0.f};
+        }
+        warp_fence(lane);                 // the matrices are visible to every lane
         L.err_acc = 0.f;
 #pragma unroll
         for (int i = 0; i < 12; ++i) L.dP[i] = 0.f;
-        HS s2a[3], s2b[3];
-        CS c2a[3], c2b[3];
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) { hs_zero(L.s1[ch]); hs_zero(s2a[ch]); hs_zero(s2b[ch]); cs_zero(L.c1[ch]); cs_zero(c2a[ch]); cs_zero(c2b[ch]); }
         L.sy_prev = F2{0.f, 0.f};
 
-        F2 xr[3], dr, xn[3], dn;
+        F2 xr[3], dr;
         L.load_owner_row(t_begin, xr, dr);
-        // two steps per iteration: the carried row (s2 / c2) alternates between two register sets instead of being copied
-        for (int t = t_begin; t <= t_end; t += 2) {
-            L.load_owner_row(t + 1, xn, dn);                    // prefetch: consumed by the second half
-            L.step(t, k, xr, dr, s2a, s2b, c2a, c2b);
-            if (t + 1 <= t_end) {
-                L.load_owner_row(t + 2, xr, dr);
-                L.step(t + 1, k, xn, dn, s2b, s2a, c2b, c2a);
-            }
+        int s0 = 0, s1i = 2, s2i = 1;          // ring slots of rows t, t-1, t-2
+        for (int t = t_begin; t <= t_end; ++t) {
+            F2 xn[3], dn;
+            L.load_owner_row(t + 1, xn, dn);                    // prefetch: consumed by the next step
+            L.step(t, k, sm.ring[s0], sm.ring[s1i], sm.ring[s2i], xr, dr);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) xr[ch] = xn[ch];
+            dr = dn;
+            const int tmp = s2i; s2i = s1i; s1i = s0; s0 = tmp;
         }
 
         // ---- publish this pass: error sum and d/dP of pair n ----

@@ -90,7 +90,8 @@ def test_argument_validation_without_launch(abi):
 
 
 def test_num_tiles(abi):
-    """work table: class-F items (B per scale) + class-R items (S*B per scale), 60x16 inner tiles"""
+    """task table: class-F tasks (B owners per scale) + class-R tasks (S*B owners per scale); a task is one strip of 60
+    inner columns x one segment of 32 rows"""
     lib = abi.lib()
     dummy = np.zeros(64, np.float32)
     args = abi.SndeLossArgs()
@@ -101,7 +102,7 @@ def test_num_tiles(abi):
         for f in ("tgt", "src"):
             getattr(sc, f).ptr = dummy.ctypes.data
         sc.depth.ptr = dummy.ctypes.data; sc.K = dummy.ctypes.data; sc.xtab = dummy.ctypes.data; sc.ytab = dummy.ctypes.data
-    per_img = [7 * 8, 4 * 4, 2 * 2, 1 * 1]
+    per_img = [7 * 4, 4 * 2, 2 * 1, 1 * 1]
     assert lib.snde_loss_num_tiles(C.byref(args)) == sum(per_img) * 32 * 3
 
 
