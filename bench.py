@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the end-to-end leg (its keys are then null)")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -240,8 +241,8 @@ def main():
         for o, g in zip(out_host, [t.grad for t in dep] + [poses.grad, detail]):
             o.copy_(g, non_blocking=True)
 
-    e2e_steps = max(5, min(args.steps, 30))
-    for _ in range(3):
+    e2e_steps = 0 if args.no_e2e else max(5, min(args.steps, 30))
+    for _ in range(3 if e2e_steps else 0):
         e2e_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -255,8 +256,8 @@ def main():
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    e2e_value = world * warped_px * e2e_steps / (e2e_ms * 1e-3)
-    e2e_loss = float(out_host[-1][0])
+    e2e_value = world * warped_px * e2e_steps / (e2e_ms * 1e-3) if e2e_steps else None
+    e2e_loss = float(out_host[-1][0]) if e2e_steps else None
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -275,7 +276,7 @@ def main():
                        "parallelism": f"dp{world} (batch sharded, no data-path collective)", "loss_check": loss_check},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "ms_per_step": e2e_ms / e2e_steps, "loss_check": e2e_loss},
+                    "ms_per_step": e2e_ms / e2e_steps if e2e_steps else None, "loss_check": e2e_loss},
             "gpu_launches": 3 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_step": algo_bytes,

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsnde.so")
+LIB_PATH = os.environ.get("SNDE_LIB", os.path.join(HERE, "libsnde.so"))   # SNDE_LIB: tuning experiments only
 
 SNDE_MAX_SCALES = 6
 SNDE_PAD_ZEROS, SNDE_PAD_BORDER = 0, 1

@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-LIB = os.path.join(HERE, "libsnde.so")
+LIB = os.environ.get("SNDE_LIB", os.path.join(HERE, "libsnde.so"))   # SNDE_LIB / SNDE_NVCC_DEFS: tuning experiments only
 # (source, fp-contraction flag): the fused kernel spells out its exact-order arithmetic, the reference-signature
 # kernels follow the reference op by op
 SOURCES = [("snde_fused.cu", "-fmad=true"), ("snde_ops.cu", "-fmad=false")]
@@ -43,11 +43,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     common = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "-Xptxas", "-v" if verbose else "-O3",
-              "-I", INCLUDE, "-I", CSRC, "-DSNDE_BUILDING=1"]
+              "-I", INCLUDE, "-I", CSRC, "-DSNDE_BUILDING=1"] + os.environ.get("SNDE_NVCC_DEFS", "").split()
     objs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src, fmad in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        obj = os.path.join(HERE, "build", os.path.basename(LIB).replace(".so", "_") + src.replace(".cu", ".o"))
         res = subprocess.run(common + [fmad, "-c", "-o", obj, os.path.join(CSRC, src)], capture_output=True, text=True)
         if verbose:
             print(res.stderr)

@@ -28,6 +28,9 @@
 #ifndef SNDE_MAX_SCALES
 #define SNDE_MAX_SCALES 6
 #endif
+#ifndef SNDE_STRIP_WARPS
+#define SNDE_STRIP_WARPS 4
+#endif
 
 namespace snde {
 
@@ -36,7 +39,7 @@ struct StripCfg {
     static constexpr int TW = RW - 4;    // inner columns (60)
     static constexpr int SEG = 32;       // default rows per segment
     static constexpr int RING = 3;       // rows kept in the lane-private ring (rows t, t-1, t-2 are live)
-    static constexpr int WARPS = 4;      // warps per CTA (independent of each other)
+    static constexpr int WARPS = SNDE_STRIP_WARPS;   // warps per CTA (independent of each other)
     static constexpr int NT = WARPS * 32;
     static constexpr int MAX_S = 8;      // most source views per target (SNDE_MAX_SOURCES)
 };
@@ -81,17 +84,20 @@ enum { FLAG_GRAD = 1, FLAG_GRAD_K = 2, FLAG_NO_PHOTO = 4, FLAG_NO_SMOOTH = 8 }; 
 // Lane-private rows and carried sums (a register-file extension: no lane ever reads another lane's slot, so there is
 // no synchronisation on any of this).  Slot-major so that one base address per row reaches every field by an immediate.
 struct alignas(16) F4 { float x, y, z, w; };
-struct RowSlot {
+struct RowXD {
     F2 X[3][32];                     // owner image row, 0 outside the image (= the pools' zero padding)
-    F2 Y[3][32];                     // warped other image row, 0 outside the image
     F2 D[32];                        // owner depth row
+};
+struct RowYG {
+    F2 Y[3][32];                     // warped other image row, 0 outside the image
     F2 G[6][32];                     // d(warped_c)/dx, /dy
 };
 struct StripSmem {
-    RowSlot ring[StripCfg::RING];
-    F4 H2a[3][2][32];                // per channel: H(t-1) = {x.x,x.y,y.x,y.y}, {xx.x,xx.y,yy.x,yy.y}
+    RowXD xd[4];                     // rows t .. t-3 (slot = row & 3)
+    RowYG yg[3];                     // rows t-1 .. t-3 (rotating)
+    F4 H2a[3][2][32];                // per channel: H(t-2) = {x.x,x.y,y.x,y.y}, {xx.x,xx.y,yy.x,yy.y}
     F2 H2b[3][32];                   //              ... {xy.x,xy.y}
-    F4 C2a[3][32];                   // per channel: Hc(t-2) = {a.x,a.y,b.x,b.y}
+    F4 C2a[3][32];                   // per channel: Hc(t-3) = {a.x,a.y,b.x,b.y}
     F2 C2b[3][32];                   //              ... {c.x,c.y}
     F4 PK[6];                        // P (12 floats) and Kinv (9 floats, padded) of the current pass: warp-uniform reads
 };
@@ -280,66 +286,65 @@ struct StripLane {
         }
     }
 
-    // ---- phase A: reproject + sample the lane's two pixels of row iy (in the image) ----
-    SNDE_STRIP_FN void phase_a(int iy, float yt, const F2 d, bool want_g, F2 (&y)[3], F2 (&g)[6]) const {
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) y[ch] = F2{0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < 6; ++i) g[i] = F2{0.f, 0.f};
-        if (FAST ? !in[0] : !(in[0] || in[1])) return;
+    // ---- phase A, first half: reproject the lane's two pixels of row iy (in the image) and start the 24 gathers;
+    //      the loads land in registers that nothing touches until the next step (software prefetch) ----
+    // wts[q] = {wx0, wx1, wy0, wy1} of pixel q (all zero for a pixel that samples nothing); border mode also needs the
+    // derivative gates, kept in dgate[q] = {dx, dy}.
+    SNDE_STRIP_FN void a_issue(float yt, const F2 d, float (&wts)[2][4], float (&dgate)[2][2], float (&taps)[24]) const {
+        // (lanes whose columns lie outside the image go through the same motions with zero weights on pixel 0)
         float P[12], Ki[9];
         load_PK(P, Ki);
-        Taps tp[2];
-        int o00[2];
         const float dq[2] = {d.x, d.y};
-        // both coordinate chains first, then all 24 gathers back to back (memory-level parallelism), then the blends.
+        const float *ob = oth_base;
+        SNDE_PIN_PTR(ob);
         // Branch-free per pixel: an invalid pixel samples address 0 of the image with four zero weights.
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             Reproj rp; reproject_fast(Ki, P, xt[q], yt, dq[q], rp);
             float x, yy; flow_coords(rp, xt[q], yt, x, yy);
+            Taps tp;
             bool valid;
             // Outside [0,w-1) x [0,h-1) the reference's clamped-corner weights cancel to zero (up to rounding
             // residue that grows with the distance from the image); the fused path writes the exact zero.
-            if (EXTRA && p.padding) { make_taps(x, yy, h, w, p.padding, tp[q]); valid = true; }   // border mode samples everywhere
-            else { make_taps_valid(x, yy, tp[q]); valid = tap_valid(x, yy, h, w, 0) != 0.f; }
-            valid = valid && (FAST || in[q]);
-            o00[q] = valid ? tp[q].y0 * oth_sh + tp[q].x0 * (FAST ? 1 : oth_sw) : 0;
-            if (!valid) { tp[q].wx0 = tp[q].wx1 = tp[q].wy0 = tp[q].wy1 = 0.f; tp[q].x1 = tp[q].x0; tp[q].y1 = tp[q].y0; }
-        }
-        float v[2][12];
-        const float *ob = oth_base;
-        SNDE_PIN_PTR(ob);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
+            if (EXTRA && p.padding) { make_taps(x, yy, h, w, p.padding, tp); valid = true; }   // border mode samples everywhere
+            else { make_taps_valid(x, yy, tp); valid = tap_valid(x, yy, h, w, 0) != 0.f; }
+            valid = valid && in[q];
+            const int o00 = valid ? tp.y0 * oth_sh + tp.x0 * (FAST ? 1 : oth_sw) : 0;
             // row / column steps to the second tap (0 when border mode clamped both taps onto the same pixel)
-            const int dyo = (EXTRA && p.padding) ? (tp[q].y1 - tp[q].y0) * oth_sh : oth_sh;
-            const int dxo = (EXTRA && p.padding) ? (tp[q].x1 - tp[q].x0) * (FAST ? 1 : oth_sw) : (FAST ? 1 : oth_sw);
+            int dyo = oth_sh, dxo = FAST ? 1 : oth_sw;
+            if (EXTRA && p.padding) { dyo = (tp.y1 - tp.y0) * oth_sh; dxo = (tp.x1 - tp.x0) * (FAST ? 1 : oth_sw); }
+            if (!valid) { dyo = 0; dxo = 0; }
+            wts[q][0] = valid ? tp.wx0 : 0.f; wts[q][1] = valid ? tp.wx1 : 0.f; wts[q][2] = valid ? tp.wy0 : 0.f; wts[q][3] = valid ? tp.wy1 : 0.f;
+            dgate[q][0] = tp.dx; dgate[q][1] = tp.dy;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                const float *q0 = ob + (o00[q] + ch * oth_sc);
+                const float *q0 = ob + (o00 + ch * oth_sc);
                 const float *q1 = q0 + dyo;
-                v[q][4 * ch + 0] = ldg(q0);          // (y0, x0)
-                v[q][4 * ch + 1] = ldg(q1);          // (y1, x0)
-                v[q][4 * ch + 2] = ldg(q0 + dxo);    // (y0, x1)
-                v[q][4 * ch + 3] = ldg(q1 + dxo);    // (y1, x1)
+                taps[12 * q + 4 * ch + 0] = ldg(q0);          // (y0, x0)
+                taps[12 * q + 4 * ch + 1] = ldg(q1);          // (y1, x0)
+                taps[12 * q + 4 * ch + 2] = ldg(q0 + dxo);    // (y0, x1)
+                taps[12 * q + 4 * ch + 3] = ldg(q1 + dxo);    // (y1, x1)
             }
         }
+    }
+
+    // ---- phase A, second half (one step later): blend the gathered taps -> warped row (+ tap derivatives) ----
+    SNDE_STRIP_FN void a_finish(int iy, const float (&wts)[2][4], const float (&dgate)[2][2], const float (&taps)[24], bool want_g, F2 (&y)[3], F2 (&g)[6]) const {
         float yv[2][3], gv[2][6];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            const float w00 = tp[q].wx0 * tp[q].wy0, w01 = tp[q].wx0 * tp[q].wy1, w10 = tp[q].wx1 * tp[q].wy0, w11 = tp[q].wx1 * tp[q].wy1;
+            const float wx0 = wts[q][0], wx1 = wts[q][1], wy0 = wts[q][2], wy1 = wts[q][3];
+            const float w00 = wx0 * wy0, w01 = wx0 * wy1, w10 = wx1 * wy0, w11 = wx1 * wy1;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                const float i00 = v[q][4 * ch], i01 = v[q][4 * ch + 1], i10 = v[q][4 * ch + 2], i11 = v[q][4 * ch + 3];
+                const float i00 = taps[12 * q + 4 * ch + 0], i01 = taps[12 * q + 4 * ch + 1];
+                const float i10 = taps[12 * q + 4 * ch + 2], i11 = taps[12 * q + 4 * ch + 3];
                 yv[q][ch] = tap_blend_fma(w00, w01, w10, w11, i00, i01, i10, i11);
                 gv[q][2 * ch] = gv[q][2 * ch + 1] = 0.f;
                 if (GRAD && want_g) {
-                    if (EXTRA) tap_derivs_fma(tp[q], i00, i01, i10, i11, gv[q][2 * ch], gv[q][2 * ch + 1]);
-                    else {     // dx = dy = 1 without border clamping
-                        gv[q][2 * ch] = fmaf(tp[q].wy1, i11 - i01, tp[q].wy0 * (i10 - i00));
-                        gv[q][2 * ch + 1] = fmaf(tp[q].wx1, i11 - i10, tp[q].wx0 * (i01 - i00));
-                    }
+                    gv[q][2 * ch] = fmaf(wy1, i11 - i01, wy0 * (i10 - i00));
+                    gv[q][2 * ch + 1] = fmaf(wx1, i11 - i10, wx0 * (i01 - i00));
+                    if (EXTRA) { gv[q][2 * ch] *= dgate[q][0]; gv[q][2 * ch + 1] *= dgate[q][1]; }
                 }
             }
             if (EXTRA && wout_base && colI[q] && iy >= y0 && iy < y1) {
@@ -355,16 +360,22 @@ struct StripLane {
 
     SNDE_STRIP_FN float mask_at(int iy, int ix) const { return ldg(mask_base + iy * mask_sh + ix * mask_sw); }
 
-    // ---- one step of the stream: row t enters, rows t-1 (B) and t-2 (C, G, S) are finished ----
-    //   r0, r1, r2 : ring slots of rows t, t-1, t-2;  xr, dr : owner row t (prefetched by the caller)
-    //   pass k (0 = first pass over this owner)
-    SNDE_STRIP_FN void step(int t, int k, RowSlot &r0, const RowSlot &r1, const RowSlot &r2, const F2 (&xr)[3], const F2 dr) {
+    // ---- one step of the stream.  Row t+1 starts its gathers, row t (gathered during the previous step) is blended
+    //      and enters the sums, rows t-1 (B) and t-2 (C, G, S) are finished ----
+    //   xd0..xd2 : owner rows t, t-1, t-2;  yg0..yg2 : warped rows t, t-1, t-2;  xn, dn : owner row t+1 (prefetched)
+    //   wts / dgate / taps : bilinear weights and gathered taps of row t on entry, of row t+1 on exit;  pass k (0 = first pass over this owner)
+    SNDE_STRIP_FN void step(int t, int k, RowXD &xdn, const RowXD &xd0, const RowXD &xd1, const RowXD &xd2,
+                            RowYG &yg0, const RowYG &yg1, const RowYG &yg2, const F2 (&xn)[3], const F2 dn,
+                            float (&wts)[2][4], float (&dgate)[2][2], float (&taps)[24], int t_last) {
         const bool row_in = t >= 0 && t < h;
         const bool doB = t >= y0;               // row t-1 needs its coefficient maps (rows y0-1 .. y1)
         const bool doC = t >= y0 + 2;           // row t-2 is an inner row (y0 .. y1-1)
         const bool has_mask = EXTRA && mask_base != nullptr;
+        F2 xr[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) xr[ch] = xd0.X[ch][lane];
 
-        // ---------------- phase A (row t) ----------------
+        // ---------------- phase A: finish row t, start row t+1 ----------------
         F2 yr[3];
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) yr[ch] = F2{0.f, 0.f};
@@ -373,17 +384,21 @@ struct StripLane {
 #pragma unroll
             for (int i = 0; i < 6; ++i) gr[i] = F2{0.f, 0.f};
             const bool want_g = t >= y0 && t < y1;
-            if (row_in) phase_a(t, ldg(sc.ytab + t), dr, want_g, yr, gr);
+            if (row_in) a_finish(t, wts, dgate, taps, want_g, yr, gr);
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) r0.Y[ch][lane] = yr[ch];
+            for (int ch = 0; ch < 3; ++ch) yg0.Y[ch][lane] = yr[ch];
             if (GRAD && want_g) {
 #pragma unroll
-                for (int i = 0; i < 6; ++i) r0.G[i][lane] = gr[i];
+                for (int i = 0; i < 6; ++i) yg0.G[i][lane] = gr[i];
             }
         }
+        // owner row t+1 goes into the ring now; its gathers fly while the rest of this step runs
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) r0.X[ch][lane] = xr[ch];
-        r0.D[lane] = dr;
+        for (int ch = 0; ch < 3; ++ch) xdn.X[ch][lane] = xn[ch];
+        xdn.D[lane] = dn;
+        if (do_photo && t + 1 <= t_last && t + 1 < h) {
+            a_issue(ldg(sc.ytab + (t + 1)), dn, wts, dgate, taps);
+        }
 
         F2 po[3];                                  // dL/d(warped) of row t-2
 #pragma unroll
@@ -414,7 +429,7 @@ struct StripLane {
                 CS co; cs_zero(co);
                 if (rowB) {
                     HS tot; hs_add(s1[ch], H, tot);
-                    const F2 xc = r1.X[ch][lane], yc = r1.Y[ch][lane];
+                    const F2 xc = xd1.X[ch][lane], yc = yg1.Y[ch][lane];
                     const float sxq[2] = {tot.x.x, tot.x.y}, syq[2] = {tot.y.x, tot.y.y}, sxxq[2] = {tot.xx.x, tot.xx.y};
                     const float syyq[2] = {tot.yy.x, tot.yy.y}, sxyq[2] = {tot.xy.x, tot.xy.y};
                     const float xcq[2] = {xc.x, xc.y}, ycq[2] = {yc.x, yc.y};
@@ -462,7 +477,7 @@ struct StripLane {
                     // ---------------- phase C (row t-2): dL/d(warped) ----------------
                     if (doC) {
                         const F2 ba = add2(c1[ch].a, Hc.a), bb = add2(c1[ch].b, Hc.b), bc = add2(c1[ch].c, Hc.c);
-                        const F2 xv = r2.X[ch][lane], yv = r2.Y[ch][lane];
+                        const F2 xv = xd2.X[ch][lane], yv = yg2.Y[ch][lane];
                         const float d0 = xv.x - yv.x, d1 = xv.y - yv.y;
                         const float l0 = d0 > 0.f ? gl[0] : (d0 < 0.f ? -gl[0] : 0.f), l1 = d1 > 0.f ? gl[1] : (d1 < 0.f ? -gl[1] : 0.f);
                         po[ch].x = fmaf(yv.x + yv.x, bb.x, fmaf(xv.x, bc.x, ba.x)) - l0;
@@ -487,10 +502,10 @@ struct StripLane {
             float P[12], Ki[9];
             load_PK(P, Ki);
             const float yt2 = ldg(sc.ytab + r2i);
-            const F2 d2 = r2.D[lane];
+            const F2 d2 = xd2.D[lane];
             F2 g[6];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) g[i] = r2.G[i][lane];
+            for (int i = 0; i < 6; ++i) g[i] = yg2.G[i][lane];
             const float dq[2] = {d2.x, d2.y};
             const float p0[2] = {po[0].x, po[0].y}, p1[2] = {po[1].x, po[1].y}, p2[2] = {po[2].x, po[2].y};
             const float g0x[2] = {g[0].x, g[0].y}, g0y[2] = {g[1].x, g[1].y}, g1x[2] = {g[2].x, g[2].y}, g1y[2] = {g[3].x, g[3].y};
@@ -532,8 +547,8 @@ struct StripLane {
             const bool r_in = r2i >= 0 && r2i < h;
             if (r_in) {
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) xa[ch] = r2.X[ch][lane];
-                da = r2.D[lane];
+                for (int ch = 0; ch < 3; ++ch) xa[ch] = xd2.X[ch][lane];
+                da = xd2.D[lane];
             }
             {
                 const float to_left[4] = {xa[0].x, xa[1].x, xa[2].x, da.x};
@@ -547,8 +562,8 @@ struct StripLane {
                 F2 xb[3], db = F2{0.f, 0.f};
                 const bool below = r2i + 1 < h;
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) xb[ch] = below ? r1.X[ch][lane] : F2{0.f, 0.f};
-                if (below) db = r1.D[lane];
+                for (int ch = 0; ch < 3; ++ch) xb[ch] = below ? xd1.X[ch][lane] : F2{0.f, 0.f};
+                if (below) db = xd1.D[lane];
                 const float xd[2][3] = {{xb[0].x, xb[1].x, xb[2].x}, {xb[0].y, xb[1].y, xb[2].y}};
                 const float dd[2] = {db.x, db.y};
                 float vxs[2] = {0.f, 0.f}, vys[2] = {0.f, 0.f};
@@ -694,17 +709,33 @@ SNDE_STRIP_FN void strip_task(const DevLoss &p, int task, int lane, StripSmem &s
         for (int i = 0; i < 12; ++i) L.dP[i] = 0.f;
         L.sy_prev = F2{0.f, 0.f};
 
-        F2 xr[3], dr;
-        L.load_owner_row(t_begin, xr, dr);
-        int s0 = 0, s1i = 2, s2i = 1;          // ring slots of rows t, t-1, t-2
-        for (int t = t_begin; t <= t_end; ++t) {
-            F2 xn[3], dn;
-            L.load_owner_row(t + 1, xn, dn);                    // prefetch: consumed by the next step
-            L.step(t, k, sm.ring[s0], sm.ring[s1i], sm.ring[s2i], xr, dr);
+        // prologue: owner row t_begin into the ring, its gathers started
+        float wts[2][4], dgate[2][2], taps[24];
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) xr[ch] = xn[ch];
-            dr = dn;
-            const int tmp = s2i; s2i = s1i; s1i = s0; s0 = tmp;
+        for (int i = 0; i < 24; ++i) taps[i] = 0.f;
+        {
+            F2 x0[3], d0;
+            L.load_owner_row(t_begin, x0, d0);
+            RowXD &slot = sm.xd[t_begin & 3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) slot.X[ch][lane] = x0[ch];
+            slot.D[lane] = d0;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) { wts[q][0] = wts[q][1] = wts[q][2] = wts[q][3] = 0.f; dgate[q][0] = dgate[q][1] = 0.f; }
+            if (L.do_photo && t_begin < L.h) L.a_issue(ldg(sc.ytab + t_begin), d0, wts, dgate, taps);
+        }
+        F2 xn[3], dn;
+        L.load_owner_row(t_begin + 1, xn, dn);
+        int g0 = 0, g1i = 2, g2i = 1;          // warped-row ring slots of rows t, t-1, t-2
+        for (int t = t_begin; t <= t_end; ++t) {
+            F2 xnn[3], dnn;
+            L.load_owner_row(t + 2, xnn, dnn);                  // prefetch: consumed by the next step
+            L.step(t, k, sm.xd[(t + 1) & 3], sm.xd[t & 3], sm.xd[(t - 1) & 3], sm.xd[(t - 2) & 3],
+                   sm.yg[g0], sm.yg[g1i], sm.yg[g2i], xn, dn, wts, dgate, taps, t_end);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) xn[ch] = xnn[ch];
+            dn = dnn;
+            const int tmp = g2i; g2i = g1i; g1i = g0; g0 = tmp;
         }
 
         // ---- publish this pass: error sum and d/dP of pair n ----
