@@ -99,20 +99,25 @@ __global__ void __launch_bounds__(64) loss_final_kernel(int B, int S, int ns, in
     }
 }
 
-// Persistent grid: every warp pulls strip tasks from a counter until none is left.  The warps of a CTA share nothing
-// (the shared-memory rows are lane-private), so there is no CTA-wide barrier in the kernel.
+// Persistent grid: every warp PAIR pulls strip tasks from a counter until none is left.  The pairs of a CTA share
+// nothing, so there is no CTA-wide barrier in the kernel; the two warps of a pair meet at a 64-thread named barrier.
+// Warps w and w + PAIRS form a pair; which of the two is the geometry warp alternates with the CTA index, so every
+// scheduler (warp index mod 4) hosts both kinds of warp.
 template <bool GRAD, bool GRADK, bool EXTRA, bool FAST>
 __global__ void __launch_bounds__(StripCfg::NT, SNDE_STRIP_CTAS_PER_SM) loss_strip_kernel(const __grid_constant__ DevLoss p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5;
-    StripSmem &sm = reinterpret_cast<StripSmem *>(smem_raw)[warp];
+    const int pair = warp % StripCfg::PAIRS;
+    const int role = ((warp / StripCfg::PAIRS) + (int)blockIdx.x) & 1;      // 0 = geometry warp, 1 = SSIM warp
+    PairSmem &sm = reinterpret_cast<PairSmem *>(smem_raw)[pair];
+    const int bar = 1 + pair;                                               // barrier 0 is __syncthreads'
     for (;;) {
-        int task = 0;
-        if (lane == 0) task = atomicAdd(p.counter, 1);
-        task = __shfl_sync(0xffffffffu, task, 0);
+        if (role == 0 && lane == 0) sm.task = atomicAdd(p.counter, 1);
+        pair_barrier(lane, bar);
+        const int task = sm.task;        // (rewritten only after both warps went through the barriers of a whole task)
         if (task >= p.total_tasks) break;
-        strip_task<GRAD, GRADK, EXTRA, FAST>(p, task, lane, sm);
-        __syncwarp();
+        if (role == 0) geo_role<GRAD, GRADK, EXTRA, FAST>(p, task, lane, sm, bar);
+        else ssim_role<GRAD, EXTRA>(p, task, lane, sm, bar);
     }
 }
 
@@ -152,7 +157,7 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     build_prep_final(a, kp, fp);
     loss_prep_kernel<<<(ns * N + 127) / 128, 128, 0, st>>>(B, S, ns, a->poses, kp, (float *)(ws + lay.P), (float *)(ws + lay.Kinv));
     SNDE_CHECK_LAUNCH();
-    const size_t smem = sizeof(StripSmem) * StripCfg::WARPS;
+    const size_t smem = sizeof(PairSmem) * StripCfg::PAIRS;
     const bool grad = a->flags & SNDE_LOSS_GRAD, gradk = a->flags & SNDE_LOSS_GRAD_K;
     // opt in to > 48 KB dynamic shared memory once per kernel variant and device (not a stream operation; kept out of
     // the per-call path so the call can be captured into a CUDA graph after one eager warm-up)
@@ -166,9 +171,9 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, devi) != cudaSuccess || n <= 0) return SNDE_ERR_CUDA;
         sm_count[devi] = n;
     }
-    // persistent grid: as many CTAs as fit, but no more warps than tasks
+    // persistent grid: as many CTAs as fit, but no more warp pairs than tasks
     long long ctas = (long long)sm_count[devi] * SNDE_STRIP_CTAS_PER_SM;
-    const long long need = (tiles + StripCfg::WARPS - 1) / StripCfg::WARPS;
+    const long long need = (tiles + StripCfg::PAIRS - 1) / StripCfg::PAIRS;
     if (ctas > need) ctas = need;
     auto launch = [&](auto kern, int variant) -> int {
         if (!attr_done[variant][devi]) {

@@ -1,35 +1,43 @@
-// snde_strip.cuh -- the fused loss as a STREAMING STRIP PROGRAM: one warp = one vertical strip of one "owner" image.
+// snde_strip.cuh -- the fused loss as a STREAMING STRIP PROGRAM run by warp PAIRS.
 //
 // Work decomposition.  Every image of the step owns exactly one depth map:
 //   class F task: owner = target image b; "others" = its S source images, projected with
 //                 P = K4 @ T_k               (the reference's fwd direction, baseline.py:903-906)
 //   class R task: owner = source image n = k*B + b; other = the target image b, projected with
 //                 P = K4 @ inverse(T_k)      (the bwd direction, baseline.py:909-913)
-// A task is (owner, strip of 60 columns, segment of seg_h rows).  The warp walks DOWN the strip one row per step;
-// lane l owns the two adjacent region columns 2l, 2l+1 (region = the 60 inner columns + a 2-column halo each side).
-// Per step t, all in registers / lane-private shared memory, no CTA barrier anywhere:
-//   A  row t  : reproject the lane's two pixels with the owner's depth, 4-tap gather of the other image -> warped row
-//               (+ the tap derivatives, kept for phase G two steps later)
-//   B  row t-1: SSIM over the 3x3 window from rolling row sums (horizontal neighbours by shuffle, vertical by two
-//               carried rows), error value, and the three backward coefficient maps of that row
-//   C  row t-2: 3x3 box sums of the coefficient maps (same rolling scheme) -> dL/d(warped)
-//   G  row t-2: dot with the tap derivatives, back through the projection -> d/d(depth), d/dP, d/dKinv
-//   S  row t-2: (first pass only) the owner's edge-aware smoothness pairs and their depth gradient
+// A task is (owner, strip of 60 columns, segment of seg_h rows).  A pair of warps walks DOWN the strip one row per
+// step; in both warps lane l owns the two adjacent region columns 2l, 2l+1 (region = the 60 inner columns + a
+// 2-column halo each side).  The two warps are specialised and hand rows to each other through shared memory, with
+// ONE 64-thread named barrier per row and no CTA-wide barrier anywhere:
+//   geometry warp           A  row t+1: reproject the lane's two pixels with the owner's depth and start the 4-tap
+//                              gathers of the other image (software prefetch: the loads land one step later)
+//                           A' row t  : blend the gathered taps -> warped row (shared) + tap derivatives (private)
+//                           G  row t-3: dot dL/d(warped) with the tap derivatives, back through the projection
+//                                       -> d/d(depth), d/dP, d/dKinv
+//                           S  row t-3: (first pass only) the owner's edge-aware smoothness pairs + depth gradient
+//   SSIM warp               B  row t-1: SSIM over the 3x3 window from rolling row sums (horizontal neighbours by
+//                                       shuffle, vertical by two carried rows), error value, backward coefficients
+//                           C  row t-2: 3x3 box sums of the coefficient maps (same rolling scheme)
+//                                       -> dL/d(warped) row (shared)
+// Splitting the work this way halves the state a warp has to carry (the rolling sums live only in the SSIM warp; the
+// projection matrices, gather registers and gradient accumulators only in the geometry warp), which is what lets
+// enough warps be resident to hide the gather and shuffle latencies.
 // Each depth-gradient element is written by exactly one lane (passes over the S others of a class-F owner add to
 // it in a fixed order), so the gradient is deterministic; only the per-sample 3x4 / 3x3 sums and the loss scalars
 // go through (double-precision) atomics.
 //
-// The code is per-lane ("SIMT") code.  On the GPU the neighbour exchange is __shfl_*_sync; under the host-emulation
-// test harness (g++, tests/host_emul) the 32 lanes are fibers and the exchange goes through a slot array, which lets
-// the strip logic be checked against the oracle without a GPU.  The product never runs the host variant.
+// The code is per-lane ("SIMT") code.  On the GPU the neighbour exchange is __shfl_*_sync and the pair barrier is
+// bar.sync; under the host-emulation test harness (g++, tests/host_emul) the 64 lanes of a pair are fibers and both
+// go through counting barriers, which lets the strip logic be checked against the oracle without a GPU.  The
+// product never runs the host variant.
 #pragma once
 #include "snde_math.cuh"
 
 #ifndef SNDE_MAX_SCALES
 #define SNDE_MAX_SCALES 6
 #endif
-#ifndef SNDE_STRIP_WARPS
-#define SNDE_STRIP_WARPS 4
+#ifndef SNDE_STRIP_PAIRS
+#define SNDE_STRIP_PAIRS 2
 #endif
 
 namespace snde {
@@ -38,9 +46,8 @@ struct StripCfg {
     static constexpr int RW = 64;        // region columns of a strip (32 lanes x 2 columns)
     static constexpr int TW = RW - 4;    // inner columns (60)
     static constexpr int SEG = 32;       // default rows per segment
-    static constexpr int RING = 3;       // rows kept in the lane-private ring (rows t, t-1, t-2 are live)
-    static constexpr int WARPS = SNDE_STRIP_WARPS;   // warps per CTA (independent of each other)
-    static constexpr int NT = WARPS * 32;
+    static constexpr int PAIRS = SNDE_STRIP_PAIRS;   // warp pairs per CTA (independent of each other)
+    static constexpr int NT = PAIRS * 64;
     static constexpr int MAX_S = 8;      // most source views per target (SNDE_MAX_SOURCES)
 };
 
@@ -81,25 +88,20 @@ struct DevLoss {
 
 enum { FLAG_GRAD = 1, FLAG_GRAD_K = 2, FLAG_NO_PHOTO = 4, FLAG_NO_SMOOTH = 8 };   // == SNDE_LOSS_* in include/snde.h
 
-// Lane-private rows and carried sums (a register-file extension: no lane ever reads another lane's slot, so there is
-// no synchronisation on any of this).  Slot-major so that one base address per row reaches every field by an immediate.
+
 struct alignas(16) F4 { float x, y, z, w; };
-struct RowXD {
-    F2 X[3][32];                     // owner image row, 0 outside the image (= the pools' zero padding)
-    F2 D[32];                        // owner depth row
-};
-struct RowYG {
-    F2 Y[3][32];                     // warped other image row, 0 outside the image
-    F2 G[6][32];                     // d(warped_c)/dx, /dy
-};
-struct StripSmem {
-    RowXD xd[4];                     // rows t .. t-3 (slot = row & 3)
-    RowYG yg[3];                     // rows t-1 .. t-3 (rotating)
-    F4 H2a[3][2][32];                // per channel: H(t-2) = {x.x,x.y,y.x,y.y}, {xx.x,xx.y,yy.x,yy.y}
-    F2 H2b[3][32];                   //              ... {xy.x,xy.y}
-    F4 C2a[3][32];                   // per channel: Hc(t-3) = {a.x,a.y,b.x,b.y}
-    F2 C2b[3][32];                   //              ... {c.x,c.y}
-    F4 PK[6];                        // P (12 floats) and Kinv (9 floats, padded) of the current pass: warp-uniform reads
+
+// Shared memory of one warp pair.  Every element is written by one lane and read by the same lane index of either
+// warp (neighbouring columns are exchanged by shuffles inside a warp), so the only synchronisation is the pair barrier.
+struct PairSmem {
+    F2 X[4][3][32];                  // owner image rows (slot = row & 3), 0 outside the image (= the pools' zero padding)
+    F2 D[4][32];                     // owner depth rows
+    F2 Y[4][3][32];                  // warped other image rows, 0 outside the image          geometry -> SSIM
+    F2 PO[2][3][32];                 // dL/d(warped) rows (slot = row & 1)                     SSIM -> geometry
+    F2 GS[2][32];                    // smoothness part of the depth gradient (slot = row & 1) SSIM -> geometry
+    F2 G[4][6][32];                  // d(warped_c)/dx, /dy (geometry warp only)
+    F4 PK[6];                        // P (12 floats) and Kinv (9 floats, padded) of the current pass (geometry warp only)
+    int task; int pad_[3];
 };
 
 #if defined(__CUDACC__)
@@ -109,7 +111,7 @@ struct StripSmem {
 #endif
 
 // ---------------------------------------------------------------------------------------------------------------
-// warp primitives
+// warp / pair primitives.  `who` is the lane on the GPU; under host emulation it is role*32 + lane.
 // ---------------------------------------------------------------------------------------------------------------
 #if defined(__CUDA_ARCH__)
 // from_left[i] = to_right[i] of lane-1, from_right[i] = to_left[i] of lane+1 (own value at the warp's edges)
@@ -141,69 +143,67 @@ SNDE_STRIP_FN void warp_sum(int, float (&v)[N]) {
 }
 SNDE_STRIP_FN void atomic_add_double(double *dst, double v) { atomicAdd(dst, v); }
 SNDE_STRIP_FN void warp_fence(int) { __syncwarp(); }
+// rendezvous of the two warps of a pair (named barrier `bar`, 64 threads); orders their shared-memory traffic
+SNDE_STRIP_FN void pair_barrier(int, int bar) { asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory"); }
+SNDE_STRIP_FN F2 ldg2(const float *p) { const float2 v = __ldg(reinterpret_cast<const float2 *>(p)); return F2{v.x, v.y}; }
+// Pin a pointer in a register pair: stops the compiler from re-deriving it from (struct field + 64-bit offset) at
+// every use, so that base[int_offset] costs one IMAD.WIDE instead of a four-instruction 64-bit add-and-shift.
+#define SNDE_PIN_PTR(p) asm volatile("" : "+l"(p))
+#define SNDE_SCHED_FENCE() asm volatile("" ::: "memory")
 #else
-// host emulation (tests/host_emul/emul.cpp): 32 fibers; slots are double-buffered, one yield per exchange
-float *host_warp_slots(int lane, int parity);       // 64 floats per lane and parity
-void host_warp_yield();
-int &host_warp_parity(int lane);
+// host emulation (tests/host_emul/emul.cpp): 64 fibers per pair; exchange slots are double-buffered
+float *host_slots(int who, int parity);             // 64 floats per fiber and parity
+int &host_parity(int who);
+void host_warp_sync(int who);                       // barrier over the 32 fibers of who's warp
+void host_pair_sync(int who);                       // barrier over the 64 fibers of the pair
 template <int N>
-SNDE_STRIP_FN void neighbor_exchange(int lane, const float (&to_right)[N], const float (&to_left)[N], float (&from_left)[N], float (&from_right)[N]) {
+SNDE_STRIP_FN void neighbor_exchange(int who, const float (&to_right)[N], const float (&to_left)[N], float (&from_left)[N], float (&from_right)[N]) {
     static_assert(2 * N <= 64, "slot array too small");
-    const int par = host_warp_parity(lane);
-    float *mine = host_warp_slots(lane, par);
+    const int par = host_parity(who), lane = who & 31;
+    float *mine = host_slots(who, par);
     for (int i = 0; i < N; ++i) { mine[i] = to_right[i]; mine[N + i] = to_left[i]; }
-    host_warp_yield();
-    const float *l = host_warp_slots(lane > 0 ? lane - 1 : lane, par), *r = host_warp_slots(lane < 31 ? lane + 1 : lane, par);
+    host_warp_sync(who);
+    const float *l = host_slots(lane > 0 ? who - 1 : who, par), *r = host_slots(lane < 31 ? who + 1 : who, par);
     for (int i = 0; i < N; ++i) { from_left[i] = l[i]; from_right[i] = r[N + i]; }
-    host_warp_parity(lane) = par ^ 1;
+    host_parity(who) = par ^ 1;
 }
 template <int N>
-SNDE_STRIP_FN void take_from_right(int lane, const float (&to_left)[N], float (&from_right)[N]) {
+SNDE_STRIP_FN void take_from_right(int who, const float (&to_left)[N], float (&from_right)[N]) {
     float zr[N], fl[N];
     for (int i = 0; i < N; ++i) zr[i] = 0.f;
-    neighbor_exchange<N>(lane, zr, to_left, fl, from_right);
+    neighbor_exchange<N>(who, zr, to_left, fl, from_right);
 }
 template <int N>
-SNDE_STRIP_FN void take_from_left(int lane, const float (&to_right)[N], float (&from_left)[N]) {
+SNDE_STRIP_FN void take_from_left(int who, const float (&to_right)[N], float (&from_left)[N]) {
     float zl[N], fr[N];
     for (int i = 0; i < N; ++i) zl[i] = 0.f;
-    neighbor_exchange<N>(lane, to_right, zl, from_left, fr);
+    neighbor_exchange<N>(who, to_right, zl, from_left, fr);
 }
 template <int N>
-SNDE_STRIP_FN void warp_sum(int lane, float (&v)[N]) {
+SNDE_STRIP_FN void warp_sum(int who, float (&v)[N]) {
     static_assert(N <= 64, "slot array too small");
-    const int par = host_warp_parity(lane);
-    float *mine = host_warp_slots(lane, par);
+    const int par = host_parity(who), base = who & ~31;
+    float *mine = host_slots(who, par);
     for (int i = 0; i < N; ++i) mine[i] = v[i];
-    host_warp_yield();
+    host_warp_sync(who);
     for (int i = 0; i < N; ++i) {
         float part[32];
-        for (int l = 0; l < 32; ++l) part[l] = host_warp_slots(l, par)[i];
+        for (int l = 0; l < 32; ++l) part[l] = host_slots(base + l, par)[i];
         for (int o = 16; o > 0; o >>= 1) for (int l = 0; l < o; ++l) part[l] += part[l + o];   // same pairing as the xor butterfly
         v[i] = part[0];
     }
-    host_warp_parity(lane) = par ^ 1;
+    host_parity(who) = par ^ 1;
 }
 SNDE_STRIP_FN void atomic_add_double(double *dst, double v) { *dst += v; }
-SNDE_STRIP_FN void warp_fence(int) { host_warp_yield(); }
-#endif
-
-#if defined(__CUDA_ARCH__)
-SNDE_STRIP_FN F2 ldg2(const float *p) { const float2 v = __ldg(reinterpret_cast<const float2 *>(p)); return F2{v.x, v.y}; }
-#else
+SNDE_STRIP_FN void warp_fence(int who) { host_warp_sync(who); }
+SNDE_STRIP_FN void pair_barrier(int who, int) { host_pair_sync(who); }
 SNDE_STRIP_FN F2 ldg2(const float *p) { return F2{p[0], p[1]}; }
-#endif
-
-// Pin a pointer in a register pair: stops the compiler from re-deriving it from (struct field + 64-bit offset) at
-// every use, so that base[int_offset] costs one IMAD.WIDE instead of a four-instruction 64-bit add-and-shift.
-#if defined(__CUDA_ARCH__)
-#define SNDE_PIN_PTR(p) asm volatile("" : "+l"(p))
-#else
 #define SNDE_PIN_PTR(p) ((void)0)
+#define SNDE_SCHED_FENCE() ((void)0)
 #endif
 
-// horizontal 3-sums of one row for the lane's two columns (same association as the reference-order tile program:
-// left column = left neighbour + (a + b), right column = (a + b) + right neighbour)
+// horizontal 3-sums of one row for the lane's two columns (left column = left neighbour + (a + b), right column =
+// (a + b) + right neighbour: the association the golden-vector tolerances were measured with)
 struct HS { F2 x, y, xx, yy, xy; };
 struct CS { F2 a, b, c; };
 
@@ -220,40 +220,276 @@ SNDE_STRIP_FN F2 add2(const F2 a, const F2 b) { return F2{a.x + b.x, a.y + b.y};
 SNDE_STRIP_FN void hs_add(const HS &a, const HS &b, HS &o) {
     o.x = add2(a.x, b.x); o.y = add2(a.y, b.y); o.xx = add2(a.xx, b.xx); o.yy = add2(a.yy, b.yy); o.xy = add2(a.xy, b.xy);
 }
+SNDE_STRIP_FN void cs_add(const CS &a, const CS &b, CS &o) { o.a = add2(a.a, b.a); o.b = add2(a.b, b.b); o.c = add2(a.c, b.c); }
 SNDE_STRIP_FN void hs_zero(HS &o) { o.x = o.y = o.xx = o.yy = o.xy = F2{0.f, 0.f}; }
 SNDE_STRIP_FN void cs_zero(CS &o) { o.a = o.b = o.c = F2{0.f, 0.f}; }
 
-// per-task constants and accumulators of one lane
-template <bool GRAD, bool GRADK, bool EXTRA, bool FAST>
-struct StripLane {
-    using C = StripCfg;
-    const DevLoss &p;
-    const DevScale &sc;
-    StripSmem &sm;
-    int lane, h, w, y0, y1, ix0;
-    bool do_smooth, do_photo;
+// ---------------------------------------------------------------------------------------------------------------
+// what both warps of a pair derive from the task number (uniform over the pair, except the column flags)
+// ---------------------------------------------------------------------------------------------------------------
+struct StripTask {
+    int scale, m, b, h, w, y0, y1, ix0, t_begin, t_end, n_others, n_pass;
+    bool clsF, do_smooth, do_photo;
     bool in[2], colB[2], colI[2];
     float mI[2];              // 1 for an inner in-image column, else 0
+};
+
+SNDE_STRIP_FN void decode_task(const DevLoss &p, int task, int lane, StripTask &T) {
+    using C = StripCfg;
+    int e = 0;
+    while (e + 1 < p.num_entries && task >= p.entry[e + 1].begin) ++e;
+    const DevEntry ent = p.entry[e];
+    const DevScale &sc = p.sc[ent.scale];
+    const int local = task - ent.begin;
+    const int per_owner = sc.tiles_x * sc.tiles_y;
+    T.scale = ent.scale;
+    T.m = local / per_owner;                         // owner index inside its class
+    const int tt = local - T.m * per_owner;
+    const int sy = tt / sc.tiles_x, sx = tt - sy * sc.tiles_x;
+    T.h = sc.h; T.w = sc.w;
+    T.y0 = sy * sc.seg_h; T.y1 = T.y0 + sc.seg_h < sc.h ? T.y0 + sc.seg_h : sc.h;
+    T.ix0 = sx * C::TW - 2 + 2 * lane;
+    T.clsF = ent.cls == 0;
+    T.b = T.clsF ? T.m : (T.m % p.B);                // batch element (selects K)
+    T.do_smooth = !(p.flags & FLAG_NO_SMOOTH);
+    T.do_photo = !(p.flags & FLAG_NO_PHOTO);
+    T.n_others = T.do_photo ? (T.clsF ? p.S : 1) : 0;
+    T.n_pass = T.n_others > 0 ? T.n_others : 1;      // smoothness alone still needs one pass over the owner
+    T.t_begin = T.y0 - 2 > 0 ? T.y0 - 2 : 0;         // rows above the image are zero rows == the initial state
+    T.t_end = T.y1 + 1;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int c = 2 * lane + q, ix = T.ix0 + q;
+        T.in[q] = ix >= 0 && ix < T.w;
+        T.colB[q] = T.in[q] && c >= 1 && c <= C::RW - 2;
+        T.colI[q] = T.in[q] && c >= 2 && c <= C::RW - 3;
+        T.mI[q] = T.colI[q] ? 1.f : 0.f;
+    }
+}
+
+// ===============================================================================================================
+// SSIM warp
+// ===============================================================================================================
+template <bool GRAD, bool EXTRA>
+SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, int bar) {
+    const int lane = who & 31;
+    StripTask T;
+    decode_task(p, task, lane, T);
+    const DevScale &sc = p.sc[T.scale];
+    const float alpha = p.alpha, oma = p.oma, g1 = p.oma * sc.gphoto;
     float gSm[2];             // -0.5*alpha*gphoto where the column takes part in phase B, else 0
+#pragma unroll
+    for (int q = 0; q < 2; ++q) gSm[q] = T.colB[q] ? -0.5f * p.alpha * sc.gphoto : 0.f;
+    const int y0 = T.y0, y1 = T.y1, h = T.h;
+    float sx_acc = 0.f, sy_acc = 0.f;
+
+    for (int k = 0; k < T.n_pass; ++k) {
+        const long long n = T.clsF ? (long long)k * p.B + T.b : T.m;      // index into the N-sized tensors
+        const float *mask_base = nullptr; int mask_sh = 0, mask_sw = 0;
+        float *eout_base = nullptr; int eout_sc = 0, eout_sh = 0, eout_sw = 0;
+        if (EXTRA) {
+            const DevMap &mask = T.clsF ? sc.mask_fwd : sc.mask_bwd;
+            const DevImageOut &eout = T.clsF ? sc.err_fwd : sc.err_bwd;
+            mask_base = mask.p ? mask.p + n * mask.sn : nullptr; mask_sh = mask.sh; mask_sw = mask.sw;
+            eout_base = eout.p ? eout.p + n * eout.sn : nullptr; eout_sc = eout.sc; eout_sh = eout.sh; eout_sw = eout.sw;
+        }
+        const bool has_mask = EXTRA && mask_base != nullptr;
+        // rolling sums: the two carried rows start as zero rows
+        HS s1[3], s2[3];          // H(t-2) + H(t-1), H(t-1)
+        CS c1[3], c2[3];          // Hc(t-3) + Hc(t-2), Hc(t-2)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) { hs_zero(s1[ch]); hs_zero(s2[ch]); cs_zero(c1[ch]); cs_zero(c2[ch]); }
+        float err_acc = 0.f;
+        F2 sy_prev = F2{0.f, 0.f};    // signed smoothness weights of the vertical pairs starting one row above
+
+        for (int t = T.t_begin; t <= T.t_end + 1; ++t) {
+            pair_barrier(who, bar);              // row t of the warped image is in shared memory
+            if (t > T.t_end) continue;
+            // smoothness of row t-2 (first pass only).  One step earlier (row y0-1) only the vertical pair weights are
+            // formed: they are the "pair above" of the first inner row.
+            if (T.do_smooth && k == 0 && t - 2 >= y0 - 1) {
+                const int r = t - 2, w = T.w, ix0 = T.ix0;
+                const bool doG = t >= y0 + 2;          // an inner row (the step before it only the pair above is formed)
+                F2 sxw = F2{0.f, 0.f}, syw = F2{0.f, 0.f};
+                float nb_x[4] = {0.f, 0.f, 0.f, 0.f};          // right neighbour column: image (3) + depth
+                F2 xa[3], da = F2{0.f, 0.f};
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) xa[ch] = F2{0.f, 0.f};
+                const bool r_in = r >= 0 && r < h;
+                if (r_in) {
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) xa[ch] = sm.X[r & 3][ch][lane];
+                    da = sm.D[r & 3][lane];
+                }
+                {
+                    const float to_left[4] = {xa[0].x, xa[1].x, xa[2].x, da.x};
+                    take_from_right<4>(who, to_left, nb_x);
+                }
+                if (r_in) {
+                    const float xq[2][3] = {{xa[0].x, xa[1].x, xa[2].x}, {xa[0].y, xa[1].y, xa[2].y}};
+                    const float xn[2][3] = {{xa[0].y, xa[1].y, xa[2].y}, {nb_x[0], nb_x[1], nb_x[2]}};
+                    const float dq[2] = {da.x, da.y}, dn[2] = {da.y, nb_x[3]};
+                    F2 xb[3], db = F2{0.f, 0.f};
+                    const bool below = r + 1 < h;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) xb[ch] = below ? sm.X[(r + 1) & 3][ch][lane] : F2{0.f, 0.f};
+                    if (below) db = sm.D[(r + 1) & 3][lane];
+                    const float xd[2][3] = {{xb[0].x, xb[1].x, xb[2].x}, {xb[0].y, xb[1].y, xb[2].y}};
+                    const float dd[2] = {db.x, db.y};
+                    float vxs[2] = {0.f, 0.f}, vys[2] = {0.f, 0.f};
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const float mi = doG ? T.mI[q] : 0.f;
+                        {
+                            const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xn[q][0], xn[q][1], xn[q][2]);
+                            const float v = (dq[q] - dn[q]) * wgt;
+                            const float sgn = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
+                            const bool ok = T.colB[q] && ix0 + q + 1 < w;
+                            vxs[q] = ok ? sgn : 0.f;
+                            sx_acc = fmaf(ok ? fabsf(v) : 0.f, mi, sx_acc);
+                        }
+                        {
+                            const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xd[q][0], xd[q][1], xd[q][2]);
+                            const float v = (dq[q] - dd[q]) * wgt;
+                            const float sgn = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
+                            const bool ok = T.colB[q] && below;
+                            vys[q] = ok ? sgn : 0.f;
+                            sy_acc = fmaf(ok ? fabsf(v) : 0.f, mi, sy_acc);
+                        }
+                    }
+                    sxw = F2{vxs[0], vxs[1]}; syw = F2{vys[0], vys[1]};
+                }
+                // the horizontal pair that ENDS at the lane's left column starts in the left neighbour lane
+                float sx_left;
+                {
+                    const float to_right[1] = {sxw.y};
+                    float from_left[1];
+                    take_from_left<1>(who, to_right, from_left);
+                    sx_left = from_left[0];
+                }
+                if (GRAD && doG)
+                    sm.GS[r & 1][lane] = F2{sc.gsx * (sxw.x - sx_left) + sc.gsy * (syw.x - sy_prev.x),
+                                            sc.gsx * (sxw.y - sxw.x) + sc.gsy * (syw.y - sy_prev.y)};
+                sy_prev = syw;
+            }
+            if (!T.do_photo) continue;
+            const int rb = t - 1, rc = t - 2;
+            const bool doB = t >= y0, doC = t >= y0 + 2;
+            const bool rowB = doB && rb >= 0 && rb < h;
+            const bool row_inner = rb >= y0 && rb < y1;
+            float mk[2] = {1.f, 1.f}, gl[2] = {g1, g1};
+            if (has_mask) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (rowB && T.colB[q]) mk[q] = ldg(mask_base + rb * mask_sh + (T.ix0 + q) * mask_sw);
+                    if (GRAD && doC && T.colI[q]) gl[q] = g1 * ldg(mask_base + rc * mask_sh + (T.ix0 + q) * mask_sw);
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                // ---------------- horizontal sums of row t ----------------
+                const F2 xr = sm.X[t & 3][ch][lane], yr = sm.Y[t & 3][ch][lane];
+                HS H;
+                {
+                    const float to_right[2] = {xr.y, yr.y}, to_left[2] = {xr.x, yr.x};
+                    float from_left[2], from_right[2];
+                    neighbor_exchange<2>(who, to_right, to_left, from_left, from_right);
+                    hsum_row(xr, yr, from_left[0], from_right[0], from_left[1], from_right[1], H);
+                }
+                // ---------------- phase B (row t-1) ----------------
+                CS co; cs_zero(co);
+                if (rowB) {
+                    HS tot; hs_add(s1[ch], H, tot);
+                    const F2 xc = sm.X[rb & 3][ch][lane], yc = sm.Y[rb & 3][ch][lane];
+                    const float sxq[2] = {tot.x.x, tot.x.y}, syq[2] = {tot.y.x, tot.y.y}, sxxq[2] = {tot.xx.x, tot.xx.y};
+                    const float syyq[2] = {tot.yy.x, tot.yy.y}, sxyq[2] = {tot.xy.x, tot.xy.y};
+                    const float xcq[2] = {xc.x, xc.y}, ycq[2] = {yc.x, yc.y};
+                    float ca[2], cb[2], cc[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        SsimS ss; ssim_sums(sxq[q], syq[q], sxxq[q], syyq[q], sxyq[q], ss);
+                        const float v = fmaf(-0.5f, ss.S, 0.5f), vc = clampf(v, 0.f, 1.f);
+                        const float err = fmaf(alpha, vc, oma * fabsf(xcq[q] - ycq[q]));
+                        if (row_inner) {
+                            err_acc = fmaf(EXTRA ? err * mk[q] : err, T.mI[q], err_acc);
+                            if (EXTRA && eout_base && T.colI[q]) eout_base[ch * eout_sc + rb * eout_sh + (T.ix0 + q) * eout_sw] = err;
+                        }
+                        ca[q] = cb[q] = cc[q] = 0.f;
+                        if (GRAD) {
+                            const float gS = (v == vc) ? (EXTRA ? gSm[q] * mk[q] : gSm[q]) : 0.f;     // the clamp passes gradient inside [0,1] only
+                            ssim_sums_bwd(ss, sxq[q], syq[q], gS, ca[q], cb[q], cc[q]);
+                        }
+                    }
+                    co.a = F2{ca[0], ca[1]}; co.b = F2{cb[0], cb[1]}; co.c = F2{cc[0], cc[1]};
+                }
+                hs_add(s2[ch], H, s1[ch]);        // s1 <- H(t-1) + H(t)
+                s2[ch] = H;
+                if (GRAD) {
+                    // ---------------- horizontal sums of the coefficient row t-1 ----------------
+                    CS Hc;
+                    {
+                        const float to_right[3] = {co.a.y, co.b.y, co.c.y}, to_left[3] = {co.a.x, co.b.x, co.c.x};
+                        float from_left[3], from_right[3];
+                        neighbor_exchange<3>(who, to_right, to_left, from_left, from_right);
+                        const float ta = co.a.x + co.a.y, tb = co.b.x + co.b.y, tc = co.c.x + co.c.y;
+                        Hc.a = F2{from_left[0] + ta, ta + from_right[0]};
+                        Hc.b = F2{from_left[1] + tb, tb + from_right[1]};
+                        Hc.c = F2{from_left[2] + tc, tc + from_right[2]};
+                    }
+                    // ---------------- phase C (row t-2): dL/d(warped) ----------------
+                    if (doC) {
+                        CS bs; cs_add(c1[ch], Hc, bs);
+                        const F2 xv = sm.X[rc & 3][ch][lane], yv = sm.Y[rc & 3][ch][lane];
+                        const float d0 = xv.x - yv.x, d1 = xv.y - yv.y;
+                        const float l0 = d0 > 0.f ? gl[0] : (d0 < 0.f ? -gl[0] : 0.f), l1 = d1 > 0.f ? gl[1] : (d1 < 0.f ? -gl[1] : 0.f);
+                        F2 po;
+                        po.x = fmaf(yv.x + yv.x, bs.b.x, fmaf(xv.x, bs.c.x, bs.a.x)) - l0;
+                        po.y = fmaf(yv.y + yv.y, bs.b.y, fmaf(xv.y, bs.c.y, bs.a.y)) - l1;
+                        sm.PO[rc & 1][ch][lane] = po;
+                    }
+                    cs_add(c2[ch], Hc, c1[ch]);   // c1 <- Hc(t-2) + Hc(t-1)
+                    c2[ch] = Hc;
+                }
+            }
+        }
+        // ---- publish this pass: error sum of pair n ----
+        if (T.n_others > 0) {
+            float v[1] = {err_acc};
+            warp_sum<1>(who, v);
+            if (lane == 0 && v[0] != 0.f) atomic_add_double(sc.loss + (T.clsF ? 0 : 1), (double)v[0]);
+        }
+    }
+    // ---- publish the per-owner smoothness sums ----
+    if (T.do_smooth) {
+        float v[2] = {sx_acc, sy_acc};
+        warp_sum<2>(who, v);
+        if (lane < 2) { const float mine = lane == 0 ? v[0] : v[1]; if (mine != 0.f) atomic_add_double(sc.loss + 2 + lane, (double)mine); }
+    }
+}
+
+// ===============================================================================================================
+// geometry warp
+// ===============================================================================================================
+template <bool GRAD, bool GRADK, bool EXTRA, bool FAST>
+struct GeoLane {
+    const DevLoss &p;
+    const DevScale &sc;
+    PairSmem &sm;
+    const StripTask &T;
+    int lane;
     float xt[2];
-    float alpha, oma, g1;
     // owner
     const float *own_base; int own_sc, own_sh, own_sw;
     const float *dep_base; int dep_sh, dep_sw;
     float *gd_base; int gd_sh, gd_sw;
     // current other image
     const float *oth_base; int oth_sc, oth_sh, oth_sw;
-    const float *mask_base; int mask_sh, mask_sw;
     float *wout_base; int wout_sc, wout_sh, wout_sw;
-    float *eout_base; int eout_sc, eout_sh, eout_sw;
     // accumulators
-    float dP[12], dK[9], err_acc, sx_acc, sy_acc;
-    // rolling state kept in registers (the other carried row lives in sm.H2 / sm.C2)
-    HS s1[3];                 // H(t-2) + H(t-1)
-    CS c1[3];                 // Hc(t-3) + Hc(t-2)
-    F2 sy_prev;               // signed smoothness weights of the vertical pairs starting one row above
+    float dP[12], dK[9];
 
-    SNDE_STRIP_FN StripLane(const DevLoss &p_, const DevScale &sc_, StripSmem &sm_, int lane_) : p(p_), sc(sc_), sm(sm_), lane(lane_) {}
+    SNDE_STRIP_FN GeoLane(const DevLoss &p_, const DevScale &sc_, PairSmem &sm_, const StripTask &T_, int lane_)
+        : p(p_), sc(sc_), sm(sm_), T(T_), lane(lane_) {}
 
     SNDE_STRIP_FN void load_PK(float (&P)[12], float (&Ki)[9]) const {
         const F4 a = sm.PK[0], b = sm.PK[1], c = sm.PK[2], d = sm.PK[3], e = sm.PK[4], f = sm.PK[5];
@@ -265,28 +501,28 @@ struct StripLane {
     // ---- owner row iy (image + depth) for the lane's two columns; zeros outside the image ----
     SNDE_STRIP_FN void load_owner_row(int iy, F2 (&x)[3], F2 &d) const {
         x[0] = x[1] = x[2] = d = F2{0.f, 0.f};
-        if (iy < 0 || iy >= h) return;
+        if (iy < 0 || iy >= T.h) return;
         if (FAST) {
-            if (in[0]) {          // w and ix0 are even: the pair is inside or outside together
-                const int q = iy * own_sh + ix0;
+            if (T.in[0]) {          // w and ix0 are even: the pair is inside or outside together
+                const int q = iy * own_sh + T.ix0;
                 x[0] = ldg2(own_base + q); x[1] = ldg2(own_base + (q + own_sc)); x[2] = ldg2(own_base + (q + 2 * own_sc));
-                d = ldg2(dep_base + (iy * dep_sh + ix0));
+                d = ldg2(dep_base + (iy * dep_sh + T.ix0));
             }
         } else {
-            if (in[0]) {
-                const int q = iy * own_sh + ix0 * own_sw;
+            if (T.in[0]) {
+                const int q = iy * own_sh + T.ix0 * own_sw;
                 x[0].x = ldg(own_base + q); x[1].x = ldg(own_base + (q + own_sc)); x[2].x = ldg(own_base + (q + 2 * own_sc));
-                d.x = ldg(dep_base + (iy * dep_sh + ix0 * dep_sw));
+                d.x = ldg(dep_base + (iy * dep_sh + T.ix0 * dep_sw));
             }
-            if (in[1]) {
-                const int q = iy * own_sh + (ix0 + 1) * own_sw;
+            if (T.in[1]) {
+                const int q = iy * own_sh + (T.ix0 + 1) * own_sw;
                 x[0].y = ldg(own_base + q); x[1].y = ldg(own_base + (q + own_sc)); x[2].y = ldg(own_base + (q + 2 * own_sc));
-                d.y = ldg(dep_base + (iy * dep_sh + (ix0 + 1) * dep_sw));
+                d.y = ldg(dep_base + (iy * dep_sh + (T.ix0 + 1) * dep_sw));
             }
         }
     }
 
-    // ---- phase A, first half: reproject the lane's two pixels of row iy (in the image) and start the 24 gathers;
+    // ---- phase A, first half: reproject the lane's two pixels of a row (in the image) and start the 24 gathers;
     //      the loads land in registers that nothing touches until the next step (software prefetch) ----
     // wts[q] = {wx0, wx1, wy0, wy1} of pixel q (all zero for a pixel that samples nothing); border mode also needs the
     // derivative gates, kept in dgate[q] = {dx, dy}.
@@ -297,6 +533,7 @@ struct StripLane {
         const float dq[2] = {d.x, d.y};
         const float *ob = oth_base;
         SNDE_PIN_PTR(ob);
+        const int h = T.h, w = T.w;
         // Branch-free per pixel: an invalid pixel samples address 0 of the image with four zero weights.
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -308,7 +545,7 @@ struct StripLane {
             // residue that grows with the distance from the image); the fused path writes the exact zero.
             if (EXTRA && p.padding) { make_taps(x, yy, h, w, p.padding, tp); valid = true; }   // border mode samples everywhere
             else { make_taps_valid(x, yy, tp); valid = tap_valid(x, yy, h, w, 0) != 0.f; }
-            valid = valid && in[q];
+            valid = valid && T.in[q];
             const int o00 = valid ? tp.y0 * oth_sh + tp.x0 * (FAST ? 1 : oth_sw) : 0;
             // row / column steps to the second tap (0 when border mode clamped both taps onto the same pixel)
             int dyo = oth_sh, dxo = FAST ? 1 : oth_sw;
@@ -329,7 +566,8 @@ struct StripLane {
     }
 
     // ---- phase A, second half (one step later): blend the gathered taps -> warped row (+ tap derivatives) ----
-    SNDE_STRIP_FN void a_finish(int iy, const float (&wts)[2][4], const float (&dgate)[2][2], const float (&taps)[24], bool want_g, F2 (&y)[3], F2 (&g)[6]) const {
+    SNDE_STRIP_FN void a_finish(int iy, const float (&wts)[2][4], const float (&dgate)[2][2], const float (&taps)[24], bool want_g,
+                                F2 (&y)[3], F2 (&g)[6]) const {
         float yv[2][3], gv[2][6];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -347,8 +585,8 @@ struct StripLane {
                     if (EXTRA) { gv[q][2 * ch] *= dgate[q][0]; gv[q][2 * ch + 1] *= dgate[q][1]; }
                 }
             }
-            if (EXTRA && wout_base && colI[q] && iy >= y0 && iy < y1) {
-                float *o = wout_base + iy * wout_sh + (ix0 + q) * wout_sw;
+            if (EXTRA && wout_base && T.colI[q] && iy >= T.y0 && iy < T.y1) {
+                float *o = wout_base + iy * wout_sh + (T.ix0 + q) * wout_sw;
                 o[0] = yv[q][0]; o[wout_sc] = yv[q][1]; o[2 * wout_sc] = yv[q][2];
             }
         }
@@ -358,161 +596,28 @@ struct StripLane {
         for (int i = 0; i < 6; ++i) g[i] = F2{gv[0][i], gv[1][i]};
     }
 
-    SNDE_STRIP_FN float mask_at(int iy, int ix) const { return ldg(mask_base + iy * mask_sh + ix * mask_sw); }
-
-    // ---- one step of the stream.  Row t+1 starts its gathers, row t (gathered during the previous step) is blended
-    //      and enters the sums, rows t-1 (B) and t-2 (C, G, S) are finished ----
-    //   xd0..xd2 : owner rows t, t-1, t-2;  yg0..yg2 : warped rows t, t-1, t-2;  xn, dn : owner row t+1 (prefetched)
-    //   wts / dgate / taps : bilinear weights and gathered taps of row t on entry, of row t+1 on exit;  pass k (0 = first pass over this owner)
-    SNDE_STRIP_FN void step(int t, int k, RowXD &xdn, const RowXD &xd0, const RowXD &xd1, const RowXD &xd2,
-                            RowYG &yg0, const RowYG &yg1, const RowYG &yg2, const F2 (&xn)[3], const F2 dn,
-                            float (&wts)[2][4], float (&dgate)[2][2], float (&taps)[24], int t_last) {
-        const bool row_in = t >= 0 && t < h;
-        const bool doB = t >= y0;               // row t-1 needs its coefficient maps (rows y0-1 .. y1)
-        const bool doC = t >= y0 + 2;           // row t-2 is an inner row (y0 .. y1-1)
-        const bool has_mask = EXTRA && mask_base != nullptr;
-        F2 xr[3];
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) xr[ch] = xd0.X[ch][lane];
-
-        // ---------------- phase A: finish row t, start row t+1 ----------------
-        F2 yr[3];
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) yr[ch] = F2{0.f, 0.f};
-        if (do_photo) {
-            F2 gr[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) gr[i] = F2{0.f, 0.f};
-            const bool want_g = t >= y0 && t < y1;
-            if (row_in) a_finish(t, wts, dgate, taps, want_g, yr, gr);
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) yg0.Y[ch][lane] = yr[ch];
-            if (GRAD && want_g) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) yg0.G[i][lane] = gr[i];
-            }
-        }
-        // owner row t+1 goes into the ring now; its gathers fly while the rest of this step runs
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) xdn.X[ch][lane] = xn[ch];
-        xdn.D[lane] = dn;
-        if (do_photo && t + 1 <= t_last && t + 1 < h) {
-            a_issue(ldg(sc.ytab + (t + 1)), dn, wts, dgate, taps);
-        }
-
-        F2 po[3];                                  // dL/d(warped) of row t-2
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) po[ch] = F2{0.f, 0.f};
-        if (do_photo) {
-            const int rb = t - 1, rc = t - 2;
-            const bool rowB = doB && rb >= 0 && rb < h;
-            const bool row_inner = rb >= y0 && rb < y1;
-            float mk[2] = {1.f, 1.f}, gl[2] = {g1, g1};
-            if (has_mask) {
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    if (rowB && colB[q]) mk[q] = mask_at(rb, ix0 + q);
-                    if (GRAD && doC && colI[q]) gl[q] = g1 * mask_at(rc, ix0 + q);
-                }
-            }
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                // ---------------- horizontal sums of row t ----------------
-                HS H;
-                {
-                    const float to_right[2] = {xr[ch].y, yr[ch].y}, to_left[2] = {xr[ch].x, yr[ch].x};
-                    float from_left[2], from_right[2];
-                    neighbor_exchange<2>(lane, to_right, to_left, from_left, from_right);
-                    hsum_row(xr[ch], yr[ch], from_left[0], from_right[0], from_left[1], from_right[1], H);
-                }
-                // ---------------- phase B (row t-1) ----------------
-                CS co; cs_zero(co);
-                if (rowB) {
-                    HS tot; hs_add(s1[ch], H, tot);
-                    const F2 xc = xd1.X[ch][lane], yc = yg1.Y[ch][lane];
-                    const float sxq[2] = {tot.x.x, tot.x.y}, syq[2] = {tot.y.x, tot.y.y}, sxxq[2] = {tot.xx.x, tot.xx.y};
-                    const float syyq[2] = {tot.yy.x, tot.yy.y}, sxyq[2] = {tot.xy.x, tot.xy.y};
-                    const float xcq[2] = {xc.x, xc.y}, ycq[2] = {yc.x, yc.y};
-                    float ca[2], cb[2], cc[2];
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        SsimS ss; ssim_sums(sxq[q], syq[q], sxxq[q], syyq[q], sxyq[q], ss);
-                        const float v = fmaf(-0.5f, ss.S, 0.5f), vc = clampf(v, 0.f, 1.f);
-                        const float err = fmaf(alpha, vc, oma * fabsf(xcq[q] - ycq[q]));
-                        if (row_inner) {
-                            err_acc = fmaf(EXTRA ? err * mk[q] : err, mI[q], err_acc);
-                            if (EXTRA && eout_base && colI[q]) eout_base[ch * eout_sc + rb * eout_sh + (ix0 + q) * eout_sw] = err;
-                        }
-                        ca[q] = cb[q] = cc[q] = 0.f;
-                        if (GRAD) {
-                            const float gS = (v == vc) ? (EXTRA ? gSm[q] * mk[q] : gSm[q]) : 0.f;     // the clamp passes gradient inside [0,1] only
-                            ssim_sums_bwd(ss, sxq[q], syq[q], gS, ca[q], cb[q], cc[q]);
-                        }
-                    }
-                    co.a = F2{ca[0], ca[1]}; co.b = F2{cb[0], cb[1]}; co.c = F2{cc[0], cc[1]};
-                }
-                // roll: s1 <- H(t-1) + H(t); H(t) replaces H(t-1) in the lane's shared slot
-                {
-                    const F4 pa = sm.H2a[ch][0][lane], pb = sm.H2a[ch][1][lane];
-                    const F2 pc = sm.H2b[ch][lane];
-                    s1[ch].x = add2(F2{pa.x, pa.y}, H.x); s1[ch].y = add2(F2{pa.z, pa.w}, H.y);
-                    s1[ch].xx = add2(F2{pb.x, pb.y}, H.xx); s1[ch].yy = add2(F2{pb.z, pb.w}, H.yy);
-                    s1[ch].xy = add2(pc, H.xy);
-                    sm.H2a[ch][0][lane] = F4{H.x.x, H.x.y, H.y.x, H.y.y};
-                    sm.H2a[ch][1][lane] = F4{H.xx.x, H.xx.y, H.yy.x, H.yy.y};
-                    sm.H2b[ch][lane] = H.xy;
-                }
-                if (GRAD) {
-                    // ---------------- horizontal sums of the coefficient row t-1 ----------------
-                    CS Hc;
-                    {
-                        const float to_right[3] = {co.a.y, co.b.y, co.c.y}, to_left[3] = {co.a.x, co.b.x, co.c.x};
-                        float from_left[3], from_right[3];
-                        neighbor_exchange<3>(lane, to_right, to_left, from_left, from_right);
-                        const float ta = co.a.x + co.a.y, tb = co.b.x + co.b.y, tc = co.c.x + co.c.y;
-                        Hc.a = F2{from_left[0] + ta, ta + from_right[0]};
-                        Hc.b = F2{from_left[1] + tb, tb + from_right[1]};
-                        Hc.c = F2{from_left[2] + tc, tc + from_right[2]};
-                    }
-                    // ---------------- phase C (row t-2): dL/d(warped) ----------------
-                    if (doC) {
-                        const F2 ba = add2(c1[ch].a, Hc.a), bb = add2(c1[ch].b, Hc.b), bc = add2(c1[ch].c, Hc.c);
-                        const F2 xv = xd2.X[ch][lane], yv = yg2.Y[ch][lane];
-                        const float d0 = xv.x - yv.x, d1 = xv.y - yv.y;
-                        const float l0 = d0 > 0.f ? gl[0] : (d0 < 0.f ? -gl[0] : 0.f), l1 = d1 > 0.f ? gl[1] : (d1 < 0.f ? -gl[1] : 0.f);
-                        po[ch].x = fmaf(yv.x + yv.x, bb.x, fmaf(xv.x, bc.x, ba.x)) - l0;
-                        po[ch].y = fmaf(yv.y + yv.y, bb.y, fmaf(xv.y, bc.y, ba.y)) - l1;
-                    }
-                    // roll: c1 <- Hc(t-2) + Hc(t-1)
-                    {
-                        const F4 pa = sm.C2a[ch][lane];
-                        const F2 pc = sm.C2b[ch][lane];
-                        c1[ch].a = add2(F2{pa.x, pa.y}, Hc.a); c1[ch].b = add2(F2{pa.z, pa.w}, Hc.b); c1[ch].c = add2(pc, Hc.c);
-                        sm.C2a[ch][lane] = F4{Hc.a.x, Hc.a.y, Hc.b.x, Hc.b.y};
-                        sm.C2b[ch][lane] = Hc.c;
-                    }
-                }
-            }
-        }
-
-        // ---------------- rows t-2: phase G, smoothness, depth-gradient write ----------------
-        const int r2i = t - 2;
+    // ---- row r = t-3 is finished: phase G, depth-gradient write ----
+    SNDE_STRIP_FN void finish_row(int r, int k) {
+        const int y0 = T.y0, ix0 = T.ix0;
+        const bool doG = r >= y0;                  // an inner row (r <= y1-1 by construction of the loop)
         float gd[2] = {0.f, 0.f};
-        if (GRAD && do_photo && doC && (FAST ? colI[0] : (colI[0] || colI[1]))) {
+        if (GRAD && T.do_photo && doG && (FAST ? T.colI[0] : (T.colI[0] || T.colI[1]))) {
             float P[12], Ki[9];
             load_PK(P, Ki);
-            const float yt2 = ldg(sc.ytab + r2i);
-            const F2 d2 = xd2.D[lane];
-            F2 g[6];
+            const float yt2 = ldg(sc.ytab + r);
+            const F2 d2 = sm.D[r & 3][lane];
+            F2 g[6], po[3];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) g[i] = yg2.G[i][lane];
+            for (int i = 0; i < 6; ++i) g[i] = sm.G[r & 3][i][lane];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) po[ch] = sm.PO[r & 1][ch][lane];
             const float dq[2] = {d2.x, d2.y};
             const float p0[2] = {po[0].x, po[0].y}, p1[2] = {po[1].x, po[1].y}, p2[2] = {po[2].x, po[2].y};
             const float g0x[2] = {g[0].x, g[0].y}, g0y[2] = {g[1].x, g[1].y}, g1x[2] = {g[2].x, g[2].y}, g1y[2] = {g[3].x, g[3].y};
             const float g2x[2] = {g[4].x, g[4].y}, g2y[2] = {g[5].x, g[5].y};
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                if (!FAST && !colI[q]) continue;
+                if (!FAST && !T.colI[q]) continue;
                 const float gx = fmaf(p2[q], g2x[q], fmaf(p1[q], g1x[q], p0[q] * g0x[q]));
                 const float gy = fmaf(p2[q], g2y[q], fmaf(p1[q], g1y[q], p0[q] * g0y[q]));
                 Reproj rp; reproject_nodiv(Ki, P, xt[q], yt2, dq[q], rp);
@@ -536,78 +641,15 @@ struct StripLane {
                 }
             }
         }
-        // smoothness of row t-2 (first pass only).  One step earlier (row y0-1) only the vertical pair weights are
-        // formed: they are the "pair above" of the first inner row.
-        if (do_smooth && k == 0 && t >= y0 + 1) {
-            F2 sxw = F2{0.f, 0.f}, syw = F2{0.f, 0.f};
-            float nb_x[4] = {0.f, 0.f, 0.f, 0.f};          // right neighbour column: image (3) + depth
-            F2 xa[3], da = F2{0.f, 0.f};
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) xa[ch] = F2{0.f, 0.f};
-            const bool r_in = r2i >= 0 && r2i < h;
-            if (r_in) {
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) xa[ch] = xd2.X[ch][lane];
-                da = xd2.D[lane];
-            }
-            {
-                const float to_left[4] = {xa[0].x, xa[1].x, xa[2].x, da.x};
-                take_from_right<4>(lane, to_left, nb_x);
-            }
-            if (r_in) {
-                const bool inner_row = doC;
-                const float xq[2][3] = {{xa[0].x, xa[1].x, xa[2].x}, {xa[0].y, xa[1].y, xa[2].y}};
-                const float xn[2][3] = {{xa[0].y, xa[1].y, xa[2].y}, {nb_x[0], nb_x[1], nb_x[2]}};
-                const float dq[2] = {da.x, da.y}, dn[2] = {da.y, nb_x[3]};
-                F2 xb[3], db = F2{0.f, 0.f};
-                const bool below = r2i + 1 < h;
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) xb[ch] = below ? xd1.X[ch][lane] : F2{0.f, 0.f};
-                if (below) db = xd1.D[lane];
-                const float xd[2][3] = {{xb[0].x, xb[1].x, xb[2].x}, {xb[0].y, xb[1].y, xb[2].y}};
-                const float dd[2] = {db.x, db.y};
-                float vxs[2] = {0.f, 0.f}, vys[2] = {0.f, 0.f};
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const float mi = inner_row ? mI[q] : 0.f;
-                    {
-                        const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xn[q][0], xn[q][1], xn[q][2]);
-                        const float v = (dq[q] - dn[q]) * wgt;
-                        const float sgn = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
-                        const bool ok = colB[q] && ix0 + q + 1 < w;
-                        vxs[q] = ok ? sgn : 0.f;
-                        sx_acc = fmaf(ok ? fabsf(v) : 0.f, mi, sx_acc);
-                    }
-                    {
-                        const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xd[q][0], xd[q][1], xd[q][2]);
-                        const float v = (dq[q] - dd[q]) * wgt;
-                        const float sgn = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
-                        const bool ok = colB[q] && below;
-                        vys[q] = ok ? sgn : 0.f;
-                        sy_acc = fmaf(ok ? fabsf(v) : 0.f, mi, sy_acc);
-                    }
-                }
-                sxw = F2{vxs[0], vxs[1]}; syw = F2{vys[0], vys[1]};
-            }
-            // the horizontal pair that ENDS at the lane's left column starts in the left neighbour lane
-            float sx_left;
-            {
-                const float to_right[1] = {sxw.y};
-                float from_left[1];
-                take_from_left<1>(lane, to_right, from_left);
-                sx_left = from_left[0];
-            }
-            if (GRAD && doC) {
-                gd[0] += sc.gsx * (sxw.x - sx_left) + sc.gsy * (syw.x - sy_prev.x);
-                gd[1] += sc.gsx * (sxw.y - sxw.x) + sc.gsy * (syw.y - sy_prev.y);
-            }
-            sy_prev = syw;
+        if (GRAD && doG && T.do_smooth && k == 0) {      // smoothness part, computed by the SSIM warp
+            const F2 gs = sm.GS[r & 1][lane];
+            gd[0] += gs.x; gd[1] += gs.y;
         }
-        if (GRAD && doC && in[0]) {
+        if (GRAD && doG && T.in[0]) {
             // every lane writes only its own inner pixels; later passes over the same owner add to what this lane wrote
             if (FAST) {
-                if (colI[0]) {     // inner lanes hold two inner pixels (w even)
-                    float *dst = gd_base + (r2i * gd_sh + ix0);
+                if (T.colI[0]) {     // inner lanes hold two inner pixels (w even)
+                    float *dst = gd_base + (r * gd_sh + ix0);
                     F2 o = F2{gd[0], gd[1]};
                     if (k > 0) { const F2 old = *reinterpret_cast<const F2 *>(dst); o.x += old.x; o.y += old.y; }
                     *reinterpret_cast<F2 *>(dst) = o;
@@ -615,8 +657,8 @@ struct StripLane {
             } else {
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    if (!colI[q]) continue;
-                    float *dst = gd_base + (r2i * gd_sh + (ix0 + q) * gd_sw);
+                    if (!T.colI[q]) continue;
+                    float *dst = gd_base + (r * gd_sh + (ix0 + q) * gd_sw);
                     *dst = k > 0 ? *dst + gd[q] : gd[q];
                 }
             }
@@ -624,146 +666,127 @@ struct StripLane {
     }
 };
 
-// The strip program: one task, all passes.  GRAD: also back-propagate.  GRADK: also accumulate d/dKinv.
-// EXTRA: honour the optional explainability masks, warped / error-map outputs and border padding.
-// FAST: planar tensors with unit x-stride and 8-byte aligned rows (64-bit loads / stores of the lane's pixel pair).
+// GRAD: also back-propagate.  GRADK: also accumulate d/dKinv.  EXTRA: honour the optional explainability masks,
+// warped / error-map outputs and border padding.  FAST: planar tensors with unit x-stride and 8-byte aligned rows
+// (64-bit loads / stores of the lane's pixel pair).
 template <bool GRAD, bool GRADK, bool EXTRA, bool FAST>
-SNDE_STRIP_FN void strip_task(const DevLoss &p, int task, int lane, StripSmem &sm) {
-    using C = StripCfg;
-    // ---- decode the task (uniform over the warp) ----
-    int e = 0;
-    while (e + 1 < p.num_entries && task >= p.entry[e + 1].begin) ++e;
-    const DevEntry ent = p.entry[e];
-    const DevScale &sc = p.sc[ent.scale];
-    const int local = task - ent.begin;
-    const int per_owner = sc.tiles_x * sc.tiles_y;
-    const int m = local / per_owner;                 // owner index inside its class
-    const int tt = local - m * per_owner;
-    const int sy = tt / sc.tiles_x, sx = tt - sy * sc.tiles_x;
-    const int B = p.B, S = p.S;
-
-    StripLane<GRAD, GRADK, EXTRA, FAST> L(p, sc, sm, lane);
-    L.h = sc.h; L.w = sc.w;
-    L.y0 = sy * sc.seg_h; L.y1 = L.y0 + sc.seg_h < sc.h ? L.y0 + sc.seg_h : sc.h;
-    L.ix0 = sx * C::TW - 2 + 2 * lane;
-    const bool clsF = ent.cls == 0;
-    L.do_smooth = !(p.flags & FLAG_NO_SMOOTH);
-    L.do_photo = !(p.flags & FLAG_NO_PHOTO);
-    L.alpha = p.alpha; L.oma = p.oma;
-    L.g1 = p.oma * sc.gphoto;
+SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, int bar) {
+    const int lane = who & 31;
+    StripTask T;
+    decode_task(p, task, lane, T);
+    const DevScale &sc = p.sc[T.scale];
+    const int B = p.B;
+    GeoLane<GRAD, GRADK, EXTRA, FAST> L(p, sc, sm, T, lane);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int c = 2 * lane + q, ix = L.ix0 + q;
-        L.in[q] = ix >= 0 && ix < L.w;
-        L.colB[q] = L.in[q] && c >= 1 && c <= C::RW - 2;
-        L.colI[q] = L.in[q] && c >= 2 && c <= C::RW - 3;
-        L.mI[q] = L.colI[q] ? 1.f : 0.f;
-        L.gSm[q] = L.colB[q] ? -0.5f * p.alpha * sc.gphoto : 0.f;
-        L.xt[q] = L.in[q] ? ldg(sc.xtab + ix) : 0.f;
-    }
-    const int b = clsF ? m : (m % B);                // batch element (selects K)
+    for (int q = 0; q < 2; ++q) L.xt[q] = T.in[q] ? ldg(sc.xtab + (T.ix0 + q)) : 0.f;
+    const bool clsF = T.clsF;
+    const int m = T.m, b = T.b;
     const DevImage &own = clsF ? sc.tgt : sc.src;
     L.own_base = own.p + (long long)m * own.sn; L.own_sc = own.sc; L.own_sh = own.sh; L.own_sw = own.sw;
     const long long depth_n = clsF ? m : (long long)B + m;
     L.dep_base = sc.depth.p + depth_n * sc.depth.sn; L.dep_sh = sc.depth.sh; L.dep_sw = sc.depth.sw;
     L.gd_base = GRAD ? sc.gdepth.p + depth_n * sc.gdepth.sn : nullptr; L.gd_sh = sc.gdepth.sh; L.gd_sw = sc.gdepth.sw;
     SNDE_PIN_PTR(L.own_base); SNDE_PIN_PTR(L.dep_base);
-    const int n_others = L.do_photo ? (clsF ? S : 1) : 0;
-    const int n_pass = n_others > 0 ? n_others : 1;  // smoothness alone still needs one pass over the owner
-    L.sx_acc = 0.f; L.sy_acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 9; ++i) L.dK[i] = 0.f;
     const float *Kinv = sc.Kinv + 9 * b;
-    const int t_begin = L.y0 - 2 > 0 ? L.y0 - 2 : 0, t_end = L.y1 + 1;     // rows above the image are zero rows == the initial state
+    const int t_begin = T.t_begin, t_end = T.t_end, h = T.h;
 
-    for (int k = 0; k < n_pass; ++k) {
+    for (int k = 0; k < T.n_pass; ++k) {
         const long long n = clsF ? (long long)k * B + b : m;      // index into the N-sized tensors
         const DevImage &oth = clsF ? sc.src : sc.tgt;
         L.oth_base = oth.p + (clsF ? n : (long long)b) * oth.sn; L.oth_sc = oth.sc; L.oth_sh = oth.sh; L.oth_sw = oth.sw;
+        L.wout_base = nullptr; L.wout_sc = L.wout_sh = L.wout_sw = 0;
         if (EXTRA) {
-            const DevMap &mask = clsF ? sc.mask_fwd : sc.mask_bwd;
             const DevImageOut &wout = clsF ? sc.warped_fwd : sc.warped_bwd;
-            const DevImageOut &eout = clsF ? sc.err_fwd : sc.err_bwd;
-            L.mask_base = mask.p ? mask.p + n * mask.sn : nullptr; L.mask_sh = mask.sh; L.mask_sw = mask.sw;
             L.wout_base = wout.p ? wout.p + n * wout.sn : nullptr; L.wout_sc = wout.sc; L.wout_sh = wout.sh; L.wout_sw = wout.sw;
-            L.eout_base = eout.p ? eout.p + n * eout.sn : nullptr; L.eout_sc = eout.sc; L.eout_sh = eout.sh; L.eout_sw = eout.sw;
-        } else {
-            L.mask_base = nullptr; L.wout_base = nullptr; L.eout_base = nullptr;
         }
-        warp_fence(lane);                 // every lane is done with the previous pass's matrices
-        if (n_others > 0 && lane < 24) {
+        warp_fence(who);                  // every lane is done with the previous pass's matrices
+        if (T.n_others > 0 && lane < 24) {
             const float *Pn = sc.P + (n * 2 + (clsF ? 0 : 1)) * 12;
             float *pk = reinterpret_cast<float *>(sm.PK);
             pk[lane] = lane < 12 ? ldg(Pn + lane) : (lane < 21 ? ldg(Kinv + (lane - 12)) : 0.f);
         }
-        // carried rows start as zero rows
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            hs_zero(L.s1[ch]); cs_zero(L.c1[ch]);
-            sm.H2a[ch][0][lane] = F4{0.f, 0.f, 0.f, 0.f}; sm.H2a[ch][1][lane] = F4{0.f, 0.f, 0.f, 0.f}; sm.H2b[ch][lane] = F2{0.f, 0.f};
-            sm.C2a[ch][lane] = F4{0.f, 0.f, 0.f, 0.f}; sm.C2b[ch][lane] = F2{0.f, 0.f};
-        }
-        warp_fence(lane);                 // the matrices are visible to every lane
-        L.err_acc = 0.f;
+        warp_fence(who);                  // the matrices are visible to every lane
 #pragma unroll
         for (int i = 0; i < 12; ++i) L.dP[i] = 0.f;
-        L.sy_prev = F2{0.f, 0.f};
 
         // prologue: owner row t_begin into the ring, its gathers started
         float wts[2][4], dgate[2][2], taps[24];
 #pragma unroll
         for (int i = 0; i < 24; ++i) taps[i] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { wts[q][0] = wts[q][1] = wts[q][2] = wts[q][3] = 0.f; dgate[q][0] = dgate[q][1] = 0.f; }
         {
             F2 x0[3], d0;
             L.load_owner_row(t_begin, x0, d0);
-            RowXD &slot = sm.xd[t_begin & 3];
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) slot.X[ch][lane] = x0[ch];
-            slot.D[lane] = d0;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) { wts[q][0] = wts[q][1] = wts[q][2] = wts[q][3] = 0.f; dgate[q][0] = dgate[q][1] = 0.f; }
-            if (L.do_photo && t_begin < L.h) L.a_issue(ldg(sc.ytab + t_begin), d0, wts, dgate, taps);
+            for (int ch = 0; ch < 3; ++ch) sm.X[t_begin & 3][ch][lane] = x0[ch];
+            sm.D[t_begin & 3][lane] = d0;
+            if (T.do_photo && t_begin < h) L.a_issue(ldg(sc.ytab + t_begin), d0, wts, dgate, taps);
         }
         F2 xn[3], dn;
         L.load_owner_row(t_begin + 1, xn, dn);
-        int g0 = 0, g1i = 2, g2i = 1;          // warped-row ring slots of rows t, t-1, t-2
-        for (int t = t_begin; t <= t_end; ++t) {
+        float yt_n = t_begin + 1 < h ? ldg(sc.ytab + (t_begin + 1)) : 0.f;      // meshgrid y of row t+1, fetched a step ahead
+
+        for (int t = t_begin; t <= t_end + 1; ++t) {
+            // ---- finish row t: the warped row goes to the SSIM warp, the tap derivatives stay here ----
+            if (T.do_photo && t <= t_end) {
+                F2 yr[3], gr[6];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) yr[ch] = F2{0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 6; ++i) gr[i] = F2{0.f, 0.f};
+                const bool want_g = t >= T.y0 && t < T.y1;
+                if (t < h) L.a_finish(t, wts, dgate, taps, want_g, yr, gr);
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) sm.Y[t & 3][ch][lane] = yr[ch];
+                if (GRAD && want_g) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) sm.G[t & 3][i][lane] = gr[i];
+                }
+            }
+            pair_barrier(who, bar);       // rows <= t of X, Y are published; dL/d(warped) of row t-3 is ready
+            // ---- start row t+1: its gathers fly while the rest of this step runs ----
+            if (T.do_photo && t + 1 <= t_end && t + 1 < h) L.a_issue(yt_n, dn, wts, dgate, taps);
             F2 xnn[3], dnn;
             L.load_owner_row(t + 2, xnn, dnn);                  // prefetch: consumed by the next step
-            L.step(t, k, sm.xd[(t + 1) & 3], sm.xd[t & 3], sm.xd[(t - 1) & 3], sm.xd[(t - 2) & 3],
-                   sm.yg[g0], sm.yg[g1i], sm.yg[g2i], xn, dn, wts, dgate, taps, t_end);
+            yt_n = t + 2 < h ? ldg(sc.ytab + (t + 2)) : 0.f;
+            // ---- row t-3: back-projection, smoothness, depth gradient ----
+            if (t - 3 >= T.y0) L.finish_row(t - 3, k);
+            // ---- owner row t+1 into the ring (its slot held row t-3 until now) ----
+            if (t + 1 <= t_end) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) sm.X[(t + 1) & 3][ch][lane] = xn[ch];
+                sm.D[(t + 1) & 3][lane] = dn;
+            }
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) xn[ch] = xnn[ch];
             dn = dnn;
-            const int tmp = g2i; g2i = g1i; g1i = g0; g0 = tmp;
         }
 
-        // ---- publish this pass: error sum and d/dP of pair n ----
-        if (n_others > 0) {
-            float v[13];
+        // ---- publish this pass: d/dP of pair n ----
+        if (GRAD && T.n_others > 0) {
+            float v[12];
 #pragma unroll
             for (int i = 0; i < 12; ++i) v[i] = L.dP[i];
-            v[12] = L.err_acc;
-            warp_sum<13>(lane, v);
+            warp_sum<12>(who, v);
             float mine = 0.f;
 #pragma unroll
-            for (int i = 0; i < 13; ++i) if (lane == i) mine = v[i];
-            if (GRAD && lane < 12 && mine != 0.f) atomic_add_double(sc.gP + (n * 2 + (clsF ? 0 : 1)) * 12 + lane, (double)mine);
-            if (lane == 12 && mine != 0.f) atomic_add_double(sc.loss + (clsF ? 0 : 1), (double)mine);
+            for (int i = 0; i < 12; ++i) if (lane == i) mine = v[i];
+            if (lane < 12 && mine != 0.f) atomic_add_double(sc.gP + (n * 2 + (clsF ? 0 : 1)) * 12 + lane, (double)mine);
         }
     }
-    // ---- publish the per-owner sums: smoothness, d/dKinv ----
-    {
-        float v[11];
+    // ---- publish the per-owner sums: d/dKinv ----
+    if (GRADK) {
+        float v[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) v[i] = L.dK[i];
-        v[9] = L.sx_acc; v[10] = L.sy_acc;
-        warp_sum<11>(lane, v);
+        warp_sum<9>(who, v);
         float mine = 0.f;
 #pragma unroll
-        for (int i = 0; i < 11; ++i) if (lane == i) mine = v[i];
-        if (GRADK && lane < 9 && mine != 0.f) atomic_add_double(sc.gKinv + 9 * b + lane, (double)mine);
-        if ((lane == 9 || lane == 10) && mine != 0.f) atomic_add_double(sc.loss + 2 + (lane - 9), (double)mine);
+        for (int i = 0; i < 9; ++i) if (lane == i) mine = v[i];
+        if (lane < 9 && mine != 0.f) atomic_add_double(sc.gKinv + 9 * b + lane, (double)mine);
     }
 }
 

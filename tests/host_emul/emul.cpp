@@ -1,6 +1,6 @@
 // Host emulation of the fused loss strip program -- TEST HARNESS ONLY (never shipped, never a
-// fallback).  Compiles csrc/snde_strip.cuh with g++: the 32 lanes of a warp run as 32 fibers
-// (ucontext) that are switched round-robin at every warp exchange, so the per-lane device code
+// fallback).  Compiles csrc/snde_strip.cuh with g++: the 64 lanes of a warp pair run as 64 fibers
+// (ucontext) that block on counting barriers at every warp exchange / pair barrier, so the per-lane device code
 // -- halo columns, rolling row sums, zero padding, task table, gradient ownership -- can be
 // checked against the oracle in the GPU-less authoring container.
 // All pointers in SndeLossArgs are HOST pointers here.
@@ -14,53 +14,71 @@
 using namespace snde;
 
 // ---------------------------------------------------------------------------------------------
-// the emulated warp
+// the emulated warp pair: 64 fibers (0..31 geometry warp, 32..63 SSIM warp), cooperative round-robin
 // ---------------------------------------------------------------------------------------------
 namespace {
-struct HostWarp {
-    static constexpr int STACK = 1 << 18;
-    ucontext_t main_ctx, lane_ctx[32];
+struct SyncObj { int count = 0; int gen = 0; };
+struct HostPair {
+    static constexpr int STACK = 1 << 18, NF = 64;
+    ucontext_t main_ctx, ctx[NF];
     std::vector<char> stacks;
-    float slots[2][32][64];
-    int parity[32];
-    bool done[32];
+    float slots[2][NF][64];
+    int parity[NF];
+    bool done[NF];
     int current = -1;
+    SyncObj warp_sync[2], pair_sync;
     // the task being run
-    const DevLoss *p = nullptr; int task = 0; int variant = 0; StripSmem *sm = nullptr;
-} g_warp;
+    const DevLoss *p = nullptr; int task = 0; int variant = 0; PairSmem *sm = nullptr;
+} g_pair;
 
-void lane_main(int lane) {
-    HostWarp &w = g_warp;
-    switch (w.variant) {
-        case 0: strip_task<false, false, true, false>(*w.p, w.task, lane, *w.sm); break;
-        case 1: strip_task<false, false, false, true>(*w.p, w.task, lane, *w.sm); break;
-        case 2: strip_task<false, false, false, false>(*w.p, w.task, lane, *w.sm); break;
-        case 3: strip_task<true, true, true, false>(*w.p, w.task, lane, *w.sm); break;
-        case 4: strip_task<true, false, false, true>(*w.p, w.task, lane, *w.sm); break;
-        default: strip_task<true, false, false, false>(*w.p, w.task, lane, *w.sm); break;
-    }
-    w.done[lane] = true;
+void yield_to_scheduler() { const int f = g_pair.current; swapcontext(&g_pair.ctx[f], &g_pair.main_ctx); }
+
+void sync_on(SyncObj &s, int n) {
+    const int g = s.gen;
+    if (++s.count == n) { s.count = 0; ++s.gen; return; }
+    while (s.gen == g) yield_to_scheduler();
 }
 
-void run_warp_task(const DevLoss &p, int task, int variant, StripSmem &sm) {
-    HostWarp &w = g_warp;
-    if (w.stacks.empty()) w.stacks.resize((size_t)32 * HostWarp::STACK);
-    w.p = &p; w.task = task; w.variant = variant; w.sm = &sm;
-    for (int l = 0; l < 32; ++l) {
-        w.parity[l] = 0; w.done[l] = false;
-        getcontext(&w.lane_ctx[l]);
-        w.lane_ctx[l].uc_stack.ss_sp = w.stacks.data() + (size_t)l * HostWarp::STACK;
-        w.lane_ctx[l].uc_stack.ss_size = HostWarp::STACK;
-        w.lane_ctx[l].uc_link = &w.main_ctx;
-        makecontext(&w.lane_ctx[l], (void (*)())lane_main, 1, l);
+template <bool GRAD, bool GRADK, bool EXTRA, bool FAST>
+void run_role(int who) {
+    HostPair &w = g_pair;
+    if (who < 32) geo_role<GRAD, GRADK, EXTRA, FAST>(*w.p, w.task, who, *w.sm, 1);
+    else ssim_role<GRAD, EXTRA>(*w.p, w.task, who, *w.sm, 1);
+}
+
+void fiber_main(int who) {
+    HostPair &w = g_pair;
+    switch (w.variant) {
+        case 0: run_role<false, false, true, false>(who); break;
+        case 1: run_role<false, false, false, true>(who); break;
+        case 2: run_role<false, false, false, false>(who); break;
+        case 3: run_role<true, true, true, false>(who); break;
+        case 4: run_role<true, false, false, true>(who); break;
+        default: run_role<true, false, false, false>(who); break;
     }
-    // lock-step at exchange granularity: every live lane runs up to its next exchange, then the next lane
+    w.done[who] = true;
+}
+
+void run_pair_task(const DevLoss &p, int task, int variant, PairSmem &sm) {
+    HostPair &w = g_pair;
+    if (w.stacks.empty()) w.stacks.resize((size_t)HostPair::NF * HostPair::STACK);
+    w.p = &p; w.task = task; w.variant = variant; w.sm = &sm;
+    w.warp_sync[0] = SyncObj(); w.warp_sync[1] = SyncObj(); w.pair_sync = SyncObj();
+    for (int l = 0; l < HostPair::NF; ++l) {
+        w.parity[l] = 0; w.done[l] = false;
+        getcontext(&w.ctx[l]);
+        w.ctx[l].uc_stack.ss_sp = w.stacks.data() + (size_t)l * HostPair::STACK;
+        w.ctx[l].uc_stack.ss_size = HostPair::STACK;
+        w.ctx[l].uc_link = &w.main_ctx;
+        makecontext(&w.ctx[l], (void (*)())fiber_main, 1, l);
+    }
+    // every live fiber runs until it blocks on a barrier (or finishes), then the next one
     for (bool any = true; any;) {
         any = false;
-        for (int l = 0; l < 32; ++l) {
+        for (int l = 0; l < HostPair::NF; ++l) {
             if (w.done[l]) continue;
             w.current = l;
-            swapcontext(&w.main_ctx, &w.lane_ctx[l]);
+            swapcontext(&w.main_ctx, &w.ctx[l]);
             any = any || !w.done[l];
         }
     }
@@ -68,9 +86,10 @@ void run_warp_task(const DevLoss &p, int task, int variant, StripSmem &sm) {
 }  // namespace
 
 namespace snde {
-float *host_warp_slots(int lane, int parity) { return g_warp.slots[parity][lane]; }
-int &host_warp_parity(int lane) { return g_warp.parity[lane]; }
-void host_warp_yield() { const int l = g_warp.current; swapcontext(&g_warp.lane_ctx[l], &g_warp.main_ctx); }
+float *host_slots(int who, int parity) { return g_pair.slots[parity][who]; }
+int &host_parity(int who) { return g_pair.parity[who]; }
+void host_warp_sync(int who) { sync_on(g_pair.warp_sync[who >> 5], 32); }
+void host_pair_sync(int) { sync_on(g_pair.pair_sync, 64); }
 }  // namespace snde
 
 extern "C" __attribute__((visibility("default"))) size_t emul_sizeof_loss_args(void) { return sizeof(SndeLossArgs); }
@@ -100,10 +119,10 @@ extern "C" __attribute__((visibility("default"))) int emul_loss_fwdbwd(const Snd
         fast = fast && d.sc[s].fast;
     }
     const int variant = !grad ? (extra ? 0 : (fast ? 1 : 2)) : (extra ? 3 : (fast ? 4 : 5));
-    StripSmem *sm = new StripSmem;
+    PairSmem *sm = new PairSmem;
     for (int64_t t = 0; t < tasks; ++t) {
-        memset(sm, 0xff, sizeof(StripSmem));   // NaN-fill: catches reads of unwritten shared memory
-        run_warp_task(d, (int)t, variant, *sm);
+        memset(sm, 0xff, sizeof(PairSmem));    // NaN-fill: catches reads of unwritten shared memory
+        run_pair_task(d, (int)t, variant, *sm);
     }
     delete sm;
     loss_final_host(B, S, ns, a->flags, a->poses, fp, (const double *)(ws + lay.gP), (const double *)(ws + lay.gKinv),
