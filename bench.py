@@ -9,7 +9,8 @@ synthetic KITTI-shaped frames (BASELINE.json configs[1]: 128x416, B=32 per GPU, 
   value  : warped pixels / s with inputs resident in HBM (CUDA-graph replay of the C-ABI call, 4 rotating
            input sets = 540 MB > L2, CUDA events, max over ranks).
   e2e    : same metric through the public autograd API (snde_b200.loss_functions.geonet_loss + backward) with
-           HOST buffers: pinned H2D copy of every input and D2H read of loss + all gradients inside the timed region.
+           HOST buffers: pinned H2D copy of every input and D2H read of loss + all gradients inside the timed region
+           (copies and compute of consecutive steps overlap on three streams).
   roofline : algorithmic bytes (60 B per warped pixel + 36 B per smoothness pixel) / step time.
   cpu_baseline : oracle/torch_port.py (the reference's ATen op chain restated) on this box's host cores.
 --impl reference times that CPU path alone (rank 0 only).
@@ -230,26 +231,60 @@ def main():
     out_host = [torch.empty_like(t).pin_memory() for t in h_dep] + [torch.empty_like(host.poses).pin_memory(), torch.empty(3 + 3 * cfg["num_scales"]).pin_memory()]
     d2h = sum(t.numel() * 4 for t in out_host)
 
+    # Two device input sets and three streams: the H2D copy of step i+1, the fused loss of step i and the D2H read of
+    # step i-1 overlap (every byte still moves every step, inside the timed region).
+    NBUF = 2
+    dev_in = [dict(tgt=[torch.empty_like(t, device=dev) for t in h_tgt], src=[torch.empty_like(t, device=dev) for t in h_src],
+                   dep=[torch.empty_like(t, device=dev) for t in h_dep], poses=torch.empty_like(h_poses, device=dev),
+                   K=torch.empty_like(h_K, device=dev)) for _ in range(NBUF)]
+    s_h2d, s_run, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    ev_in = [torch.cuda.Event() for _ in range(NBUF)]      # inputs of set j are on the device
+    ev_free = [torch.cuda.Event() for _ in range(NBUF)]    # set j has been consumed
+    ev_out = torch.cuda.Event()
+    step_no = [0]
+
     def e2e_step():
-        tgt = [t.to(dev, non_blocking=True) for t in h_tgt]
-        src = [t.to(dev, non_blocking=True) for t in h_src]
-        dep = [t.to(dev, non_blocking=True).requires_grad_(True) for t in h_dep]
-        poses = h_poses.to(dev, non_blocking=True).requires_grad_(True)
-        K = h_K.to(dev, non_blocking=True)
-        total, detail = geonet_loss(tgt, src, dep, poses, K)
-        total.backward()
-        for o, g in zip(out_host, [t.grad for t in dep] + [poses.grad, detail]):
-            o.copy_(g, non_blocking=True)
+        j = step_no[0] % NBUF
+        step_no[0] += 1
+        d = dev_in[j]
+        with torch.cuda.stream(s_h2d):
+            s_h2d.wait_event(ev_free[j])
+            for dst, srcs in ((d["tgt"], h_tgt), (d["src"], h_src), (d["dep"], h_dep)):
+                for a, b in zip(dst, srcs):
+                    a.copy_(b, non_blocking=True)
+            d["poses"].copy_(h_poses, non_blocking=True)
+            d["K"].copy_(h_K, non_blocking=True)
+            ev_in[j].record(s_h2d)
+        with torch.cuda.stream(s_run):
+            s_run.wait_event(ev_in[j])
+            s_run.wait_event(ev_out)                           # the previous step's results have left their buffers
+            dep = [t.detach().requires_grad_(True) for t in d["dep"]]
+            poses = d["poses"].detach().requires_grad_(True)
+            total, detail = geonet_loss(d["tgt"], d["src"], dep, poses, d["K"])
+            total.backward()
+            grads = [t.grad for t in dep] + [poses.grad, detail]
+            ev_free[j].record(s_run)
+        with torch.cuda.stream(s_d2h):
+            s_d2h.wait_event(ev_free[j])
+            for o, g in zip(out_host, grads):
+                o.copy_(g, non_blocking=True)
+                g.record_stream(s_d2h)
+            ev_out.record(s_d2h)
 
     e2e_steps = 0 if args.no_e2e else max(5, min(args.steps, 30))
     for _ in range(3 if e2e_steps else 0):
         e2e_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    cur = torch.cuda.current_stream(dev)
+    e0.record(cur)
+    for s_ in (s_h2d, s_run, s_d2h):
+        s_.wait_event(e0)
     for _ in range(e2e_steps):
         e2e_step()
-    e1.record()
+    for s_ in (s_h2d, s_run, s_d2h):
+        cur.wait_stream(s_)
+    e1.record(cur)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     if world > 1:
@@ -266,6 +301,13 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of the strip kernel, one launch, from the committed ncu capture
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("workload") == args.workload:
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -278,11 +320,11 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "ms_per_step": e2e_ms / e2e_steps if e2e_steps else None, "loss_check": e2e_loss},
             "gpu_launches": 3 * args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_step": algo_bytes,
-                         "note": "duration = whole step (memset + prep + tile kernel + finalize); the tile kernel is >95% of it "
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_step": algo_bytes, "traffic_source": traffic_src,
+                         "note": "duration = whole step (memset + prep + strip kernel + finalize); the strip kernel is 96% of it "
                                  "(profiles/). Bytes per SURVEY 8(d): 60 B/warped px + 36 B/smooth px, as for separate fwd and bwd "
-                                 "passes; the single-pass kernel actually moves less (DESIGN.md section 5)."},
+                                 "passes; the single-pass kernel moves less and is instruction-issue bound (DESIGN.md section 5)."},
         }
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_baseline(cfg, iters=3, batch=min(cfg["B"], 8))

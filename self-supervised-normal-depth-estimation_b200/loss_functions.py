@@ -74,6 +74,37 @@ def inverse_warp(img, depth, pose, intrinsics, reverse_pose=False, padding_mode=
     return warped, valid
 
 
+_PLAN_CACHE: "dict[tuple, ops.FusedLossPlan]" = {}
+_PLAN_CACHE_MAX = 16
+
+
+def _cached_plan(cfg, poses, K_ms, depth_pyr, tgt_pyr, src_pyr, need, want_K):
+    """FusedLossPlan for these exact buffers (pointers, shapes, strides) and options.  A trainer that keeps its input
+    buffers (or a CUDA-graph style static step) hits the cache and skips the per-call allocation and marshalling."""
+    def sig(t):
+        return (t.data_ptr(), tuple(t.shape), tuple(t.stride()))
+    masks = cfg["masks"]
+    key = (sig(poses), sig(K_ms), tuple(sig(t) for t in depth_pyr), tuple(sig(t) for t in tgt_pyr), tuple(sig(t) for t in src_pyr),
+           cfg["alpha"], tuple(cfg["photo_weights"]), tuple(cfg["smooth_weights"]), need, want_K, cfg["padding_mode"],
+           None if masks is None else tuple((sig(a), sig(b)) for a, b in masks), cfg["no_photo"], cfg["no_smooth"])
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        if not poses.is_contiguous() or not K_ms.is_contiguous():
+            # the plan would hold private contiguous copies: not reusable
+            return ops.FusedLossPlan(tgt_pyr, src_pyr, depth_pyr, poses, K_ms, cfg["alpha"], cfg["photo_weights"], cfg["smooth_weights"],
+                                     want_grad=need, want_grad_K=want_K, padding_mode=cfg["padding_mode"], masks=masks,
+                                     no_photo=cfg["no_photo"], no_smooth=cfg["no_smooth"])
+        if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+        plan = ops.FusedLossPlan(tgt_pyr, src_pyr, depth_pyr, poses, K_ms, cfg["alpha"], cfg["photo_weights"], cfg["smooth_weights"],
+                                 want_grad=need, want_grad_K=want_K, padding_mode=cfg["padding_mode"], masks=masks,
+                                 no_photo=cfg["no_photo"], no_smooth=cfg["no_smooth"])
+        _PLAN_CACHE[key] = plan
+    else:
+        plan.refresh_intrinsics(K_ms)            # same buffer, possibly new values
+    return plan
+
+
 class _FusedLoss(torch.autograd.Function):
     """loss_total (differentiable w.r.t. poses, depth_pyr, K_ms) + (loss_rigid_warp, loss_disp_smooth) for logging.
     Gradients are produced in the same single pass as the loss and scaled by the upstream gradient here."""
@@ -85,22 +116,26 @@ class _FusedLoss(torch.autograd.Function):
         tgt_pyr, src_pyr = rest[ns:2 * ns], rest[2 * ns:3 * ns]
         need = any(ctx.needs_input_grad)
         want_K = ctx.needs_input_grad[2]
-        plan = ops.FusedLossPlan(tgt_pyr, src_pyr, depth_pyr, poses.detach(), K_ms.detach(), cfg["alpha"], cfg["photo_weights"],
-                                 cfg["smooth_weights"], want_grad=need, want_grad_K=want_K, padding_mode=cfg["padding_mode"],
-                                 masks=cfg["masks"], no_photo=cfg["no_photo"], no_smooth=cfg["no_smooth"])
+        plan = _cached_plan(cfg, poses.detach(), K_ms.detach(), depth_pyr, tgt_pyr, src_pyr, need, want_K)
         plan.run()
-        ctx.plan = plan if need else None
-        out = plan.loss_out
+        out = plan.loss_out.clone()              # the plan's buffers are rewritten by the next call on the same inputs
+        if need:
+            # gradients for upstream gradient 1, copied out of the (possibly shared) plan in stream order
+            ctx.ns, ctx.has_K = ns, plan.grad_K is not None
+            ctx.save_for_backward(plan.grad_poses.clone(), *([plan.grad_K.clone()] if ctx.has_K else []),
+                                  *[g.clone() for g in plan.grad_depth])
         ctx.mark_non_differentiable(out)
         return out[0].clone(), out
 
     @staticmethod
     def backward(ctx, g, _g_all):
-        plan = ctx.plan
-        ns = plan.ns
-        gd = [t * g for t in plan.grad_depth]
-        return (None, plan.grad_poses * g if ctx.needs_input_grad[1] else None,
-                plan.grad_K * g if plan.grad_K is not None else None, *gd, *([None] * (2 * ns)))
+        saved = ctx.saved_tensors
+        ns = ctx.ns
+        gposes = saved[0]
+        gK = saved[1] if ctx.has_K else None
+        gdepth = saved[1 + (1 if ctx.has_K else 0):]
+        return (None, gposes * g if ctx.needs_input_grad[1] else None, gK * g if gK is not None else None,
+                *[t * g for t in gdepth], *([None] * (2 * ns)))
 
 
 def geonet_loss(tgt_pyr: Sequence[torch.Tensor], src_pyr: Sequence[torch.Tensor], depth_pyr: Sequence[torch.Tensor],

@@ -124,6 +124,11 @@ class FusedLossPlan:
         self.num_tiles = int(_abi.lib().snde_loss_num_tiles(self._ref))
         self.kernel_launches = 3   # prep, tile, finalize (+ one memset node)
 
+    def refresh_intrinsics(self, K_ms: torch.Tensor) -> None:
+        """Re-copy the per-scale intrinsics (the plan keeps contiguous (B,3,3) copies of the strided K_ms[:, s])."""
+        for s in range(self.ns):
+            self.K[s].copy_(K_ms[:, s])
+
     def run(self) -> None:
         """Launch on the current stream (asynchronous)."""
         rc = self._fn(self._ref, _stream())

@@ -121,3 +121,14 @@ def test_cpu_tensors_are_rejected():
         image_similarity(0.85, x, x)
     with pytest.raises(RuntimeError):
         smooth_loss(torch.rand(1, 8, 8, 1), x)
+
+
+def test_product_never_imports_oracle():
+    """the package must not route through the CPU oracle (or anything under tests/): grep the sources"""
+    import pathlib
+    import re
+    pkg = pathlib.Path(__file__).resolve().parents[1] / "self-supervised-normal-depth-estimation_b200"
+    for f in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*")):
+        txt = f.read_text()
+        assert not re.search(r"^\s*(from|import)\s+(oracle|emul|tests)\b", txt, re.M), f
+        assert "snde_oracle" not in txt and "host_emul/emul.cpp" not in txt.replace("tests/host_emul/emul.cpp", ""), f
