@@ -204,25 +204,24 @@ SNDE_STRIP_FN F2 ldg2(const float *p) { return F2{p[0], p[1]}; }
 
 // horizontal 3-sums of one row for the lane's two columns (left column = left neighbour + (a + b), right column =
 // (a + b) + right neighbour: the association the golden-vector tolerances were measured with)
-struct HS { F2 x, y, xx, yy, xy; };
-struct CS { F2 a, b, c; };
+struct HS { P2 x, y, xx, yy, xy; };
+struct CS { P2 a, b, c; };
 
 SNDE_STRIP_FN void hsum_row(const F2 xv, const F2 yv, float xm, float xp, float ym, float yp, HS &o) {
     const float tx = xv.x + xv.y, ty = yv.x + yv.y;
     const float txx = fmaf(xv.y, xv.y, xv.x * xv.x), tyy = fmaf(yv.y, yv.y, yv.x * yv.x), txy = fmaf(xv.y, yv.y, xv.x * yv.x);
-    o.x.x = xm + tx;             o.x.y = tx + xp;
-    o.y.x = ym + ty;             o.y.y = ty + yp;
-    o.xx.x = fmaf(xm, xm, txx);  o.xx.y = fmaf(xp, xp, txx);
-    o.yy.x = fmaf(ym, ym, tyy);  o.yy.y = fmaf(yp, yp, tyy);
-    o.xy.x = fmaf(xm, ym, txy);  o.xy.y = fmaf(xp, yp, txy);
+    o.x = p2(xm + tx, tx + xp);
+    o.y = p2(ym + ty, ty + yp);
+    o.xx = p2(fmaf(xm, xm, txx), fmaf(xp, xp, txx));
+    o.yy = p2(fmaf(ym, ym, tyy), fmaf(yp, yp, tyy));
+    o.xy = p2(fmaf(xm, ym, txy), fmaf(xp, yp, txy));
 }
-SNDE_STRIP_FN F2 add2(const F2 a, const F2 b) { return F2{a.x + b.x, a.y + b.y}; }
 SNDE_STRIP_FN void hs_add(const HS &a, const HS &b, HS &o) {
-    o.x = add2(a.x, b.x); o.y = add2(a.y, b.y); o.xx = add2(a.xx, b.xx); o.yy = add2(a.yy, b.yy); o.xy = add2(a.xy, b.xy);
+    o.x = p2add(a.x, b.x); o.y = p2add(a.y, b.y); o.xx = p2add(a.xx, b.xx); o.yy = p2add(a.yy, b.yy); o.xy = p2add(a.xy, b.xy);
 }
-SNDE_STRIP_FN void cs_add(const CS &a, const CS &b, CS &o) { o.a = add2(a.a, b.a); o.b = add2(a.b, b.b); o.c = add2(a.c, b.c); }
-SNDE_STRIP_FN void hs_zero(HS &o) { o.x = o.y = o.xx = o.yy = o.xy = F2{0.f, 0.f}; }
-SNDE_STRIP_FN void cs_zero(CS &o) { o.a = o.b = o.c = F2{0.f, 0.f}; }
+SNDE_STRIP_FN void cs_add(const CS &a, const CS &b, CS &o) { o.a = p2add(a.a, b.a); o.b = p2add(a.b, b.b); o.c = p2add(a.c, b.c); }
+SNDE_STRIP_FN void hs_zero(HS &o) { o.x = o.y = o.xx = o.yy = o.xy = p2s(0.f); }
+SNDE_STRIP_FN void cs_zero(CS &o) { o.a = o.b = o.c = p2s(0.f); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // what both warps of a pair derive from the task number (uniform over the pair, except the column flags)
@@ -277,9 +276,9 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
     decode_task(p, task, lane, T);
     const DevScale &sc = p.sc[T.scale];
     const float alpha = p.alpha, oma = p.oma, g1 = p.oma * sc.gphoto;
-    float gSm[2];             // -0.5*alpha*gphoto where the column takes part in phase B, else 0
+    float ngSm[2];            // -dL/dS = 0.5*alpha*gphoto where the column takes part in phase B, else 0
 #pragma unroll
-    for (int q = 0; q < 2; ++q) gSm[q] = T.colB[q] ? -0.5f * p.alpha * sc.gphoto : 0.f;
+    for (int q = 0; q < 2; ++q) ngSm[q] = T.colB[q] ? -(-0.5f * p.alpha * sc.gphoto) : 0.f;
     const int y0 = T.y0, y1 = T.y1, h = T.h;
     float sx_acc = 0.f, sy_acc = 0.f;
 
@@ -401,26 +400,22 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                 if (rowB) {
                     HS tot; hs_add(s1[ch], H, tot);
                     const F2 xc = sm.X[rb & 3][ch][lane], yc = sm.Y[rb & 3][ch][lane];
-                    const float sxq[2] = {tot.x.x, tot.x.y}, syq[2] = {tot.y.x, tot.y.y}, sxxq[2] = {tot.xx.x, tot.xx.y};
-                    const float syyq[2] = {tot.yy.x, tot.yy.y}, sxyq[2] = {tot.xy.x, tot.xy.y};
-                    const float xcq[2] = {xc.x, xc.y}, ycq[2] = {yc.x, yc.y};
-                    float ca[2], cb[2], cc[2];
+                    SsimP ss; ssim_sums_p(tot.x, tot.y, tot.xx, tot.yy, tot.xy, ss);
+                    const P2 v = p2fma(p2s(-0.5f), ss.S, p2s(0.5f));
+                    const float vq[2] = {p2lo(v), p2hi(v)};
+                    const float vcq[2] = {clampf(vq[0], 0.f, 1.f), clampf(vq[1], 0.f, 1.f)};
+                    const float dq[2] = {xc.x - yc.x, xc.y - yc.y};
+                    float ngq[2];
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        SsimS ss; ssim_sums(sxq[q], syq[q], sxxq[q], syyq[q], sxyq[q], ss);
-                        const float v = fmaf(-0.5f, ss.S, 0.5f), vc = clampf(v, 0.f, 1.f);
-                        const float err = fmaf(alpha, vc, oma * fabsf(xcq[q] - ycq[q]));
+                        const float err = fmaf(alpha, vcq[q], oma * fabsf(dq[q]));
                         if (row_inner) {
                             err_acc = fmaf(EXTRA ? err * mk[q] : err, T.mI[q], err_acc);
                             if (EXTRA && eout_base && T.colI[q]) eout_base[ch * eout_sc + rb * eout_sh + (T.ix0 + q) * eout_sw] = err;
                         }
-                        ca[q] = cb[q] = cc[q] = 0.f;
-                        if (GRAD) {
-                            const float gS = (v == vc) ? (EXTRA ? gSm[q] * mk[q] : gSm[q]) : 0.f;     // the clamp passes gradient inside [0,1] only
-                            ssim_sums_bwd(ss, sxq[q], syq[q], gS, ca[q], cb[q], cc[q]);
-                        }
+                        ngq[q] = (vq[q] == vcq[q]) ? (EXTRA ? ngSm[q] * mk[q] : ngSm[q]) : 0.f;       // the clamp passes gradient inside [0,1] only
                     }
-                    co.a = F2{ca[0], ca[1]}; co.b = F2{cb[0], cb[1]}; co.c = F2{cc[0], cc[1]};
+                    if (GRAD) ssim_sums_bwd_p(ss, tot.x, tot.y, p2(ngq[0], ngq[1]), co.a, co.b, co.c);
                 }
                 hs_add(s2[ch], H, s1[ch]);        // s1 <- H(t-1) + H(t)
                 s2[ch] = H;
@@ -428,24 +423,24 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                     // ---------------- horizontal sums of the coefficient row t-1 ----------------
                     CS Hc;
                     {
-                        const float to_right[3] = {co.a.y, co.b.y, co.c.y}, to_left[3] = {co.a.x, co.b.x, co.c.x};
+                        const float al = p2lo(co.a), ah = p2hi(co.a), bl = p2lo(co.b), bh = p2hi(co.b), cl = p2lo(co.c), chh = p2hi(co.c);
+                        const float to_right[3] = {ah, bh, chh}, to_left[3] = {al, bl, cl};
                         float from_left[3], from_right[3];
                         neighbor_exchange<3>(who, to_right, to_left, from_left, from_right);
-                        const float ta = co.a.x + co.a.y, tb = co.b.x + co.b.y, tc = co.c.x + co.c.y;
-                        Hc.a = F2{from_left[0] + ta, ta + from_right[0]};
-                        Hc.b = F2{from_left[1] + tb, tb + from_right[1]};
-                        Hc.c = F2{from_left[2] + tc, tc + from_right[2]};
+                        const float ta = al + ah, tb = bl + bh, tc = cl + chh;
+                        Hc.a = p2(from_left[0] + ta, ta + from_right[0]);
+                        Hc.b = p2(from_left[1] + tb, tb + from_right[1]);
+                        Hc.c = p2(from_left[2] + tc, tc + from_right[2]);
                     }
                     // ---------------- phase C (row t-2): dL/d(warped) ----------------
                     if (doC) {
                         CS bs; cs_add(c1[ch], Hc, bs);
-                        const F2 xv = sm.X[rc & 3][ch][lane], yv = sm.Y[rc & 3][ch][lane];
-                        const float d0 = xv.x - yv.x, d1 = xv.y - yv.y;
+                        const F2 xf = sm.X[rc & 3][ch][lane], yf = sm.Y[rc & 3][ch][lane];
+                        const P2 xv = p2f(xf), yv = p2f(yf);
+                        const float d0 = xf.x - yf.x, d1 = xf.y - yf.y;
                         const float l0 = d0 > 0.f ? gl[0] : (d0 < 0.f ? -gl[0] : 0.f), l1 = d1 > 0.f ? gl[1] : (d1 < 0.f ? -gl[1] : 0.f);
-                        F2 po;
-                        po.x = fmaf(yv.x + yv.x, bs.b.x, fmaf(xv.x, bs.c.x, bs.a.x)) - l0;
-                        po.y = fmaf(yv.y + yv.y, bs.b.y, fmaf(xv.y, bs.c.y, bs.a.y)) - l1;
-                        sm.PO[rc & 1][ch][lane] = po;
+                        const P2 po = p2sub(p2fma(p2add(yv, yv), bs.b, p2fma(xv, bs.c, bs.a)), p2(l0, l1));
+                        sm.PO[rc & 1][ch][lane] = f2p(po);
                     }
                     cs_add(c2[ch], Hc, c1[ch]);   // c1 <- Hc(t-2) + Hc(t-1)
                     c2[ch] = Hc;
