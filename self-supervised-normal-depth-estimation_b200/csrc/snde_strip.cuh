@@ -31,6 +31,8 @@
 // go through counting barriers, which lets the strip logic be checked against the oracle without a GPU.  The
 // product never runs the host variant.
 #pragma once
+#include <string.h>
+
 #include "snde_math.cuh"
 
 #ifndef SNDE_MAX_SCALES
@@ -94,13 +96,12 @@ struct alignas(16) F4 { float x, y, z, w; };
 // Shared memory of one warp pair.  Every element is written by one lane and read by the same lane index of either
 // warp (neighbouring columns are exchanged by shuffles inside a warp), so the only synchronisation is the pair barrier.
 struct PairSmem {
-    F2 X[4][3][32];                  // owner image rows (slot = row & 3), 0 outside the image (= the pools' zero padding)
-    F2 D[4][32];                     // owner depth rows
+    F2 X[8][3][32];                  // owner image rows (slot = row & 7; rows t-3 .. t+3 are live), 0 outside the image (= the pools' zero padding)
+    F2 D[8][32];                     // owner depth rows
     F2 Y[4][3][32];                  // warped other image rows, 0 outside the image          geometry -> SSIM
     F2 PO[2][3][32];                 // dL/d(warped) rows (slot = row & 1)                     SSIM -> geometry
     F2 GS[2][32];                    // smoothness part of the depth gradient (slot = row & 1) SSIM -> geometry
     F2 G[4][6][32];                  // d(warped_c)/dx, /dy (geometry warp only)
-    F4 PK[6];                        // P (12 floats) and Kinv (9 floats, padded) of the current pass (geometry warp only)
     int task; int pad_[3];
 };
 
@@ -145,6 +146,16 @@ SNDE_STRIP_FN void atomic_add_double(double *dst, double v) { atomicAdd(dst, v);
 SNDE_STRIP_FN void warp_fence(int) { __syncwarp(); }
 // rendezvous of the two warps of a pair (named barrier `bar`, 64 threads); orders their shared-memory traffic
 SNDE_STRIP_FN void pair_barrier(int, int bar) { asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory"); }
+// asynchronous global -> shared copy of BYTES (4 or 8) bytes; `take` == false writes zeros instead (LDGSTS with src-size 0)
+template <int BYTES>
+SNDE_STRIP_FN void row_copy_async(void *smem_dst, const void *src, bool take) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = take ? BYTES : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(d), "l"(src), "n"(BYTES), "r"(n) : "memory");
+}
+SNDE_STRIP_FN void row_copy_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+SNDE_STRIP_FN void row_copy_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 SNDE_STRIP_FN F2 ldg2(const float *p) { const float2 v = __ldg(reinterpret_cast<const float2 *>(p)); return F2{v.x, v.y}; }
 // Pin a pointer in a register pair: stops the compiler from re-deriving it from (struct field + 64-bit offset) at
 // every use, so that base[int_offset] costs one IMAD.WIDE instead of a four-instruction 64-bit add-and-shift.
@@ -197,6 +208,13 @@ SNDE_STRIP_FN void warp_sum(int who, float (&v)[N]) {
 SNDE_STRIP_FN void atomic_add_double(double *dst, double v) { *dst += v; }
 SNDE_STRIP_FN void warp_fence(int who) { host_warp_sync(who); }
 SNDE_STRIP_FN void pair_barrier(int who, int) { host_pair_sync(who); }
+template <int BYTES>
+SNDE_STRIP_FN void row_copy_async(void *smem_dst, const void *src, bool take) {
+    if (take) memcpy(smem_dst, src, BYTES); else memset(smem_dst, 0, BYTES);
+}
+SNDE_STRIP_FN void row_copy_commit() {}
+template <int PENDING>
+SNDE_STRIP_FN void row_copy_wait() {}
 SNDE_STRIP_FN F2 ldg2(const float *p) { return F2{p[0], p[1]}; }
 #define SNDE_PIN_PTR(p) ((void)0)
 #define SNDE_SCHED_FENCE() ((void)0)
@@ -317,8 +335,8 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                 const bool r_in = r >= 0 && r < h;
                 if (r_in) {
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) xa[ch] = sm.X[r & 3][ch][lane];
-                    da = sm.D[r & 3][lane];
+                    for (int ch = 0; ch < 3; ++ch) xa[ch] = sm.X[r & 7][ch][lane];
+                    da = sm.D[r & 7][lane];
                 }
                 {
                     const float to_left[4] = {xa[0].x, xa[1].x, xa[2].x, da.x};
@@ -331,8 +349,8 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                     F2 xb[3], db = F2{0.f, 0.f};
                     const bool below = r + 1 < h;
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) xb[ch] = below ? sm.X[(r + 1) & 3][ch][lane] : F2{0.f, 0.f};
-                    if (below) db = sm.D[(r + 1) & 3][lane];
+                    for (int ch = 0; ch < 3; ++ch) xb[ch] = below ? sm.X[(r + 1) & 7][ch][lane] : F2{0.f, 0.f};
+                    if (below) db = sm.D[(r + 1) & 7][lane];
                     const float xd[2][3] = {{xb[0].x, xb[1].x, xb[2].x}, {xb[0].y, xb[1].y, xb[2].y}};
                     const float dd[2] = {db.x, db.y};
                     float vxs[2] = {0.f, 0.f}, vys[2] = {0.f, 0.f};
@@ -387,7 +405,7 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 // ---------------- horizontal sums of row t ----------------
-                const F2 xr = sm.X[t & 3][ch][lane], yr = sm.Y[t & 3][ch][lane];
+                const F2 xr = sm.X[t & 7][ch][lane], yr = sm.Y[t & 3][ch][lane];
                 HS H;
                 {
                     const float to_right[2] = {xr.y, yr.y}, to_left[2] = {xr.x, yr.x};
@@ -399,7 +417,7 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                 CS co; cs_zero(co);
                 if (rowB) {
                     HS tot; hs_add(s1[ch], H, tot);
-                    const F2 xc = sm.X[rb & 3][ch][lane], yc = sm.Y[rb & 3][ch][lane];
+                    const F2 xc = sm.X[rb & 7][ch][lane], yc = sm.Y[rb & 3][ch][lane];
                     SsimP ss; ssim_sums_p(tot.x, tot.y, tot.xx, tot.yy, tot.xy, ss);
                     const P2 v = p2fma(p2s(-0.5f), ss.S, p2s(0.5f));
                     const float vq[2] = {p2lo(v), p2hi(v)};
@@ -435,7 +453,7 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                     // ---------------- phase C (row t-2): dL/d(warped) ----------------
                     if (doC) {
                         CS bs; cs_add(c1[ch], Hc, bs);
-                        const F2 xf = sm.X[rc & 3][ch][lane], yf = sm.Y[rc & 3][ch][lane];
+                        const F2 xf = sm.X[rc & 7][ch][lane], yf = sm.Y[rc & 3][ch][lane];
                         const P2 xv = p2f(xf), yv = p2f(yf);
                         const float d0 = xf.x - yf.x, d1 = xf.y - yf.y;
                         const float l0 = d0 > 0.f ? gl[0] : (d0 < 0.f ? -gl[0] : 0.f), l1 = d1 > 0.f ? gl[1] : (d1 < 0.f ? -gl[1] : 0.f);
@@ -480,41 +498,39 @@ struct GeoLane {
     // current other image
     const float *oth_base; int oth_sc, oth_sh, oth_sw;
     float *wout_base; int wout_sc, wout_sh, wout_sw;
+    float P[12], Ki[9];       // projection and inverse intrinsics of the current pass
     // accumulators
     float dP[12], dK[9];
 
     SNDE_STRIP_FN GeoLane(const DevLoss &p_, const DevScale &sc_, PairSmem &sm_, const StripTask &T_, int lane_)
         : p(p_), sc(sc_), sm(sm_), T(T_), lane(lane_) {}
 
-    SNDE_STRIP_FN void load_PK(float (&P)[12], float (&Ki)[9]) const {
-        const F4 a = sm.PK[0], b = sm.PK[1], c = sm.PK[2], d = sm.PK[3], e = sm.PK[4], f = sm.PK[5];
-        P[0] = a.x; P[1] = a.y; P[2] = a.z; P[3] = a.w; P[4] = b.x; P[5] = b.y; P[6] = b.z; P[7] = b.w;
-        P[8] = c.x; P[9] = c.y; P[10] = c.z; P[11] = c.w;
-        Ki[0] = d.x; Ki[1] = d.y; Ki[2] = d.z; Ki[3] = d.w; Ki[4] = e.x; Ki[5] = e.y; Ki[6] = e.z; Ki[7] = e.w; Ki[8] = f.x;
-    }
-
-    // ---- owner row iy (image + depth) for the lane's two columns; zeros outside the image ----
-    SNDE_STRIP_FN void load_owner_row(int iy, F2 (&x)[3], F2 &d) const {
-        x[0] = x[1] = x[2] = d = F2{0.f, 0.f};
-        if (iy < 0 || iy >= T.h) return;
+    // ---- owner row iy (image + depth) of the lane's two columns -> ring slot iy & 7, asynchronously (no registers, no
+    //      copy instruction waits for it); zeros outside the image.  One commit group per row. ----
+    SNDE_STRIP_FN void prefetch_row(int iy) const {
+        const bool row_in = iy >= 0 && iy < T.h;
+        const int y = row_in ? iy : 0;                        // any valid address when nothing is taken
+        F2 (*xs)[32] = sm.X[iy & 7];
         if (FAST) {
-            if (T.in[0]) {          // w and ix0 are even: the pair is inside or outside together
-                const int q = iy * own_sh + T.ix0;
-                x[0] = ldg2(own_base + q); x[1] = ldg2(own_base + (q + own_sc)); x[2] = ldg2(own_base + (q + 2 * own_sc));
-                d = ldg2(dep_base + (iy * dep_sh + T.ix0));
-            }
+            const bool take = row_in && T.in[0];              // w and ix0 are even: the pair is inside or outside together
+            const int q = y * own_sh + (take ? T.ix0 : 0);
+            row_copy_async<8>(&xs[0][lane], own_base + q, take);
+            row_copy_async<8>(&xs[1][lane], own_base + (q + own_sc), take);
+            row_copy_async<8>(&xs[2][lane], own_base + (q + 2 * own_sc), take);
+            row_copy_async<8>(&sm.D[iy & 7][lane], dep_base + (y * dep_sh + (take ? T.ix0 : 0)), take);
         } else {
-            if (T.in[0]) {
-                const int q = iy * own_sh + T.ix0 * own_sw;
-                x[0].x = ldg(own_base + q); x[1].x = ldg(own_base + (q + own_sc)); x[2].x = ldg(own_base + (q + 2 * own_sc));
-                d.x = ldg(dep_base + (iy * dep_sh + T.ix0 * dep_sw));
-            }
-            if (T.in[1]) {
-                const int q = iy * own_sh + (T.ix0 + 1) * own_sw;
-                x[0].y = ldg(own_base + q); x[1].y = ldg(own_base + (q + own_sc)); x[2].y = ldg(own_base + (q + 2 * own_sc));
-                d.y = ldg(dep_base + (iy * dep_sh + (T.ix0 + 1) * dep_sw));
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2) {
+                const bool take = row_in && T.in[k2];
+                const int ix = take ? T.ix0 + k2 : 0;
+                const int q = y * own_sh + ix * own_sw;
+                row_copy_async<4>(&xs[0][lane].x + k2, own_base + q, take);
+                row_copy_async<4>(&xs[1][lane].x + k2, own_base + (q + own_sc), take);
+                row_copy_async<4>(&xs[2][lane].x + k2, own_base + (q + 2 * own_sc), take);
+                row_copy_async<4>(&sm.D[iy & 7][lane].x + k2, dep_base + (y * dep_sh + ix * dep_sw), take);
             }
         }
+        row_copy_commit();
     }
 
     // ---- phase A, first half: reproject the lane's two pixels of a row (in the image) and start the 24 gathers;
@@ -523,8 +539,6 @@ struct GeoLane {
     // derivative gates, kept in dgate[q] = {dx, dy}.
     SNDE_STRIP_FN void a_issue(float yt, const F2 d, float (&wts)[2][4], float (&dgate)[2][2], float (&taps)[24]) const {
         // (lanes whose columns lie outside the image go through the same motions with zero weights on pixel 0)
-        float P[12], Ki[9];
-        load_PK(P, Ki);
         const float dq[2] = {d.x, d.y};
         const float *ob = oth_base;
         SNDE_PIN_PTR(ob);
@@ -597,10 +611,8 @@ struct GeoLane {
         const bool doG = r >= y0;                  // an inner row (r <= y1-1 by construction of the loop)
         float gd[2] = {0.f, 0.f};
         if (GRAD && T.do_photo && doG && (FAST ? T.colI[0] : (T.colI[0] || T.colI[1]))) {
-            float P[12], Ki[9];
-            load_PK(P, Ki);
             const float yt2 = ldg(sc.ytab + r);
-            const F2 d2 = sm.D[r & 3][lane];
+            const F2 d2 = sm.D[r & 7][lane];
             F2 g[6], po[3];
 #pragma unroll
             for (int i = 0; i < 6; ++i) g[i] = sm.G[r & 3][i][lane];
@@ -696,32 +708,25 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
             const DevImageOut &wout = clsF ? sc.warped_fwd : sc.warped_bwd;
             L.wout_base = wout.p ? wout.p + n * wout.sn : nullptr; L.wout_sc = wout.sc; L.wout_sh = wout.sh; L.wout_sw = wout.sw;
         }
-        warp_fence(who);                  // every lane is done with the previous pass's matrices
-        if (T.n_others > 0 && lane < 24) {
+        if (T.n_others > 0) {
             const float *Pn = sc.P + (n * 2 + (clsF ? 0 : 1)) * 12;
-            float *pk = reinterpret_cast<float *>(sm.PK);
-            pk[lane] = lane < 12 ? ldg(Pn + lane) : (lane < 21 ? ldg(Kinv + (lane - 12)) : 0.f);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) L.P[i] = ldg(Pn + i);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) L.Ki[i] = ldg(Kinv + i);
         }
-        warp_fence(who);                  // the matrices are visible to every lane
 #pragma unroll
         for (int i = 0; i < 12; ++i) L.dP[i] = 0.f;
 
-        // prologue: owner row t_begin into the ring, its gathers started
+        // prologue: owner rows t_begin .. t_begin+2 on their way into the ring; the gathers of row t_begin started
         float wts[2][4], dgate[2][2], taps[24];
 #pragma unroll
         for (int i = 0; i < 24; ++i) taps[i] = 0.f;
 #pragma unroll
         for (int q = 0; q < 2; ++q) { wts[q][0] = wts[q][1] = wts[q][2] = wts[q][3] = 0.f; dgate[q][0] = dgate[q][1] = 0.f; }
-        {
-            F2 x0[3], d0;
-            L.load_owner_row(t_begin, x0, d0);
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) sm.X[t_begin & 3][ch][lane] = x0[ch];
-            sm.D[t_begin & 3][lane] = d0;
-            if (T.do_photo && t_begin < h) L.a_issue(ldg(sc.ytab + t_begin), d0, wts, dgate, taps);
-        }
-        F2 xn[3], dn;
-        L.load_owner_row(t_begin + 1, xn, dn);
+        L.prefetch_row(t_begin); L.prefetch_row(t_begin + 1); L.prefetch_row(t_begin + 2);
+        row_copy_wait<1>();               // rows t_begin, t_begin+1 have landed
+        if (T.do_photo && t_begin < h) L.a_issue(ldg(sc.ytab + t_begin), sm.D[t_begin & 7][lane], wts, dgate, taps);
         float yt_n = t_begin + 1 < h ? ldg(sc.ytab + (t_begin + 1)) : 0.f;      // meshgrid y of row t+1, fetched a step ahead
 
         for (int t = t_begin; t <= t_end + 1; ++t) {
@@ -741,24 +746,18 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
                     for (int i = 0; i < 6; ++i) sm.G[t & 3][i][lane] = gr[i];
                 }
             }
-            pair_barrier(who, bar);       // rows <= t of X, Y are published; dL/d(warped) of row t-3 is ready
+            pair_barrier(who, bar);       // owner rows <= t+1 and warped rows <= t are published; dL/d(warped) of row t-3 is ready
             // ---- start row t+1: its gathers fly while the rest of this step runs ----
-            if (T.do_photo && t + 1 <= t_end && t + 1 < h) L.a_issue(yt_n, dn, wts, dgate, taps);
-            F2 xnn[3], dnn;
-            L.load_owner_row(t + 2, xnn, dnn);                  // prefetch: consumed by the next step
+            if (T.do_photo && t + 1 <= t_end && t + 1 < h) L.a_issue(yt_n, sm.D[(t + 1) & 7][lane], wts, dgate, taps);
             yt_n = t + 2 < h ? ldg(sc.ytab + (t + 2)) : 0.f;
-            // ---- row t-3: back-projection, smoothness, depth gradient ----
+            // ---- row t-3: back-projection, depth gradient ----
             if (t - 3 >= T.y0) L.finish_row(t - 3, k);
-            // ---- owner row t+1 into the ring (its slot held row t-3 until now) ----
-            if (t + 1 <= t_end) {
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) sm.X[(t + 1) & 3][ch][lane] = xn[ch];
-                sm.D[(t + 1) & 3][lane] = dn;
-            }
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) xn[ch] = xnn[ch];
-            dn = dnn;
+            // ---- owner row t+3 starts its way into the ring (its slot held row t-5); row t+2 must have landed before the
+            //      next barrier publishes it ----
+            L.prefetch_row(t + 3);
+            row_copy_wait<1>();
         }
+        row_copy_wait<0>();
 
         // ---- publish this pass: d/dP of pair n ----
         if (GRAD && T.n_others > 0) {
