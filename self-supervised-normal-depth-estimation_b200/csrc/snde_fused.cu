@@ -114,7 +114,9 @@ __global__ void __launch_bounds__(StripCfg::NT, SNDE_STRIP_CTAS_PER_SM) loss_str
     for (;;) {
         if (role == 0 && lane == 0) sm.task = atomicAdd(p.counter, 1);
         pair_barrier(lane, bar);
-        const int task = sm.task;        // (rewritten only after both warps went through the barriers of a whole task)
+        // (rewritten only after both warps went through the barriers of a whole task; the shuffle tells the compiler the
+        // value -- and every row index derived from it -- is warp-uniform: uniform branches, no reconvergence stack)
+        const int task = __shfl_sync(0xffffffffu, sm.task, 0);
         if (task >= p.total_tasks) break;
         if (role == 0) geo_role<GRAD, GRADK, EXTRA, FAST>(p, task, lane, sm, bar);
         else ssim_role<GRAD, EXTRA>(p, task, lane, sm, bar);

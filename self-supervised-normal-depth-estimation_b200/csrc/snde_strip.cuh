@@ -100,7 +100,6 @@ struct PairSmem {
     F2 D[8][32];                     // owner depth rows
     F2 Y[4][3][32];                  // warped other image rows, 0 outside the image          geometry -> SSIM
     F2 PO[2][3][32];                 // dL/d(warped) rows (slot = row & 1)                     SSIM -> geometry
-    F2 GS[2][32];                    // smoothness part of the depth gradient (slot = row & 1) SSIM -> geometry
     F2 G[4][6][32];                  // d(warped_c)/dx, /dy (geometry warp only)
     int task; int pad_[3];
 };
@@ -298,8 +297,6 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
 #pragma unroll
     for (int q = 0; q < 2; ++q) ngSm[q] = T.colB[q] ? -(-0.5f * p.alpha * sc.gphoto) : 0.f;
     const int y0 = T.y0, y1 = T.y1, h = T.h;
-    float sx_acc = 0.f, sy_acc = 0.f;
-
     for (int k = 0; k < T.n_pass; ++k) {
         const long long n = T.clsF ? (long long)k * p.B + T.b : T.m;      // index into the N-sized tensors
         const float *mask_base = nullptr; int mask_sh = 0, mask_sw = 0;
@@ -317,78 +314,10 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) { hs_zero(s1[ch]); hs_zero(s2[ch]); cs_zero(c1[ch]); cs_zero(c2[ch]); }
         float err_acc = 0.f;
-        F2 sy_prev = F2{0.f, 0.f};    // signed smoothness weights of the vertical pairs starting one row above
 
         for (int t = T.t_begin; t <= T.t_end + 1; ++t) {
             pair_barrier(who, bar);              // row t of the warped image is in shared memory
             if (t > T.t_end) continue;
-            // smoothness of row t-2 (first pass only).  One step earlier (row y0-1) only the vertical pair weights are
-            // formed: they are the "pair above" of the first inner row.
-            if (T.do_smooth && k == 0 && t - 2 >= y0 - 1) {
-                const int r = t - 2, w = T.w, ix0 = T.ix0;
-                const bool doG = t >= y0 + 2;          // an inner row (the step before it only the pair above is formed)
-                F2 sxw = F2{0.f, 0.f}, syw = F2{0.f, 0.f};
-                float nb_x[4] = {0.f, 0.f, 0.f, 0.f};          // right neighbour column: image (3) + depth
-                F2 xa[3], da = F2{0.f, 0.f};
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) xa[ch] = F2{0.f, 0.f};
-                const bool r_in = r >= 0 && r < h;
-                if (r_in) {
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) xa[ch] = sm.X[r & 7][ch][lane];
-                    da = sm.D[r & 7][lane];
-                }
-                {
-                    const float to_left[4] = {xa[0].x, xa[1].x, xa[2].x, da.x};
-                    take_from_right<4>(who, to_left, nb_x);
-                }
-                if (r_in) {
-                    const float xq[2][3] = {{xa[0].x, xa[1].x, xa[2].x}, {xa[0].y, xa[1].y, xa[2].y}};
-                    const float xn[2][3] = {{xa[0].y, xa[1].y, xa[2].y}, {nb_x[0], nb_x[1], nb_x[2]}};
-                    const float dq[2] = {da.x, da.y}, dn[2] = {da.y, nb_x[3]};
-                    F2 xb[3], db = F2{0.f, 0.f};
-                    const bool below = r + 1 < h;
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) xb[ch] = below ? sm.X[(r + 1) & 7][ch][lane] : F2{0.f, 0.f};
-                    if (below) db = sm.D[(r + 1) & 7][lane];
-                    const float xd[2][3] = {{xb[0].x, xb[1].x, xb[2].x}, {xb[0].y, xb[1].y, xb[2].y}};
-                    const float dd[2] = {db.x, db.y};
-                    float vxs[2] = {0.f, 0.f}, vys[2] = {0.f, 0.f};
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const float mi = doG ? T.mI[q] : 0.f;
-                        {
-                            const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xn[q][0], xn[q][1], xn[q][2]);
-                            const float v = (dq[q] - dn[q]) * wgt;
-                            const float sgn = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
-                            const bool ok = T.colB[q] && ix0 + q + 1 < w;
-                            vxs[q] = ok ? sgn : 0.f;
-                            sx_acc = fmaf(ok ? fabsf(v) : 0.f, mi, sx_acc);
-                        }
-                        {
-                            const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xd[q][0], xd[q][1], xd[q][2]);
-                            const float v = (dq[q] - dd[q]) * wgt;
-                            const float sgn = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
-                            const bool ok = T.colB[q] && below;
-                            vys[q] = ok ? sgn : 0.f;
-                            sy_acc = fmaf(ok ? fabsf(v) : 0.f, mi, sy_acc);
-                        }
-                    }
-                    sxw = F2{vxs[0], vxs[1]}; syw = F2{vys[0], vys[1]};
-                }
-                // the horizontal pair that ENDS at the lane's left column starts in the left neighbour lane
-                float sx_left;
-                {
-                    const float to_right[1] = {sxw.y};
-                    float from_left[1];
-                    take_from_left<1>(who, to_right, from_left);
-                    sx_left = from_left[0];
-                }
-                if (GRAD && doG)
-                    sm.GS[r & 1][lane] = F2{sc.gsx * (sxw.x - sx_left) + sc.gsy * (syw.x - sy_prev.x),
-                                            sc.gsx * (sxw.y - sxw.x) + sc.gsy * (syw.y - sy_prev.y)};
-                sy_prev = syw;
-            }
             if (!T.do_photo) continue;
             const int rb = t - 1, rc = t - 2;
             const bool doB = t >= y0, doC = t >= y0 + 2;
@@ -472,12 +401,6 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
             if (lane == 0 && v[0] != 0.f) atomic_add_double(sc.loss + (T.clsF ? 0 : 1), (double)v[0]);
         }
     }
-    // ---- publish the per-owner smoothness sums ----
-    if (T.do_smooth) {
-        float v[2] = {sx_acc, sy_acc};
-        warp_sum<2>(who, v);
-        if (lane < 2) { const float mine = lane == 0 ? v[0] : v[1]; if (mine != 0.f) atomic_add_double(sc.loss + 2 + lane, (double)mine); }
-    }
 }
 
 // ===============================================================================================================
@@ -500,7 +423,8 @@ struct GeoLane {
     float *wout_base; int wout_sc, wout_sh, wout_sw;
     float P[12], Ki[9];       // projection and inverse intrinsics of the current pass
     // accumulators
-    float dP[12], dK[9];
+    float dP[12], dK[9], sx_acc, sy_acc;
+    F2 sy_prev;               // signed smoothness weights of the vertical pairs starting one row above
 
     SNDE_STRIP_FN GeoLane(const DevLoss &p_, const DevScale &sc_, PairSmem &sm_, const StripTask &T_, int lane_)
         : p(p_), sc(sc_), sm(sm_), T(T_), lane(lane_) {}
@@ -605,8 +529,8 @@ struct GeoLane {
         for (int i = 0; i < 6; ++i) g[i] = F2{gv[0][i], gv[1][i]};
     }
 
-    // ---- row r = t-3 is finished: phase G, depth-gradient write ----
-    SNDE_STRIP_FN void finish_row(int r, int k) {
+    // ---- row r = t-3 is finished: phase G, smoothness, depth-gradient write ----
+    SNDE_STRIP_FN void finish_row(int r, int k, int who) {
         const int y0 = T.y0, ix0 = T.ix0;
         const bool doG = r >= y0;                  // an inner row (r <= y1-1 by construction of the loop)
         float gd[2] = {0.f, 0.f};
@@ -648,9 +572,72 @@ struct GeoLane {
                 }
             }
         }
-        if (GRAD && doG && T.do_smooth && k == 0) {      // smoothness part, computed by the SSIM warp
-            const F2 gs = sm.GS[r & 1][lane];
-            gd[0] += gs.x; gd[1] += gs.y;
+    // smoothness of row r (first pass only).  One step earlier (row y0-1) only the vertical pair weights are
+        // formed: they are the "pair above" of the first inner row.
+        if (T.do_smooth && k == 0) {
+            const int w = T.w, h = T.h;
+            F2 sxw = F2{0.f, 0.f}, syw = F2{0.f, 0.f};
+            float nb_x[4] = {0.f, 0.f, 0.f, 0.f};          // right neighbour column: image (3) + depth
+            F2 xa[3], da = F2{0.f, 0.f};
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) xa[ch] = F2{0.f, 0.f};
+            const bool r_in = r >= 0 && r < h;
+            if (r_in) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) xa[ch] = sm.X[r & 7][ch][lane];
+                da = sm.D[r & 7][lane];
+            }
+            {
+                const float to_left[4] = {xa[0].x, xa[1].x, xa[2].x, da.x};
+                take_from_right<4>(who, to_left, nb_x);
+            }
+            if (r_in) {
+                const float xq[2][3] = {{xa[0].x, xa[1].x, xa[2].x}, {xa[0].y, xa[1].y, xa[2].y}};
+                const float xn[2][3] = {{xa[0].y, xa[1].y, xa[2].y}, {nb_x[0], nb_x[1], nb_x[2]}};
+                const float dq[2] = {da.x, da.y}, dn[2] = {da.y, nb_x[3]};
+                F2 xb[3], db = F2{0.f, 0.f};
+                const bool below = r + 1 < h;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) xb[ch] = below ? sm.X[(r + 1) & 7][ch][lane] : F2{0.f, 0.f};
+                if (below) db = sm.D[(r + 1) & 7][lane];
+                const float xd[2][3] = {{xb[0].x, xb[1].x, xb[2].x}, {xb[0].y, xb[1].y, xb[2].y}};
+                const float dd[2] = {db.x, db.y};
+                float vxs[2] = {0.f, 0.f}, vys[2] = {0.f, 0.f};
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const float mi = doG ? T.mI[q] : 0.f;
+                    {
+                        const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xn[q][0], xn[q][1], xn[q][2]);
+                        const float v = (dq[q] - dn[q]) * wgt;
+                        const float sgn = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
+                        const bool ok = T.colB[q] && ix0 + q + 1 < w;
+                        vxs[q] = ok ? sgn : 0.f;
+                        sx_acc = fmaf(ok ? fabsf(v) : 0.f, mi, sx_acc);
+                    }
+                    {
+                        const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xd[q][0], xd[q][1], xd[q][2]);
+                        const float v = (dq[q] - dd[q]) * wgt;
+                        const float sgn = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
+                        const bool ok = T.colB[q] && below;
+                        vys[q] = ok ? sgn : 0.f;
+                        sy_acc = fmaf(ok ? fabsf(v) : 0.f, mi, sy_acc);
+                    }
+                }
+                sxw = F2{vxs[0], vxs[1]}; syw = F2{vys[0], vys[1]};
+            }
+            // the horizontal pair that ENDS at the lane's left column starts in the left neighbour lane
+            float sx_left;
+            {
+                const float to_right[1] = {sxw.y};
+                float from_left[1];
+                take_from_left<1>(who, to_right, from_left);
+                sx_left = from_left[0];
+            }
+            if (GRAD && doG) {
+                gd[0] += sc.gsx * (sxw.x - sx_left) + sc.gsy * (syw.x - sy_prev.x);
+                gd[1] += sc.gsx * (sxw.y - sxw.x) + sc.gsy * (syw.y - sy_prev.y);
+            }
+            sy_prev = syw;
         }
         if (GRAD && doG && T.in[0]) {
             // every lane writes only its own inner pixels; later passes over the same owner add to what this lane wrote
@@ -694,6 +681,7 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
     L.dep_base = sc.depth.p + depth_n * sc.depth.sn; L.dep_sh = sc.depth.sh; L.dep_sw = sc.depth.sw;
     L.gd_base = GRAD ? sc.gdepth.p + depth_n * sc.gdepth.sn : nullptr; L.gd_sh = sc.gdepth.sh; L.gd_sw = sc.gdepth.sw;
     SNDE_PIN_PTR(L.own_base); SNDE_PIN_PTR(L.dep_base);
+    L.sx_acc = 0.f; L.sy_acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 9; ++i) L.dK[i] = 0.f;
     const float *Kinv = sc.Kinv + 9 * b;
@@ -717,6 +705,7 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
         }
 #pragma unroll
         for (int i = 0; i < 12; ++i) L.dP[i] = 0.f;
+        L.sy_prev = F2{0.f, 0.f};
 
         // prologue: owner rows t_begin .. t_begin+2 on their way into the ring; the gathers of row t_begin started
         float wts[2][4], dgate[2][2], taps[24];
@@ -751,7 +740,7 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
             if (T.do_photo && t + 1 <= t_end && t + 1 < h) L.a_issue(yt_n, sm.D[(t + 1) & 7][lane], wts, dgate, taps);
             yt_n = t + 2 < h ? ldg(sc.ytab + (t + 2)) : 0.f;
             // ---- row t-3: back-projection, depth gradient ----
-            if (t - 3 >= T.y0) L.finish_row(t - 3, k);
+            if (t - 3 >= T.y0 - 1) L.finish_row(t - 3, k, who);
             // ---- owner row t+3 starts its way into the ring (its slot held row t-5); row t+2 must have landed before the
             //      next barrier publishes it ----
             L.prefetch_row(t + 3);
@@ -771,16 +760,18 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
             if (lane < 12 && mine != 0.f) atomic_add_double(sc.gP + (n * 2 + (clsF ? 0 : 1)) * 12 + lane, (double)mine);
         }
     }
-    // ---- publish the per-owner sums: d/dKinv ----
-    if (GRADK) {
-        float v[9];
+    // ---- publish the per-owner sums: smoothness, d/dKinv ----
+    {
+        float v[11];
 #pragma unroll
         for (int i = 0; i < 9; ++i) v[i] = L.dK[i];
-        warp_sum<9>(who, v);
+        v[9] = L.sx_acc; v[10] = L.sy_acc;
+        warp_sum<11>(who, v);
         float mine = 0.f;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) if (lane == i) mine = v[i];
-        if (lane < 9 && mine != 0.f) atomic_add_double(sc.gKinv + 9 * b + lane, (double)mine);
+        for (int i = 0; i < 11; ++i) if (lane == i) mine = v[i];
+        if (GRADK && lane < 9 && mine != 0.f) atomic_add_double(sc.gKinv + 9 * b + lane, (double)mine);
+        if ((lane == 9 || lane == 10) && mine != 0.f) atomic_add_double(sc.loss + 2 + (lane - 9), (double)mine);
     }
 }
 
