@@ -141,6 +141,29 @@ SNDE_STRIP_FN void warp_sum(int, float (&v)[N]) {
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
 }
+// Warp sums of N <= 16 per-lane values by a transposing butterfly: every xor step halves the number of live values
+// (16 shuffles in all instead of 5 per value).  The sum of value i comes back in the even lane whose index is
+// warp_sum_owner(i); other lanes get unspecified values.
+SNDE_STRIP_FN int warp_sum_slot(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+template <int N>
+SNDE_STRIP_FN float warp_sum_scatter(int lane, const float (&in)[N]) {
+    static_assert(N <= 16, "at most 16 values");
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = i < N ? in[i] : 0.f;
+#pragma unroll
+    for (int half = 8; half >= 1; half >>= 1) {
+        const int mask = half * 2;                      // lane bit consumed at this step: 16, 8, 4, 2
+        const bool upper = (lane & mask) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
 SNDE_STRIP_FN void atomic_add_double(double *dst, double v) { atomicAdd(dst, v); }
 SNDE_STRIP_FN void warp_fence(int) { __syncwarp(); }
 // rendezvous of the two warps of a pair (named barrier `bar`, 64 threads); orders their shared-memory traffic
@@ -203,6 +226,15 @@ SNDE_STRIP_FN void warp_sum(int who, float (&v)[N]) {
         v[i] = part[0];
     }
     host_parity(who) = par ^ 1;
+}
+SNDE_STRIP_FN int warp_sum_slot(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+template <int N>
+SNDE_STRIP_FN float warp_sum_scatter(int who, const float (&in)[N]) {
+    float v[N];
+    for (int i = 0; i < N; ++i) v[i] = in[i];
+    warp_sum<N>(who, v);
+    const int slot = warp_sum_slot(who & 31);
+    return slot < N ? v[slot] : 0.f;
 }
 SNDE_STRIP_FN void atomic_add_double(double *dst, double v) { *dst += v; }
 SNDE_STRIP_FN void warp_fence(int who) { host_warp_sync(who); }
@@ -395,10 +427,10 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
             }
         }
         // ---- publish this pass: error sum of pair n ----
-        if (T.n_others > 0) {
+        {
             float v[1] = {err_acc};
             warp_sum<1>(who, v);
-            if (lane == 0 && v[0] != 0.f) atomic_add_double(sc.loss + (T.clsF ? 0 : 1), (double)v[0]);
+            if (T.n_others > 0 && lane == 0 && v[0] != 0.f) atomic_add_double(sc.loss + (T.clsF ? 0 : 1), (double)v[0]);
         }
     }
 }
@@ -748,16 +780,12 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
         }
         row_copy_wait<0>();
 
-        // ---- publish this pass: d/dP of pair n ----
-        if (GRAD && T.n_others > 0) {
-            float v[12];
-#pragma unroll
-            for (int i = 0; i < 12; ++i) v[i] = L.dP[i];
-            warp_sum<12>(who, v);
-            float mine = 0.f;
-#pragma unroll
-            for (int i = 0; i < 12; ++i) if (lane == i) mine = v[i];
-            if (lane < 12 && mine != 0.f) atomic_add_double(sc.gP + (n * 2 + (clsF ? 0 : 1)) * 12 + lane, (double)mine);
+        // ---- publish this pass: d/dP of pair n (the reduction runs unconditionally: warp-collective code stays uniform) ----
+        {
+            const float mine = warp_sum_scatter<12>(who, L.dP);
+            const int slot = warp_sum_slot(lane);
+            if (GRAD && T.n_others > 0 && !(lane & 1) && slot < 12 && mine != 0.f)
+                atomic_add_double(sc.gP + (n * 2 + (clsF ? 0 : 1)) * 12 + slot, (double)mine);
         }
     }
     // ---- publish the per-owner sums: smoothness, d/dKinv ----
@@ -766,12 +794,12 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
 #pragma unroll
         for (int i = 0; i < 9; ++i) v[i] = L.dK[i];
         v[9] = L.sx_acc; v[10] = L.sy_acc;
-        warp_sum<11>(who, v);
-        float mine = 0.f;
-#pragma unroll
-        for (int i = 0; i < 11; ++i) if (lane == i) mine = v[i];
-        if (GRADK && lane < 9 && mine != 0.f) atomic_add_double(sc.gKinv + 9 * b + lane, (double)mine);
-        if ((lane == 9 || lane == 10) && mine != 0.f) atomic_add_double(sc.loss + 2 + (lane - 9), (double)mine);
+        const float mine = warp_sum_scatter<11>(who, v);
+        const int slot = warp_sum_slot(lane);
+        if (!(lane & 1) && mine != 0.f) {
+            if (GRADK && slot < 9) atomic_add_double(sc.gKinv + 9 * b + slot, (double)mine);
+            if (slot == 9 || slot == 10) atomic_add_double(sc.loss + 2 + (slot - 9), (double)mine);
+        }
     }
 }
 
