@@ -29,7 +29,8 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     "config2": dict(B=32, S=2, H=128, W=416, num_scales=4, intrinsics="kitti"),
     "config1": dict(B=4, S=2, H=128, W=416, num_scales=4, intrinsics="kitti"),
-    "nyu": dict(B=8, S=2, H=480, W=640, num_scales=4, intrinsics="nyu"),
+    "nyu": dict(B=8, S=2, H=480, W=640, num_scales=4, intrinsics="nyu"),                 # BASELINE config 3 shape
+    "hires": dict(B=8, S=4, H=376, W=1248, num_scales=4, intrinsics="kitti"),             # config 4: B=64 sharded over 8 GPUs
 }
 METRIC = "warped_pixel_fwd_bwd_per_sec"
 UNIT = "warped-px/s"

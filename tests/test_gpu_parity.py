@@ -302,3 +302,103 @@ def test_large_batch_indices_beyond_2_pow_24():
     full = bilinear_sampler(img, coords.expand(N, -1, -1, -1).contiguous())
     last = bilinear_sampler(img[8:9].contiguous(), coords)
     assert torch.equal(full[8:9], last)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the lean hot-path instance (<GRAD, FAST>: what bench.py times) and the other BASELINE shapes
+# ---------------------------------------------------------------------------------------------------
+def _fused_lean(inp):
+    """want_grad only: selects loss_strip_kernel<GRAD=1, GRADK=0, EXTRA=0, FAST=1> for planar inputs"""
+    from snde_b200 import ops
+    d = inp.to(DEV)
+    plan = ops.FusedLossPlan(d.tgt_pyr, d.src_pyr, d.depth_pyr, d.poses, d.K_ms, want_grad=True)
+    plan.run()
+    torch.cuda.synchronize()
+    lo = plan.loss_out.cpu().numpy()
+    return dict(loss_total=float(lo[0]), fwd_mean=lo[3::3], bwd_mean=lo[4::3], smooth=lo[5::3],
+                grad_depth=[g.cpu().numpy() for g in plan.grad_depth], grad_poses=plan.grad_poses.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", SMALL + ["config1_smooth"])
+def test_lean_instance_equals_general_instance(name):
+    """the two template instances share every arithmetic statement: identical depth gradients, same sums"""
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**CASES[name])
+    a, b = _fused_lean(inp), _fused(inp)
+    assert abs(a["loss_total"] - b["loss_total"]) < 1e-6 * abs(b["loss_total"])
+    for s in range(inp.num_scales):
+        assert np.array_equal(a["grad_depth"][s], b["grad_depth"][s])
+    assert rel_l2(a["grad_poses"], b["grad_poses"]) < 1e-5
+
+
+def test_lean_instance_config1_vs_golden(oracle32):
+    from oracle.compose import geonet_loss
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**CASES["config1_smooth"])
+    e = _fused_lean(inp)
+    g = load_golden("config1_smooth")
+    o = geonet_loss(oracle32, **oracle_inputs(inp))
+    assert abs(e["loss_total"] - g["loss_total"]) < 1e-5 * abs(g["loss_total"])
+    np.testing.assert_allclose(e["fwd_mean"], g["fwd_mean"], rtol=1e-5)
+    np.testing.assert_allclose(e["bwd_mean"], g["bwd_mean"], rtol=1e-5)
+    np.testing.assert_allclose(e["smooth"], g["smooth"], rtol=1e-5)
+    for s in range(4):
+        ok, rel, frac = close_except_flips(e["grad_depth"][s], o["grad_depth"][s])
+        assert ok, (s, rel, frac)
+    assert rel_l2(e["grad_poses"], g["grad_poses"]) < 1e-3
+
+
+@pytest.mark.parametrize("shape", [dict(B=1, S=2, H=480, W=640, num_scales=4, intrinsics="nyu"),      # BASELINE config 3 shape
+                                   dict(B=1, S=4, H=376, W=1248, num_scales=4, intrinsics="kitti")])   # config 4 shape (S = 4)
+def test_lean_instance_other_baseline_shapes_vs_oracle(oracle32, shape):
+    from oracle.compose import geonet_loss
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(seed=21, smooth=True, motion="small", **shape)
+    e = _fused_lean(inp)
+    o = geonet_loss(oracle32, **oracle_inputs(inp))
+    assert abs(e["loss_total"] - o["loss_total"]) < 1e-5 * abs(o["loss_total"])
+    for s in range(inp.num_scales):
+        ok, rel, frac = close_except_flips(e["grad_depth"][s], o["grad_depth"][s])
+        assert ok, (s, rel, frac)
+    assert rel_l2(e["grad_poses"], o["grad_poses"]) < 1e-3
+
+
+@pytest.mark.parametrize("cfg", [dict(B=32, S=2, H=128, W=416, num_scales=4),                          # config 2, full size
+                                 dict(B=8, S=2, H=480, W=640, num_scales=4, intrinsics="nyu")])          # config 3, full size
+def test_full_size_batch_split_property(cfg):
+    """Size-independent property at the BASELINE sizes: samples are independent, so the loss on each half of the batch
+    has per-sample gradients exactly twice those of the whole batch (the mean's 1/N is a power of two apart) and the
+    two half losses average to the whole loss.  This is also what makes batch sharding across GPUs exact."""
+    from snde_b200.sharding import shard_inputs
+    from snde_b200.synthetic import make_inputs
+    full = make_inputs(seed=3, smooth=False, motion="small", **cfg)
+    whole = _fused_lean(full)
+    B, S = full.B, full.S
+    halves = [_fused_lean(shard_inputs(full, r, 2)) for r in range(2)]
+    assert abs(0.5 * (halves[0]["loss_total"] + halves[1]["loss_total"]) - whole["loss_total"]) < 2e-6 * abs(whole["loss_total"])
+    b = B // 2
+    for r in range(2):
+        for s in range(full.num_scales):
+            gw = whole["grad_depth"][s]
+            mine = np.concatenate([gw[r * b:(r + 1) * b]] + [gw[B * (k + 1) + r * b:B * (k + 1) + (r + 1) * b] for k in range(S)], 0)
+            assert np.array_equal(halves[r]["grad_depth"][s], 2.0 * mine)
+        assert rel_l2(halves[r]["grad_poses"], 2.0 * whole["grad_poses"][r * b:(r + 1) * b]) < 1e-5
+
+
+def test_identity_pose_large_image_sweep_shape():
+    """config 5 sweep corner (1024x2048, single scale): with a zero pose every pixel reprojects onto itself, so the
+    warped image is the source image except the last row / column, which the reference sampler zeroes (x = W-1)."""
+    from snde_b200.loss_functions import inverse_warp
+    g = torch.Generator().manual_seed(11)
+    N, H, W = 2, 1024, 2048
+    img = torch.rand(N, H, W, 3, generator=g).to(DEV)
+    depth = (torch.rand(N, H, W, generator=g) + 0.5).to(DEV)
+    pose = torch.zeros(N, 6, device=DEV)
+    K = torch.tensor([[0.58 * W, 0, 0.5 * W], [0, 1.92 * H, 0.5 * H], [0, 0, 1]], device=DEV).repeat(N, 1, 1)
+    warped, valid = inverse_warp(img, depth, pose, K)
+    # the projection round trip leaves ~1e-4 px of fp32 noise: interior pixels stay valid, pixels ON the first row /
+    # column (x = 0 or y = 0 exactly) may land an ulp outside
+    assert valid[:, 1:-1, 1:-1].min().item() == 1.0
+    inner = valid.bool()
+    assert (warped[inner] - img[inner]).abs().max().item() < 2e-3   # coordinates carry ~1e-4 px of fp32 noise at this size
+    assert warped[:, -1].abs().max().item() == 0.0 and warped[:, :, -1].abs().max().item() == 0.0
