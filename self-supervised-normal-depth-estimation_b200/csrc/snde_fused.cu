@@ -3,6 +3,7 @@
 // (fmaf / SNDE_X* ops in snde_math.cuh), everything else may be contracted.  See build.py.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "snde.h"
@@ -130,12 +131,14 @@ extern "C" size_t snde_loss_workspace_bytes(int B, int S, int num_scales) {
     return loss_ws_layout(B, S, num_scales).end;
 }
 
+// host-only preview of the task count, with the segment-height rule of snde_loss_fwdbwd evaluated for a B200
+// (148 SMs x SNDE_STRIP_CTAS_PER_SM CTAs x PAIRS warp pairs)
 extern "C" int64_t snde_loss_num_tiles(const SndeLossArgs *args) {
     DevLoss d; int64_t n = 0;
-    SndeLossArgs tmp;
     if (!args) return SNDE_ERR_NULL;
-    tmp = *args;
-    int rc = build_dev_loss(&tmp, d, nullptr, &n);
+    int rc = build_dev_loss(args, d, nullptr, &n, 64);
+    if (rc) return rc;
+    if (n < 2LL * 148 * SNDE_STRIP_CTAS_PER_SM * StripCfg::PAIRS) rc = build_dev_loss(args, d, nullptr, &n, 32);
     return rc ? rc : n;
 }
 
@@ -149,8 +152,26 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     const LossWorkspace lay = loss_ws_layout(a->B, a->S, a->num_scales);
     if (!a->workspace || a->workspace_bytes < lay.end || ((uintptr_t)a->workspace & 15)) return SNDE_ERR_WORKSPACE;
     DevLoss d; int64_t tiles = 0;
-    int rc = build_dev_loss(a, d, &lay, &tiles);
+    // Rows per strip segment.  Longer segments recompute fewer halo rows (a segment of s rows costs s + 6 row steps) but
+    // give fewer tasks to balance over the resident warp pairs: 64 rows when that still leaves two tasks per pair,
+    // else 32 (measured at config 2: 16 -> 344 us, 32 -> 318, 64 -> 308, 128 -> 416).  SNDE_SEG_ROWS overrides (tuning only).
+    static int seg_env = -1;
+    if (seg_env < 0) { const char *e = getenv("SNDE_SEG_ROWS"); seg_env = e ? atoi(e) : 0; if (seg_env < 0) seg_env = 0; }
+    int rc = build_dev_loss(a, d, &lay, &tiles, seg_env ? seg_env : 64);       // validates every argument before any CUDA call
     if (rc) return rc;
+    int devi = 0;
+    if (cudaGetDevice(&devi) != cudaSuccess || devi < 0 || devi >= 64) return SNDE_ERR_CUDA;
+    static int sm_count[64] = {};
+    if (!sm_count[devi]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, devi) != cudaSuccess || n <= 0) return SNDE_ERR_CUDA;
+        sm_count[devi] = n;
+    }
+    const long long resident_pairs = (long long)sm_count[devi] * SNDE_STRIP_CTAS_PER_SM * StripCfg::PAIRS;
+    if (!seg_env && tiles < 2 * resident_pairs) {
+        rc = build_dev_loss(a, d, &lay, &tiles, 32);
+        if (rc) return rc;
+    }
     cudaStream_t st = as_stream(stream_);
     const int B = a->B, S = a->S, ns = a->num_scales, N = B * S;
     unsigned char *ws = (unsigned char *)a->workspace;
@@ -164,15 +185,6 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     // opt in to > 48 KB dynamic shared memory once per kernel variant and device (not a stream operation; kept out of
     // the per-call path so the call can be captured into a CUDA graph after one eager warm-up)
     static bool attr_done[8][64] = {};
-    static int sm_count[64] = {};
-    int devi = 0;
-    cudaGetDevice(&devi);
-    if (devi < 0 || devi >= 64) return SNDE_ERR_CUDA;
-    if (!sm_count[devi]) {
-        int n = 0;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, devi) != cudaSuccess || n <= 0) return SNDE_ERR_CUDA;
-        sm_count[devi] = n;
-    }
     // persistent grid: as many CTAs as fit, but no more warp pairs than tasks
     long long ctas = (long long)sm_count[devi] * SNDE_STRIP_CTAS_PER_SM;
     const long long need = (tiles + StripCfg::PAIRS - 1) / StripCfg::PAIRS;

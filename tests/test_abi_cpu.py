@@ -91,7 +91,7 @@ def test_argument_validation_without_launch(abi):
 
 def test_num_tiles(abi):
     """task table: class-F tasks (B owners per scale) + class-R tasks (S*B owners per scale); a task is one strip of 60
-    inner columns x one segment of 32 rows"""
+    inner columns x one segment of 64 rows (32 when that would leave fewer than two tasks per resident warp pair)"""
     lib = abi.lib()
     dummy = np.zeros(64, np.float32)
     args = abi.SndeLossArgs()
@@ -102,8 +102,10 @@ def test_num_tiles(abi):
         for f in ("tgt", "src"):
             getattr(sc, f).ptr = dummy.ctypes.data
         sc.depth.ptr = dummy.ctypes.data; sc.K = dummy.ctypes.data; sc.xtab = dummy.ctypes.data; sc.ytab = dummy.ctypes.data
-    per_img = [7 * 4, 4 * 2, 2 * 1, 1 * 1]
+    per_img = [7 * 2, 4 * 1, 2 * 1, 1 * 1]
     assert lib.snde_loss_num_tiles(C.byref(args)) == sum(per_img) * 32 * 3
+    args.B = 4                                        # config 1: too few tasks at 64 rows -> 32-row segments
+    assert lib.snde_loss_num_tiles(C.byref(args)) == (7 * 4 + 4 * 2 + 2 * 1 + 1 * 1) * 4 * 3
 
 
 def test_no_fallback_when_library_missing(abi, monkeypatch):
