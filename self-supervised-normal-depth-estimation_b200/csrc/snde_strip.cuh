@@ -446,6 +446,7 @@ struct GeoLane {
     const StripTask &T;
     int lane;
     float xt[2];
+    float mxs[2], mys[2], mxi[2], myi[2];      // 0/1: the horizontal / vertical smoothness pair starting at column q exists (.. and is an inner column)
     // owner
     const float *own_base; int own_sc, own_sh, own_sw;
     const float *dep_base; int dep_sh, dep_sw;
@@ -512,10 +513,11 @@ struct GeoLane {
             else { make_taps_valid(x, yy, tp); valid = tap_valid(x, yy, h, w, 0) != 0.f; }
             valid = valid && T.in[q];
             const int o00 = valid ? tp.y0 * oth_sh + tp.x0 * (FAST ? 1 : oth_sw) : 0;
-            // row / column steps to the second tap (0 when border mode clamped both taps onto the same pixel)
+            // row / column steps to the second tap: constants, so that the four taps of a channel are two base addresses
+            // with immediate offsets (an invalid pixel reads the 2x2 block at the image origin; h, w >= 2 is checked on
+            // the host).  Border mode may have clamped both taps onto the same pixel: step 0.
             int dyo = oth_sh, dxo = FAST ? 1 : oth_sw;
             if (EXTRA && p.padding) { dyo = (tp.y1 - tp.y0) * oth_sh; dxo = (tp.x1 - tp.x0) * (FAST ? 1 : oth_sw); }
-            if (!valid) { dyo = 0; dxo = 0; }
             wts[q][0] = valid ? tp.wx0 : 0.f; wts[q][1] = valid ? tp.wx1 : 0.f; wts[q][2] = valid ? tp.wy0 : 0.f; wts[q][3] = valid ? tp.wy1 : 0.f;
             dgate[q][0] = tp.dx; dgate[q][1] = tp.dy;
 #pragma unroll
@@ -543,7 +545,7 @@ struct GeoLane {
                 const float i00 = taps[12 * q + 4 * ch + 0], i01 = taps[12 * q + 4 * ch + 1];
                 const float i10 = taps[12 * q + 4 * ch + 2], i11 = taps[12 * q + 4 * ch + 3];
                 yv[q][ch] = tap_blend_fma(w00, w01, w10, w11, i00, i01, i10, i11);
-                gv[q][2 * ch] = gv[q][2 * ch + 1] = 0.f;
+                gv[q][2 * ch] = gv[q][2 * ch + 1] = 0.f;      // (dead unless want_g: the caller does not store them then)
                 if (GRAD && want_g) {
                     gv[q][2 * ch] = fmaf(wy1, i11 - i01, wy0 * (i10 - i00));
                     gv[q][2 * ch + 1] = fmaf(wx1, i11 - i10, wx0 * (i01 - i00));
@@ -634,26 +636,24 @@ struct GeoLane {
                 if (below) db = sm.D[(r + 1) & 7][lane];
                 const float xd[2][3] = {{xb[0].x, xb[1].x, xb[2].x}, {xb[0].y, xb[1].y, xb[2].y}};
                 const float dd[2] = {db.x, db.y};
-                float vxs[2] = {0.f, 0.f}, vys[2] = {0.f, 0.f};
+                float vxs[2], vys[2];
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    const float mi = doG ? T.mI[q] : 0.f;
+                    // pairs that do not exist (image border, halo column) are switched off by 0/1 factors fixed per task
                     {
                         const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xn[q][0], xn[q][1], xn[q][2]);
                         const float v = (dq[q] - dn[q]) * wgt;
                         const float sgn = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
-                        const bool ok = T.colB[q] && ix0 + q + 1 < w;
-                        vxs[q] = ok ? sgn : 0.f;
-                        sx_acc = fmaf(ok ? fabsf(v) : 0.f, mi, sx_acc);
+                        vxs[q] = sgn * mxs[q];
+                        if (doG) sx_acc = fmaf(fabsf(v), mxi[q], sx_acc);
                     }
-                    {
+                    if (below) {
                         const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xd[q][0], xd[q][1], xd[q][2]);
                         const float v = (dq[q] - dd[q]) * wgt;
                         const float sgn = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
-                        const bool ok = T.colB[q] && below;
-                        vys[q] = ok ? sgn : 0.f;
-                        sy_acc = fmaf(ok ? fabsf(v) : 0.f, mi, sy_acc);
-                    }
+                        vys[q] = sgn * mys[q];
+                        if (doG) sy_acc = fmaf(fabsf(v), myi[q], sy_acc);
+                    } else vys[q] = 0.f;
                 }
                 sxw = F2{vxs[0], vxs[1]}; syw = F2{vys[0], vys[1]};
             }
@@ -704,7 +704,11 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
     const int B = p.B;
     GeoLane<GRAD, GRADK, EXTRA, FAST> L(p, sc, sm, T, lane);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) L.xt[q] = T.in[q] ? ldg(sc.xtab + (T.ix0 + q)) : 0.f;
+    for (int q = 0; q < 2; ++q) {
+        L.xt[q] = T.in[q] ? ldg(sc.xtab + (T.ix0 + q)) : 0.f;
+        L.mxs[q] = (T.colB[q] && T.ix0 + q + 1 < T.w) ? 1.f : 0.f; L.mys[q] = T.colB[q] ? 1.f : 0.f;
+        L.mxi[q] = L.mxs[q] * T.mI[q]; L.myi[q] = L.mys[q] * T.mI[q];
+    }
     const bool clsF = T.clsF;
     const int m = T.m, b = T.b;
     const DevImage &own = clsF ? sc.tgt : sc.src;
@@ -753,18 +757,19 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
         for (int t = t_begin; t <= t_end + 1; ++t) {
             // ---- finish row t: the warped row goes to the SSIM warp, the tap derivatives stay here ----
             if (T.do_photo && t <= t_end) {
-                F2 yr[3], gr[6];
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) yr[ch] = F2{0.f, 0.f};
-#pragma unroll
-                for (int i = 0; i < 6; ++i) gr[i] = F2{0.f, 0.f};
                 const bool want_g = t >= T.y0 && t < T.y1;
-                if (t < h) L.a_finish(t, wts, dgate, taps, want_g, yr, gr);
+                if (t < h) {
+                    F2 yr[3], gr[6];
+                    L.a_finish(t, wts, dgate, taps, want_g, yr, gr);
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) sm.Y[t & 3][ch][lane] = yr[ch];
-                if (GRAD && want_g) {
+                    for (int ch = 0; ch < 3; ++ch) sm.Y[t & 3][ch][lane] = yr[ch];
+                    if (GRAD && want_g) {
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) sm.G[t & 3][i][lane] = gr[i];
+                        for (int i = 0; i < 6; ++i) sm.G[t & 3][i][lane] = gr[i];
+                    }
+                } else {                      // rows below the image are zero rows of the pools (never inner rows)
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) sm.Y[t & 3][ch][lane] = F2{0.f, 0.f};
                 }
             }
             pair_barrier(who, bar);       // owner rows <= t+1 and warped rows <= t are published; dL/d(warped) of row t-3 is ready
