@@ -8,9 +8,11 @@ A "step" is one fused fwd+bwd of the whole loss (all scales, both directions, sm
 synthetic KITTI-shaped frames (BASELINE.json configs[1]: 128x416, B=32 per GPU, S=2, 4 scales).
   value  : warped pixels / s with inputs resident in HBM (CUDA-graph replay of the C-ABI call, 4 rotating
            input sets = 540 MB > L2, CUDA events, max over ranks).
-  e2e    : same metric through the public autograd API (snde_b200.loss_functions.geonet_loss + backward) with
-           HOST buffers: pinned H2D copy of every input and D2H read of loss + all gradients inside the timed region
-           (copies and compute of consecutive steps overlap on three streams).
+  e2e    : same metric through the public autograd API (snde_b200.loss_functions.geonet_loss_from_frames + backward) with
+           HOST buffers as the reference's trainer has them: uint8 frames + intrinsics from the DataLoader, depth pyramid +
+           poses from the networks.  Pinned H2D copy of every input, on-device normalisation + pyramid (one kernel per
+           frame set), fused loss, D2H read of loss + all gradients, all inside the timed region (copies and compute of
+           consecutive steps overlap on three streams).
   roofline : algorithmic bytes (60 B per warped pixel + 36 B per smoothness pixel) / step time.
   cpu_baseline : oracle/torch_port.py (the reference's ATen op chain restated) on this box's host cores.
 --impl reference times that CPU path alone (rank 0 only).
@@ -110,10 +112,15 @@ def run_reference(args, cfg, rank):
     inp = make_inputs(seed=0, **c)
     depth = [d.clone().requires_grad_(True) for d in inp.depth_pyr]
     poses = inp.poses.clone().requires_grad_(True)
+    to_u8 = lambda x: ((x + 1) * 127.5).round().clamp(0, 255).to(torch.uint8)
+    tgt_u8, src_u8 = to_u8(inp.tgt_pyr[0]), to_u8(inp.src_pyr[0])          # what the DataLoader hands over
+    ns = c["num_scales"]
     def step():
         for t in depth + [poses]:
             t.grad = None
-        total, _, _ = torch_port.loss_path(inp.tgt_pyr, inp.src_pyr, depth, poses, inp.K_ms)
+        # iter_data_preparation (baseline.py:761-792) + loss path, as in one trainer iteration
+        tgt_pyr, src_pyr = torch_port.frames_to_pyramid(tgt_u8, ns), torch_port.frames_to_pyramid(src_u8, ns)
+        total, _, _ = torch_port.loss_path(tgt_pyr, src_pyr, depth, poses, inp.K_ms)
         total.backward()
     for _ in range(args.warmup):
         step()
@@ -156,7 +163,7 @@ def main():
     import torch
     import torch.distributed as dist
     from snde_b200 import ops
-    from snde_b200.loss_functions import geonet_loss
+    from snde_b200.loss_functions import geonet_loss_from_frames
     from snde_b200.synthetic import make_inputs
 
     torch.cuda.set_device(local_rank)
@@ -224,18 +231,24 @@ def main():
     value = world * warped_px / (ms_per_step * 1e-3)
 
     # ---- end to end through the public API with host buffers ----
+    # host inputs as the reference's DataLoader delivers them (models/baseline.py:746-770): uint8 frames, tgt (B,3,H,W) and
+    # src (B,3*S,H,W), intrinsics (B,3,3); plus the network outputs the loss consumes (depth pyramid, poses)
     host = make_inputs(seed=7 + rank, **cfg)
     pin = lambda t: t.contiguous().pin_memory()
-    h_tgt, h_src, h_dep = [pin(t) for t in host.tgt_pyr], [pin(t) for t in host.src_pyr], [pin(t) for t in host.depth_pyr]
-    h_poses, h_K = pin(host.poses), pin(host.K_ms)
-    h2d = sum(t.numel() * 4 for t in h_tgt + h_src + h_dep + [h_poses, h_K])
+    B_, S_ = cfg["B"], cfg["S"]
+    to_u8 = lambda x: ((x + 1) * 127.5).round().clamp(0, 255).to(torch.uint8)
+    h_tgt = pin(to_u8(host.tgt_pyr[0]))
+    h_src = pin(to_u8(host.src_pyr[0]).view(S_, B_, 3, cfg["H"], cfg["W"]).transpose(0, 1).reshape(B_, 3 * S_, cfg["H"], cfg["W"]))
+    h_dep = [pin(t) for t in host.depth_pyr]
+    h_poses, h_K = pin(host.poses), pin(host.K)
+    h2d = sum(t.numel() * t.element_size() for t in [h_tgt, h_src] + h_dep + [h_poses, h_K])
     out_host = [torch.empty_like(t).pin_memory() for t in h_dep] + [torch.empty_like(host.poses).pin_memory(), torch.empty(3 + 3 * cfg["num_scales"]).pin_memory()]
     d2h = sum(t.numel() * 4 for t in out_host)
 
     # Two device input sets and three streams: the H2D copy of step i+1, the fused loss of step i and the D2H read of
     # step i-1 overlap (every byte still moves every step, inside the timed region).
     NBUF = 2
-    dev_in = [dict(tgt=[torch.empty_like(t, device=dev) for t in h_tgt], src=[torch.empty_like(t, device=dev) for t in h_src],
+    dev_in = [dict(tgt=torch.empty_like(h_tgt, device=dev), src=torch.empty_like(h_src, device=dev),
                    dep=[torch.empty_like(t, device=dev) for t in h_dep], poses=torch.empty_like(h_poses, device=dev),
                    K=torch.empty_like(h_K, device=dev)) for _ in range(NBUF)]
     s_h2d, s_run, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -250,9 +263,10 @@ def main():
         d = dev_in[j]
         with torch.cuda.stream(s_h2d):
             s_h2d.wait_event(ev_free[j])
-            for dst, srcs in ((d["tgt"], h_tgt), (d["src"], h_src), (d["dep"], h_dep)):
-                for a, b in zip(dst, srcs):
-                    a.copy_(b, non_blocking=True)
+            d["tgt"].copy_(h_tgt, non_blocking=True)
+            d["src"].copy_(h_src, non_blocking=True)
+            for a, b in zip(d["dep"], h_dep):
+                a.copy_(b, non_blocking=True)
             d["poses"].copy_(h_poses, non_blocking=True)
             d["K"].copy_(h_K, non_blocking=True)
             ev_in[j].record(s_h2d)
@@ -261,7 +275,7 @@ def main():
             s_run.wait_event(ev_out)                           # the previous step's results have left their buffers
             dep = [t.detach().requires_grad_(True) for t in d["dep"]]
             poses = d["poses"].detach().requires_grad_(True)
-            total, detail = geonet_loss(d["tgt"], d["src"], dep, poses, d["K"])
+            total, detail = geonet_loss_from_frames(d["tgt"], d["src"], dep, poses, d["K"])
             total.backward()
             grads = [t.grad for t in dep] + [poses.grad, detail]
             ev_free[j].record(s_run)

@@ -173,6 +173,20 @@ SNDE_API int snde_smooth_loss_fwd(int M, int h, int w, SndeMap depth, SndeImage 
 SNDE_API int snde_smooth_loss_bwd(int M, int h, int w, SndeMap depth, SndeImage img, const float *gscale_dev,
                          SndeMapOut gdepth, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Caller-side prep just before the path: the image part of
+ * GeoNetModel.iter_data_preparation (models/baseline.py:761-767: uint8 -> float, * 1/255, * 2 - 1)
+ * fused with scale_pyramid (utils/utils_edited.py:89-112: F.interpolate(mode='area') to
+ * int(H/2^s) x int(W/2^s)).  One pass: every byte is read once, every level written once.
+ *   frames : uint8 (n,3,H,W) addressed through element (= byte) strides (sn, sc, sh, sw), so
+ *            NHWC camera buffers work too
+ *   levels : HOST array of num_scales DEVICE pointers; level s is planar contiguous fp32
+ *            (n,3,H>>s,W>>s) = the mean over 2^s x 2^s blocks of the normalised pixels
+ * H and W must be multiples of 2^(num_scales-1) (the sizes at which the reference's
+ * int(H/2^s) pyramid agrees with its networks); else SNDE_ERR_SHAPE. */
+SNDE_API int snde_frames_to_pyramid(int n, int H, int W, int num_scales, const uint8_t *frames, int64_t sn, int64_t sc,
+                           int64_t sh, int64_t sw, float *const *levels, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

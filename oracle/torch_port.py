@@ -98,6 +98,15 @@ def smooth_loss(depth, image):
     return torch.mean(torch.abs(gx(depth) * wx)) + torch.mean(torch.abs(gy(depth) * wy))
 
 
+def frames_to_pyramid(frames_u8, num_scales):
+    """models/baseline.py:761-767 (uint8 -> float, *= 1/255, * 2 - 1) + utils/utils_edited.py:89-112 (area pyramid), planar levels"""
+    x = frames_u8.float()
+    x *= 1. / 255.
+    x = x * 2. - 1.
+    h, w = x.shape[2:]
+    return [x] + [F.interpolate(x, size=(int(h / 2 ** s), int(w / 2 ** s)), mode="area") for s in range(1, num_scales)]
+
+
 def loss_path(tgt_pyr, src_pyr, depth_pyr, poses, K_ms, alpha=0.85, w_rigid=1.0, w_smooth=0.5):
     """tgt_pyr[s] (B,3,h,w), src_pyr[s] (S*B,3,h,w) planar; depth_pyr[s] (B(1+S),h,w); poses (B,S,6); K_ms (B,scales,3,3)."""
     B, S = poses.shape[:2]

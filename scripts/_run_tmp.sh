@@ -1,3 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3
-python bench.py --steps 500 --warmup 20 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print("default lib", round(d["ms_per_step"]*1e3,1), "us  loss", d["config"]["loss_check"])'
-bash scripts/gpu_profile.sh
+timeout 900 python -m pytest tests -m gpu -q -k "frames or lean_instance_equals" 2>&1 | tail -2
+timeout 600 python bench.py --steps 300 --warmup 30 --no-cpu-baseline 2>gpurun_out/bench.err | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print("step", round(d["ms_per_step"]*1e3,1), "us; e2e", d["e2e"])'

@@ -402,3 +402,86 @@ extern "C" int snde_smooth_loss_bwd(int M, int h, int w, SndeMap depth, SndeImag
     SNDE_CHECK_LAUNCH();
     return SNDE_OK;
 }
+
+// =============================================================================================
+// frames -> normalised fp32 pyramid (caller-side prep)
+// reference: models/baseline.py:761-767 (uint8 -> float, *= 1/255, * 2 - 1) and
+// utils/utils_edited.py:89-112 (scale_pyramid: F.interpolate(mode='area')).
+// One thread owns one R x R block of one channel plane (R = 2^(num_scales-1)): it reads R rows of R bytes and writes
+// the block of every level; neighbouring threads own neighbouring blocks of a row, so every access is coalesced.
+// Sums run over each window in row-major order and are divided by the (power of two) count, like adaptive_avg_pool2d.
+// =============================================================================================
+struct PyrLevels { float *p[SNDE_MAX_SCALES]; };
+
+template <int NS>
+__global__ void __launch_bounds__(128) frames_to_pyramid_kernel(long long total, int H, int W, const uint8_t *__restrict__ frames,
+                                                                long long sn, long long sc, long long sh, long long sw, PyrLevels lv) {
+    constexpr int R = 1 << (NS - 1);
+    const int bw = W / R, bh = H / R;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int bx = (int)(i % bw);
+        long long r = i / bw;
+        const int by = (int)(r % bh);
+        r /= bh;
+        const int c = (int)(r % 3);
+        const long long n = r / 3;
+        const uint8_t *src = frames + n * sn + c * sc + (long long)(by * R) * sh + (long long)(bx * R) * sw;
+        float v[R][R];
+#pragma unroll
+        for (int y = 0; y < R; ++y) {
+            if (sw == 1 && R == 8 && (((uintptr_t)(src + y * sh)) & 7) == 0) {
+                const uint2 w8 = __ldg(reinterpret_cast<const uint2 *>(src + y * sh));
+#pragma unroll
+                for (int x = 0; x < 8; ++x) v[y][x] = (float)(((x < 4 ? w8.x : w8.y) >> (8 * (x & 3))) & 0xffu);
+            } else {
+#pragma unroll
+                for (int x = 0; x < R; ++x) v[y][x] = (float)__ldg(src + y * sh + x * sw);
+            }
+#pragma unroll
+            for (int x = 0; x < R; ++x) v[y][x] = __fsub_rn(__fmul_rn(__fmul_rn(v[y][x], 1.f / 255.f), 2.f), 1.f);   // (u8 * 1/255) * 2 - 1, op by op
+        }
+        const long long plane = n * 3 + c;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            constexpr int dummy = 0; (void)dummy;
+            const int k = 1 << s, hs = H >> s, ws = W >> s, m = R >> s;      // window size, level size, block size at this level
+            float *dst = lv.p[s] + (plane * hs + (long long)by * m) * ws + (long long)bx * m;
+#pragma unroll
+            for (int y = 0; y < m; ++y)
+#pragma unroll
+                for (int x = 0; x < m; ++x) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int dy = 0; dy < k; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < k; ++dx) acc = __fadd_rn(acc, v[y * k + dy][x * k + dx]);
+                    dst[(long long)y * ws + x] = s == 0 ? v[y][x] : __fmul_rn(acc, 1.f / (float)(k * k));
+                }
+        }
+    }
+}
+
+extern "C" int snde_frames_to_pyramid(int n, int H, int W, int num_scales, const uint8_t *frames, int64_t sn, int64_t sc, int64_t sh,
+                                      int64_t sw, float *const *levels, void *stream) {
+    if (!frames || !levels) return SNDE_ERR_NULL;
+    if (n <= 0 || H <= 0 || W <= 0 || num_scales <= 0 || num_scales > 5) return SNDE_ERR_SHAPE;     // R x R floats live in registers: R <= 16
+    const int R = 1 << (num_scales - 1);
+    if (H % R || W % R) return SNDE_ERR_SHAPE;
+    if ((long long)n * 3 * H * W >= (1LL << 40)) return SNDE_ERR_TOO_LARGE;
+    PyrLevels lv;
+    for (int s = 0; s < SNDE_MAX_SCALES; ++s) lv.p[s] = nullptr;
+    for (int s = 0; s < num_scales; ++s) { if (!levels[s]) return SNDE_ERR_NULL; lv.p[s] = levels[s]; }
+    const long long total = (long long)n * 3 * (H / R) * (W / R);
+    const long long want = (total + 127) / 128;
+    const int blocks = (int)(want < 148LL * 32 ? want : 148LL * 32);
+    cudaStream_t st = as_stream(stream);
+    switch (num_scales) {
+        case 1: frames_to_pyramid_kernel<1><<<blocks, 128, 0, st>>>(total, H, W, frames, sn, sc, sh, sw, lv); break;
+        case 2: frames_to_pyramid_kernel<2><<<blocks, 128, 0, st>>>(total, H, W, frames, sn, sc, sh, sw, lv); break;
+        case 3: frames_to_pyramid_kernel<3><<<blocks, 128, 0, st>>>(total, H, W, frames, sn, sc, sh, sw, lv); break;
+        case 4: frames_to_pyramid_kernel<4><<<blocks, 128, 0, st>>>(total, H, W, frames, sn, sc, sh, sw, lv); break;
+        default: frames_to_pyramid_kernel<5><<<blocks, 128, 0, st>>>(total, H, W, frames, sn, sc, sh, sw, lv); break;
+    }
+    SNDE_CHECK_LAUNCH();
+    return SNDE_OK;
+}

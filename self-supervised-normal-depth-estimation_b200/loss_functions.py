@@ -75,6 +75,7 @@ def inverse_warp(img, depth, pose, intrinsics, reverse_pose=False, padding_mode=
 
 
 _PLAN_CACHE: "dict[tuple, ops.FusedLossPlan]" = {}
+_PYR_CACHE: "dict[tuple, tuple]" = {}
 _PLAN_CACHE_MAX = 16
 
 
@@ -89,7 +90,7 @@ def _cached_plan(cfg, poses, K_ms, depth_pyr, tgt_pyr, src_pyr, need, want_K):
            None if masks is None else tuple((sig(a), sig(b)) for a, b in masks), cfg["no_photo"], cfg["no_smooth"])
     plan = _PLAN_CACHE.get(key)
     if plan is None:
-        if not poses.is_contiguous() or not K_ms.is_contiguous():
+        if not poses.is_contiguous():
             # the plan would hold private contiguous copies: not reusable
             return ops.FusedLossPlan(tgt_pyr, src_pyr, depth_pyr, poses, K_ms, cfg["alpha"], cfg["photo_weights"], cfg["smooth_weights"],
                                      want_grad=need, want_grad_K=want_K, padding_mode=cfg["padding_mode"], masks=masks,
@@ -134,8 +135,9 @@ class _FusedLoss(torch.autograd.Function):
         gposes = saved[0]
         gK = saved[1] if ctx.has_K else None
         gdepth = saved[1 + (1 if ctx.has_K else 0):]
+        gd = torch._foreach_mul(list(gdepth), g)         # one multi-tensor launch for the whole pyramid
         return (None, gposes * g if ctx.needs_input_grad[1] else None, gK * g if gK is not None else None,
-                *[t * g for t in gdepth], *([None] * (2 * ns)))
+                *gd, *([None] * (2 * ns)))
 
 
 def geonet_loss(tgt_pyr: Sequence[torch.Tensor], src_pyr: Sequence[torch.Tensor], depth_pyr: Sequence[torch.Tensor],
@@ -163,3 +165,42 @@ def photometric_reconstruction_loss(tgt_pyr, src_pyr, intrinsics_ms, depth_pyr, 
     total, _ = geonet_loss(tgt_pyr, src_pyr, depth_pyr, poses, intrinsics_ms, alpha, weight, 0.0, padding_mode,
                            explainability_mask, no_smooth=True)
     return total
+
+
+def geonet_loss_from_frames(tgt_u8, src_u8, depth_pyr, poses, intrinsics, alpha: float = 0.85, loss_weight_rigid_warp: float = 1.0,
+                            loss_weight_disparity_smooth: float = 0.5):
+    """The step as the reference's trainer sees it (models/baseline.py:746-792 + 867-986 + 1115-1161): uint8 frames as the
+    DataLoader delivers them -- tgt_u8 (B,3,H,W), src_u8 (B,3*S,H,W) -- are normalised and turned into pyramids on the
+    device (one kernel each), intrinsics (B,3,3) into their per-scale copies, then the fused loss runs.
+    depth_pyr[s] (B*(1+S),h_s,w_s), poses (B,S,6).  Returns (loss_total, detail) like geonet_loss."""
+    ns = len(depth_pyr)
+    B, S = poses.shape[0], poses.shape[1]
+    H, W = tgt_u8.shape[2], tgt_u8.shape[3]
+    # pyramid buffers are kept per (frame buffers, shape): a trainer that re-uses its input buffers re-uses these too,
+    # which also keeps the fused-loss plan (keyed on buffer addresses) cached
+    key = (tgt_u8.data_ptr(), src_u8.data_ptr(), tuple(tgt_u8.shape), tuple(src_u8.shape), tuple(tgt_u8.stride()), tuple(src_u8.stride()), ns)
+    bufs = _PYR_CACHE.get(key)
+    if bufs is None:
+        if len(_PYR_CACHE) >= _PLAN_CACHE_MAX:
+            _PYR_CACHE.pop(next(iter(_PYR_CACHE)))
+        dev = tgt_u8.device
+        # per-scale intrinsics K_s = K * M_s + E (fx, fy, cx, cy / 2^s, zeros and a one elsewhere: utils_edited.py:149-169),
+        # stored scale-major so that every scale is a contiguous (B,3,3) block the C call can point at
+        M = torch.zeros(ns, 1, 3, 3, device=dev)
+        for s in range(ns):
+            M[s, 0, 0, 0] = M[s, 0, 1, 1] = M[s, 0, 0, 2] = M[s, 0, 1, 2] = 1.0 / 2 ** s
+        E = torch.zeros(1, 1, 3, 3, device=dev)
+        E[0, 0, 2, 2] = 1.0
+        bufs = ([torch.empty(B, 3, H >> s, W >> s, device=dev) for s in range(ns)],
+                [torch.empty(S * B, 3, H >> s, W >> s, device=dev) for s in range(ns)],
+                torch.empty(ns, B, 3, 3, device=dev), M, E)
+        _PYR_CACHE[key] = bufs
+    tgt_pyr, src_pyr, K_sb, M, E = bufs
+    ops.frames_to_pyramid(tgt_u8, ns, out=tgt_pyr)
+    # (B,3S,H,W) -> source-major (S*B,3,h,w) levels (baseline.py:772-775): one call per source on a strided view, no copy
+    for k in range(S):
+        ops.frames_to_pyramid(src_u8[:, 3 * k:3 * (k + 1)], ns, out=[t[k * B:(k + 1) * B] for t in src_pyr])
+    torch.mul(intrinsics.float().unsqueeze(0), M, out=K_sb)
+    K_sb += E
+    K_ms = K_sb.permute(1, 0, 2, 3)                 # (B,scales,3,3) view; K_ms[:, s] is contiguous
+    return geonet_loss(tgt_pyr, src_pyr, depth_pyr, poses, K_ms, alpha, loss_weight_rigid_warp, loss_weight_disparity_smooth)

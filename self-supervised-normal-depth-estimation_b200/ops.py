@@ -127,7 +127,8 @@ class FusedLossPlan:
     def refresh_intrinsics(self, K_ms: torch.Tensor) -> None:
         """Re-copy the per-scale intrinsics (the plan keeps contiguous (B,3,3) copies of the strided K_ms[:, s])."""
         for s in range(self.ns):
-            self.K[s].copy_(K_ms[:, s])
+            if self.K[s].data_ptr() != K_ms[:, s].data_ptr():     # the plan already points at the caller's block
+                self.K[s].copy_(K_ms[:, s])
 
     def run(self) -> None:
         """Launch on the current stream (asynchronous)."""
@@ -256,3 +257,22 @@ def smooth_bwd(depth_mhw, img_nhwc_, gscale):
     gscale = gscale.reshape(1).contiguous().float()
     _abi.check(_abi.lib().snde_smooth_loss_bwd(M, h, w, map_nhw(depth_mhw), img_nhwc(img_nhwc_), gscale.data_ptr(), map_nhw(g), _stream()))
     return g
+
+
+def frames_to_pyramid(frames_u8: torch.Tensor, num_scales: int, out: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+    """uint8 frames (n,3,H,W), any strides -> list of planar fp32 levels (n,3,H>>s,W>>s) with values (u8/255)*2-1 averaged
+    over 2^s x 2^s blocks: the image part of iter_data_preparation fused with scale_pyramid (one kernel).
+    out: optional pre-allocated contiguous levels (e.g. slices of a source-major buffer)."""
+    if not frames_u8.is_cuda or frames_u8.dtype != torch.uint8:
+        raise RuntimeError("frames_to_pyramid needs a CUDA uint8 tensor (there is no CPU fallback)")
+    n, c, H, W = frames_u8.shape
+    if c != 3:
+        raise ValueError("frames must be (n,3,H,W)")
+    levels = list(out) if out is not None else [torch.empty(n, 3, H >> s, W >> s, device=frames_u8.device) for s in range(num_scales)]
+    for s, t in enumerate(levels):
+        if t.shape != (n, 3, H >> s, W >> s) or not t.is_contiguous() or t.dtype != torch.float32:
+            raise ValueError("pyramid level buffers must be contiguous fp32 (n,3,H>>s,W>>s)")
+    ptrs = (C.c_void_p * num_scales)(*[t.data_ptr() for t in levels])
+    st = frames_u8.stride()
+    _abi.check(_abi.lib().snde_frames_to_pyramid(n, H, W, num_scales, frames_u8.data_ptr(), st[0], st[1], st[2], st[3], ptrs, _stream()))
+    return levels

@@ -30,14 +30,14 @@ def scale_pyramid(img, num_scales):
 
 
 def compute_multi_scale_intrinsics(intrinsics, num_scales):
-    """reference :149-169 -> (B, num_scales, 3, 3)"""
+    """reference :149-169 -> (B, num_scales, 3, 3): fx, fy, cx, cy divided by 2^s, zeros and a one elsewhere."""
+    div = (2.0 ** torch.arange(num_scales, device=intrinsics.device, dtype=intrinsics.dtype)).view(1, num_scales)
     out = torch.zeros(intrinsics.shape[0], num_scales, 3, 3, dtype=intrinsics.dtype, device=intrinsics.device)
-    for s in range(num_scales):
-        out[:, s, 0, 0] = intrinsics[:, 0, 0] / (2 ** s)
-        out[:, s, 1, 1] = intrinsics[:, 1, 1] / (2 ** s)
-        out[:, s, 0, 2] = intrinsics[:, 0, 2] / (2 ** s)
-        out[:, s, 1, 2] = intrinsics[:, 1, 2] / (2 ** s)
-        out[:, s, 2, 2] = 1.0
+    out[:, :, 0, 0] = intrinsics[:, 0, 0, None] / div
+    out[:, :, 1, 1] = intrinsics[:, 1, 1, None] / div
+    out[:, :, 0, 2] = intrinsics[:, 0, 2, None] / div
+    out[:, :, 1, 2] = intrinsics[:, 1, 2, None] / div
+    out[:, :, 2, 2] = 1.0
     return out
 
 

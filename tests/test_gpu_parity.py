@@ -404,3 +404,60 @@ def test_identity_pose_large_image_sweep_shape():
     # outside [0,W-1) x [0,H-1) the reference's clamped-corner weights cancel: zero up to rounding residue
     assert warped[~inner].abs().max().item() < 1e-6
     assert valid[:, -1].mean().item() < 0.9 and valid[:, :, -1].mean().item() < 0.9
+
+
+# ---------------------------------------------------------------------------------------------------
+# caller-side prep (section 8(f1)): uint8 frames -> normalised pyramids
+# ---------------------------------------------------------------------------------------------------
+def _reference_prep(frames_u8, num_scales):
+    """models/baseline.py:761-767 + utils/utils_edited.py:89-112, stated with torch ops"""
+    import torch.nn.functional as F
+    x = frames_u8.float()
+    x = x * (1. / 255.)
+    x = x * 2. - 1.
+    h, w = x.shape[2:]
+    return [x] + [F.interpolate(x, size=(int(h / 2 ** s), int(w / 2 ** s)), mode="area") for s in range(1, num_scales)]
+
+
+@pytest.mark.parametrize("shape", [(3, 128, 416, 4), (2, 480, 640, 4), (1, 64, 96, 3), (2, 376, 1248, 4)])
+def test_frames_to_pyramid_matches_reference_prep(shape):
+    from snde_b200 import ops
+    n, H, W, ns = shape
+    g = torch.Generator().manual_seed(n + H)
+    frames = torch.randint(0, 256, (n, 3, H, W), generator=g, dtype=torch.uint8).to(DEV)
+    got = ops.frames_to_pyramid(frames, ns)
+    ref = _reference_prep(frames, ns)
+    for a, b in zip(got, ref):
+        assert a.shape == b.shape
+        assert (a - b).abs().max().item() <= 2e-7
+    # NHWC camera buffers through strides give the same values
+    nhwc = frames.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    for a, b in zip(ops.frames_to_pyramid(nhwc, ns), got):
+        assert torch.equal(a, b)
+    with pytest.raises(RuntimeError):
+        ops.frames_to_pyramid(frames[:, :, :H - 1], ns)          # H not a multiple of 2^(ns-1)
+
+
+def test_geonet_loss_from_frames_equals_reference_prep_then_loss():
+    from snde_b200.loss_functions import geonet_loss, geonet_loss_from_frames
+    from snde_b200.synthetic import make_inputs
+    from snde_b200.utils_edited import compute_multi_scale_intrinsics
+    B, S, H, W, ns = 2, 2, 64, 96, 3
+    g = torch.Generator().manual_seed(4)
+    tgt = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).to(DEV)
+    src = torch.randint(0, 256, (B, 3 * S, H, W), generator=g, dtype=torch.uint8).to(DEV)
+    inp = make_inputs(B=B, S=S, H=H, W=W, num_scales=ns, seed=8).to(DEV)
+    depth = [d.clone().requires_grad_(True) for d in inp.depth_pyr]
+    poses = inp.poses.clone().requires_grad_(True)
+    total, detail = geonet_loss_from_frames(tgt, src, depth, poses, inp.K)
+    total.backward()
+    src_cat = torch.cat([src[:, 3 * k:3 * (k + 1)] for k in range(S)], 0)
+    depth2 = [d.detach().clone().requires_grad_(True) for d in inp.depth_pyr]
+    poses2 = inp.poses.clone().requires_grad_(True)
+    total2, _ = geonet_loss(_reference_prep(tgt, ns), _reference_prep(src_cat, ns), depth2, poses2,
+                            compute_multi_scale_intrinsics(inp.K, ns))
+    total2.backward()
+    assert abs(total.item() - total2.item()) < 1e-6 * abs(total2.item())
+    for a, b in zip(depth, depth2):
+        assert rel_l2(a.grad.cpu().numpy(), b.grad.cpu().numpy()) < 1e-5
+    assert rel_l2(poses.grad.cpu().numpy(), poses2.grad.cpu().numpy()) < 1e-5
