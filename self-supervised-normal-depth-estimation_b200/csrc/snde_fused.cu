@@ -157,7 +157,12 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     // else 32 (measured at config 2: 16 -> 344 us, 32 -> 318, 64 -> 308, 128 -> 416).  SNDE_SEG_ROWS overrides (tuning only).
     static int seg_env = -1;
     if (seg_env < 0) { const char *e = getenv("SNDE_SEG_ROWS"); seg_env = e ? atoi(e) : 0; if (seg_env < 0) seg_env = 0; }
-    int rc = build_dev_loss(a, d, &lay, &tiles, seg_env ? seg_env : 64);       // validates every argument before any CUDA call
+    // SNDE_FINE_ROWS / SNDE_FINE_PERMILLE: cut the last share of the owners into short tail-filling segments (tuning only;
+    // off by default: measured at config 2, 16 rows for 15 % .. 60 % of the owners gave 301 .. 323 us against 301 .. 306 us without)
+    static int fine_rows = -1, fine_pm = -1;
+    if (fine_rows < 0) { const char *e = getenv("SNDE_FINE_ROWS"); fine_rows = e ? atoi(e) : 0; }
+    if (fine_pm < 0) { const char *e = getenv("SNDE_FINE_PERMILLE"); fine_pm = e ? atoi(e) : 0; }
+    int rc = build_dev_loss(a, d, &lay, &tiles, seg_env ? seg_env : 64, fine_rows, fine_pm);       // validates every argument before any CUDA call
     if (rc) return rc;
     int devi = 0;
     if (cudaGetDevice(&devi) != cudaSuccess || devi < 0 || devi >= 64) return SNDE_ERR_CUDA;
@@ -169,7 +174,7 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     }
     const long long resident_pairs = (long long)sm_count[devi] * SNDE_STRIP_CTAS_PER_SM * StripCfg::PAIRS;
     if (!seg_env && tiles < 2 * resident_pairs) {
-        rc = build_dev_loss(a, d, &lay, &tiles, 32);
+        rc = build_dev_loss(a, d, &lay, &tiles, 32, fine_rows, fine_pm);
         if (rc) return rc;
     }
     cudaStream_t st = as_stream(stream_);

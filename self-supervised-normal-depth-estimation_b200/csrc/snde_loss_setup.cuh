@@ -116,7 +116,8 @@ static inline void loss_final_host(int B, int S, int ns, int flags, const float 
     }
 }
 
-static inline int build_dev_loss(const SndeLossArgs *a, DevLoss &d, const LossWorkspace *lay, int64_t *num_tiles, int seg_rows = 0) {
+static inline int build_dev_loss(const SndeLossArgs *a, DevLoss &d, const LossWorkspace *lay, int64_t *num_tiles, int seg_rows = 0,
+                                 int fine_rows = 0, int fine_permille = 0) {
     if (!a) return SNDE_ERR_NULL;
     if (a->B <= 0 || a->S <= 0 || a->num_scales <= 0 || a->num_scales > SNDE_MAX_SCALES) return SNDE_ERR_SHAPE;
     if (a->S > StripCfg::MAX_S) return SNDE_ERR_SHAPE;       // SNDE_MAX_SOURCES
@@ -144,10 +145,7 @@ static inline int build_dev_loss(const SndeLossArgs *a, DevLoss &d, const LossWo
             !fits32(in.err_fwd.sc, in.err_fwd.sh, in.err_fwd.sw, in.h, in.w) || !fits32(in.err_bwd.sc, in.err_bwd.sh, in.err_bwd.sw, in.h, in.w))
             return SNDE_ERR_TOO_LARGE;
         o.h = in.h; o.w = in.w;
-        o.seg_h = seg_rows > 0 ? seg_rows : StripCfg::SEG;
-        if (o.seg_h > in.h) o.seg_h = in.h;
         o.tiles_x = (in.w + StripCfg::TW - 1) / StripCfg::TW;
-        o.tiles_y = (in.h + o.seg_h - 1) / o.seg_h;
         // fast path: planar tensors, unit x-stride, even row / plane / batch strides and 8-byte aligned bases, even width:
         // the lane's pixel pair is then one aligned 64-bit access everywhere
         {
@@ -177,16 +175,28 @@ static inline int build_dev_loss(const SndeLossArgs *a, DevLoss &d, const LossWo
         o.err_fwd = dev(in.err_fwd); o.err_bwd = dev(in.err_bwd);
     }
     if (lay) d.counter = (int *)(ws + lay->counter);
-    // work table: the heavy class-F tasks (S passes each) first, then the class-R tasks
+    // Task table.  Most owners are cut into long segments (seg_rows rows: few halo rows recomputed); the last fine_permille
+    // of the owners of every (class, scale) into short ones (fine_rows), queued last, so that the tail of the dynamic
+    // queue is made of small tasks.  Heavy class-F tasks (S passes each) come first within each group.
     long long total = 0;
     int ne = 0;
-    for (int cls = 0; cls < 2; ++cls)
-        for (int s = 0; s < ns; ++s) {
-            const long long cnt = (long long)d.sc[s].tiles_x * d.sc[s].tiles_y * (cls == 0 ? B : N);
-            if (total + cnt >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
-            d.entry[ne++] = DevEntry{(int)total, (int)cnt, s, cls};
-            total += cnt;
-        }
+    const int coarse = seg_rows > 0 ? seg_rows : StripCfg::SEG;
+    for (int grp = 0; grp < 2; ++grp)
+        for (int cls = 0; cls < 2; ++cls)
+            for (int s = 0; s < ns; ++s) {
+                const int owners = cls == 0 ? B : (int)N, h = d.sc[s].h;
+                int n_fine = (fine_rows > 0 && fine_rows < coarse && h > fine_rows) ? (int)(((long long)owners * fine_permille + 999) / 1000) : 0;
+                if (n_fine > owners) n_fine = owners;
+                const int first = grp == 0 ? 0 : owners - n_fine, cnt_owners = grp == 0 ? owners - n_fine : n_fine;
+                if (cnt_owners <= 0) continue;
+                int seg = grp == 0 ? coarse : fine_rows;
+                if (seg > h) seg = h;
+                const int ty = (h + seg - 1) / seg;
+                const long long cnt = (long long)d.sc[s].tiles_x * ty * cnt_owners;
+                if (total + cnt >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
+                d.entry[ne++] = DevEntry{(int)total, (int)cnt, s, cls, first, seg, ty, 0};
+                total += cnt;
+            }
     d.num_entries = ne;
     d.total_tasks = (int)total;
     if (num_tiles) *num_tiles = total;

@@ -59,8 +59,8 @@ struct DevMap { const float *p; long long sn; int sh, sw; };
 struct DevMapOut { float *p; long long sn; int sh, sw; };
 
 struct DevScale {
-    int h, w, tiles_x, tiles_y;      // tiles_x = strips per row, tiles_y = segments per column
-    int seg_h, fast;                 // rows per segment; fast != 0: every tensor of this scale is planar, unit x-stride, 8-byte aligned rows
+    int h, w, tiles_x, fast;         // tiles_x = strips per row; fast != 0: every tensor of this scale is planar, unit x-stride, 8-byte aligned rows
+    int pad0_, pad1_;
     DevImage tgt, src;
     DevMap depth;
     DevMapOut gdepth;
@@ -77,14 +77,16 @@ struct DevScale {
     DevImageOut warped_fwd, warped_bwd, err_fwd, err_bwd;
 };
 
-struct DevEntry { int begin, count, scale, cls; };   // cls 0 = F tasks, 1 = R tasks
+// one block of the task table: `count` tasks starting at number `begin`; owners first_owner.. of class cls (0 = F, 1 = R)
+// at `scale`, cut into tiles_y segments of seg_h rows
+struct DevEntry { int begin, count, scale, cls, first_owner, seg_h, tiles_y, pad_; };
 
 struct DevLoss {
     int B, S, num_scales, flags, padding, num_entries;
     float alpha, oma;
     int total_tasks, pad_;
     int *counter;                    // workspace: next task to hand out (zeroed per call)
-    DevEntry entry[2 * SNDE_MAX_SCALES];
+    DevEntry entry[4 * SNDE_MAX_SCALES];
     DevScale sc[SNDE_MAX_SCALES];
 };
 
@@ -289,13 +291,14 @@ SNDE_STRIP_FN void decode_task(const DevLoss &p, int task, int lane, StripTask &
     const DevEntry ent = p.entry[e];
     const DevScale &sc = p.sc[ent.scale];
     const int local = task - ent.begin;
-    const int per_owner = sc.tiles_x * sc.tiles_y;
+    const int per_owner = sc.tiles_x * ent.tiles_y;
     T.scale = ent.scale;
-    T.m = local / per_owner;                         // owner index inside its class
-    const int tt = local - T.m * per_owner;
+    const int mo = local / per_owner;
+    T.m = ent.first_owner + mo;                      // owner index inside its class
+    const int tt = local - mo * per_owner;
     const int sy = tt / sc.tiles_x, sx = tt - sy * sc.tiles_x;
     T.h = sc.h; T.w = sc.w;
-    T.y0 = sy * sc.seg_h; T.y1 = T.y0 + sc.seg_h < sc.h ? T.y0 + sc.seg_h : sc.h;
+    T.y0 = sy * ent.seg_h; T.y1 = T.y0 + ent.seg_h < sc.h ? T.y0 + ent.seg_h : sc.h;
     T.ix0 = sx * C::TW - 2 + 2 * lane;
     T.clsF = ent.cls == 0;
     T.b = T.clsF ? T.m : (T.m % p.B);                // batch element (selects K)

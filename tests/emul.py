@@ -32,7 +32,7 @@ def _map(a):   # numpy (n,h,w)
     return _abi.map_view(a.ctypes.data, [s // 4 for s in a.strides])
 
 
-def run_loss(inp, alpha=0.85, w_rigid=1.0, w_smooth=0.5, flags=1, padding=0, masks=None, want_maps=False, seg_rows=0):
+def run_loss(inp, alpha=0.85, w_rigid=1.0, w_smooth=0.5, flags=1, padding=0, masks=None, want_maps=False, seg_rows=0, fine_rows=0, fine_permille=0):
     """inp: snde_b200.synthetic.LossInputs (CPU torch). Returns dict like oracle.compose.geonet_loss."""
     from snde_b200 import _abi
     lib = C.CDLL(build())
@@ -74,7 +74,7 @@ def run_loss(inp, alpha=0.85, w_rigid=1.0, w_smooth=0.5, flags=1, padding=0, mas
     wsp = (ws.ctypes.data + 15) & ~15
     args = _abi.make_loss_args(B, S, alpha, flags, padding, poses.ctypes.data, scales, loss_out.ctypes.data, gposes.ctypes.data,
                                gK.ctypes.data, wsp, nbytes)
-    rc = lib.emul_loss_fwdbwd(C.byref(args), C.c_int(seg_rows))
+    rc = lib.emul_loss_fwdbwd(C.byref(args), C.c_int(seg_rows), C.c_int(fine_rows), C.c_int(fine_permille))
     if rc < 0:
         raise RuntimeError(abi.snde_strerror(rc).decode())
     res = dict(variant=rc, loss_total=float(loss_out[0]), loss_rigid_warp=float(loss_out[1]), loss_disp_smooth=float(loss_out[2]),

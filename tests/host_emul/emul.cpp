@@ -94,8 +94,9 @@ void host_pair_sync(int) { sync_on(g_pair.pair_sync, 64); }
 
 extern "C" __attribute__((visibility("default"))) size_t emul_sizeof_loss_args(void) { return sizeof(SndeLossArgs); }
 
-// seg_rows: rows per strip segment (0 = the library's default); lets the tests exercise segment seams on small images
-extern "C" __attribute__((visibility("default"))) int emul_loss_fwdbwd(const SndeLossArgs *a, int seg_rows) {
+// seg_rows: rows per strip segment (0 = the library's default), fine_rows / fine_permille: the tail-filling short segments;
+// they let the tests exercise segment seams and mixed task tables on small images
+extern "C" __attribute__((visibility("default"))) int emul_loss_fwdbwd(const SndeLossArgs *a, int seg_rows, int fine_rows, int fine_permille) {
     if (!a || !a->poses || !a->loss_out) return SNDE_ERR_NULL;
     if ((a->flags & SNDE_LOSS_GRAD) && !a->grad_poses) return SNDE_ERR_NULL;
     if ((a->flags & SNDE_LOSS_GRAD_K) && !a->grad_K) return SNDE_ERR_NULL;
@@ -103,7 +104,7 @@ extern "C" __attribute__((visibility("default"))) int emul_loss_fwdbwd(const Snd
     const LossWorkspace lay = loss_ws_layout(a->B, a->S, a->num_scales);
     if (!a->workspace || a->workspace_bytes < lay.end || ((uintptr_t)a->workspace & 15)) return SNDE_ERR_WORKSPACE;
     DevLoss d; int64_t tasks = 0;
-    int rc = build_dev_loss(a, d, &lay, &tasks, seg_rows);
+    int rc = build_dev_loss(a, d, &lay, &tasks, seg_rows, fine_rows, fine_permille);
     if (rc) return rc;
     const int B = a->B, S = a->S, ns = a->num_scales, N = B * S;
     unsigned char *ws = (unsigned char *)a->workspace;

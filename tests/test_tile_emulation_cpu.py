@@ -122,6 +122,19 @@ def test_emulated_segment_seams(seg_rows):
     assert rel_l2(b["grad_K_ms"], a["grad_K_ms"]) < 1e-5
 
 
+def test_emulated_mixed_task_table():
+    """long segments for most owners, short tail-filling segments for the rest: same bits"""
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**CASES["small_smooth"])
+    a = emul.run_loss(inp, flags=1)
+    for fine_rows, pm in ((5, 500), (8, 1000), (4, 300)):
+        b = emul.run_loss(inp, flags=1, seg_rows=16, fine_rows=fine_rows, fine_permille=pm)
+        assert abs(a["loss_total"] - b["loss_total"]) < 1e-6 * abs(a["loss_total"])
+        for s in range(inp.num_scales):
+            assert np.array_equal(a["grad_depth"][s], b["grad_depth"][s])
+        assert rel_l2(b["grad_poses"], a["grad_poses"]) < 1e-5
+
+
 def test_emulated_variants_selected():
     """planar inputs take the FAST (64-bit pair access) variant, permuted NHWC views and odd widths the generic one"""
     import torch
