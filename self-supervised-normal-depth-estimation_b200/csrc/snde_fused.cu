@@ -138,7 +138,8 @@ extern "C" int64_t snde_loss_num_tiles(const SndeLossArgs *args) {
     if (!args) return SNDE_ERR_NULL;
     int rc = build_dev_loss(args, d, nullptr, &n, 64);
     if (rc) return rc;
-    if (n < 2LL * 148 * SNDE_STRIP_CTAS_PER_SM * StripCfg::PAIRS) rc = build_dev_loss(args, d, nullptr, &n, 32);
+    const long long pairs = 148LL * SNDE_STRIP_CTAS_PER_SM * StripCfg::PAIRS;
+    if (n < 2 * pairs) { rc = build_dev_loss(args, d, nullptr, &n, 32); if (!rc && n < pairs) rc = build_dev_loss(args, d, nullptr, &n, 16); }
     return rc ? rc : n;
 }
 
@@ -154,7 +155,7 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     DevLoss d; int64_t tiles = 0;
     // Rows per strip segment.  Longer segments recompute fewer halo rows (a segment of s rows costs s + 6 row steps) but
     // give fewer tasks to balance over the resident warp pairs: 64 rows when that still leaves two tasks per pair,
-    // else 32 (measured at config 2: 16 -> 344 us, 32 -> 318, 64 -> 308, 128 -> 416).  SNDE_SEG_ROWS overrides (tuning only).
+    // else 32, else (fewer tasks than pairs) 16 (measured at config 2: 16 -> 344 us, 32 -> 318, 64 -> 308, 128 -> 416).  SNDE_SEG_ROWS overrides (tuning only).
     static int seg_env = -1;
     if (seg_env < 0) { const char *e = getenv("SNDE_SEG_ROWS"); seg_env = e ? atoi(e) : 0; if (seg_env < 0) seg_env = 0; }
     // SNDE_FINE_ROWS / SNDE_FINE_PERMILLE: cut the last share of the owners into short tail-filling segments (tuning only;
@@ -176,6 +177,10 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     if (!seg_env && tiles < 2 * resident_pairs) {
         rc = build_dev_loss(a, d, &lay, &tiles, 32, fine_rows, fine_pm);
         if (rc) return rc;
+        if (tiles < resident_pairs) {             // small batches (the reference's default B = 4): latency, not throughput
+            rc = build_dev_loss(a, d, &lay, &tiles, 16, fine_rows, fine_pm);
+            if (rc) return rc;
+        }
     }
     cudaStream_t st = as_stream(stream_);
     const int B = a->B, S = a->S, ns = a->num_scales, N = B * S;

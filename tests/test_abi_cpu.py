@@ -104,8 +104,8 @@ def test_num_tiles(abi):
         sc.depth.ptr = dummy.ctypes.data; sc.K = dummy.ctypes.data; sc.xtab = dummy.ctypes.data; sc.ytab = dummy.ctypes.data
     per_img = [7 * 2, 4 * 1, 2 * 1, 1 * 1]
     assert lib.snde_loss_num_tiles(C.byref(args)) == sum(per_img) * 32 * 3
-    args.B = 4                                        # config 1: too few tasks at 64 rows -> 32-row segments
-    assert lib.snde_loss_num_tiles(C.byref(args)) == (7 * 4 + 4 * 2 + 2 * 1 + 1 * 1) * 4 * 3
+    args.B = 4                                        # config 1: fewer tasks than resident pairs even at 32 rows -> 16-row segments
+    assert lib.snde_loss_num_tiles(C.byref(args)) == (7 * 8 + 4 * 4 + 2 * 2 + 1 * 1) * 4 * 3
 
 
 def test_no_fallback_when_library_missing(abi, monkeypatch):
