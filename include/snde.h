@@ -100,7 +100,10 @@ enum {
     SNDE_LOSS_GRAD = 1,         /* also produce grad_depth / grad_poses (/ grad_K) */
     SNDE_LOSS_GRAD_K = 2,       /* also produce grad_K (needs SNDE_LOSS_GRAD) */
     SNDE_LOSS_NO_PHOTO = 4,     /* skip the warp/photometric term */
-    SNDE_LOSS_NO_SMOOTH = 8     /* skip the smoothness term */
+    SNDE_LOSS_NO_SMOOTH = 8,    /* skip the smoothness term */
+    SNDE_LOSS_DISPARITY = 16    /* the `depth` maps hold DISPARITIES (DispNetS heads, models/DispNetS.py:113): the kernel uses
+                                   depth = 1/disp (models/baseline.py:835) and grad_depth receives d loss / d disparity
+                                   = -(g * depth^2), what autograd's reciprocal backward computes (section 8(f2)) */
 };
 
 typedef struct SndeLossArgs {

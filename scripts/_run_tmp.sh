@@ -1,1 +1,2 @@
-for w in config1 config2 nyu hires; do python bench.py --workload $w --steps 300 --warmup 20 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print(d["config"]["workload"][:8], round(d["ms_per_step"]*1e3,1), "us", round(d["value"]/1e9,2), "Gpx/s frac", round(d["roofline"]["frac"],3))'; done
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3
+python bench.py --steps 500 --warmup 20 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print("default lib", round(d["ms_per_step"]*1e3,1), "us  loss", d["config"]["loss_check"])'

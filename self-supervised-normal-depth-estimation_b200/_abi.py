@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("SNDE_LIB", os.path.join(HERE, "libsnde.so"))   # SNDE
 
 SNDE_MAX_SCALES = 6
 SNDE_PAD_ZEROS, SNDE_PAD_BORDER = 0, 1
-SNDE_LOSS_GRAD, SNDE_LOSS_GRAD_K, SNDE_LOSS_NO_PHOTO, SNDE_LOSS_NO_SMOOTH = 1, 2, 4, 8
+SNDE_LOSS_GRAD, SNDE_LOSS_GRAD_K, SNDE_LOSS_NO_PHOTO, SNDE_LOSS_NO_SMOOTH, SNDE_LOSS_DISPARITY = 1, 2, 4, 8, 16
 
 c_float_p = C.POINTER(C.c_float)
 c_double_p = C.POINTER(C.c_double)

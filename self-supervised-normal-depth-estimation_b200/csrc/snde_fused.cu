@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(64) loss_final_kernel(int B, int S, int ns, in
 // nothing, so there is no CTA-wide barrier in the kernel; the two warps of a pair meet at a 64-thread named barrier.
 // Warps w and w + PAIRS form a pair; which of the two is the geometry warp alternates with the CTA index, so every
 // scheduler (warp index mod 4) hosts both kinds of warp.
-template <bool GRAD, bool GRADK, bool EXTRA, bool FAST>
+template <bool GRAD, bool GRADK, bool EXTRA, bool FAST, bool DISP = false>
 __global__ void __launch_bounds__(StripCfg::NT, SNDE_STRIP_CTAS_PER_SM) loss_strip_kernel(const __grid_constant__ DevLoss p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(StripCfg::NT, SNDE_STRIP_CTAS_PER_SM) loss_str
         // value -- and every row index derived from it -- is warp-uniform: uniform branches, no reconvergence stack)
         const int task = __shfl_sync(0xffffffffu, sm.task, 0);
         if (task >= p.total_tasks) break;
-        if (role == 0) geo_role<GRAD, GRADK, EXTRA, FAST>(p, task, lane, sm, bar);
+        if (role == 0) geo_role<GRAD, GRADK, EXTRA, FAST, DISP>(p, task, lane, sm, bar);
         else ssim_role<GRAD, EXTRA>(p, task, lane, sm, bar);
     }
 }
@@ -210,15 +210,19 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     // EXTRA variants honour masks / warped+error outputs / border padding / intrinsics gradients; FAST ones need planar,
     // aligned tensors at every scale.  The lean fast one is the hot path.
     bool extra = gradk || a->padding_mode != SNDE_PAD_ZEROS, fast = true;
+    const bool disp = (a->flags & SNDE_LOSS_DISPARITY) != 0;
     for (int s = 0; s < ns; ++s) {
         const SndeLossScale &in = a->scale[s];
         extra = extra || in.mask_fwd.ptr || in.mask_bwd.ptr || in.warped_fwd.ptr || in.warped_bwd.ptr || in.err_fwd.ptr || in.err_bwd.ptr;
         fast = fast && d.sc[s].fast;
     }
+    // disparity input: one more lean instance (<GRAD, FAST, DISP>); every other combination goes through the general one
+    if (disp && !(grad && fast && !extra)) extra = true;
     if (!grad) {
         if (extra) rc = launch(loss_strip_kernel<false, false, true, false>, 0);
         else rc = fast ? launch(loss_strip_kernel<false, false, false, true>, 1) : launch(loss_strip_kernel<false, false, false, false>, 2);
     } else if (extra) rc = launch(loss_strip_kernel<true, true, true, false>, 3);
+    else if (disp) rc = launch(loss_strip_kernel<true, false, false, true, true>, 6);
     else rc = fast ? launch(loss_strip_kernel<true, false, false, true>, 4) : launch(loss_strip_kernel<true, false, false, false>, 5);
     if (rc) return rc;
     SNDE_CHECK_LAUNCH();

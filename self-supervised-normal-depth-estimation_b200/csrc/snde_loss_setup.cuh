@@ -122,7 +122,7 @@ static inline int build_dev_loss(const SndeLossArgs *a, DevLoss &d, const LossWo
     if (a->B <= 0 || a->S <= 0 || a->num_scales <= 0 || a->num_scales > SNDE_MAX_SCALES) return SNDE_ERR_SHAPE;
     if (a->S > StripCfg::MAX_S) return SNDE_ERR_SHAPE;       // SNDE_MAX_SOURCES
     if (a->padding_mode != SNDE_PAD_ZEROS && a->padding_mode != SNDE_PAD_BORDER) return SNDE_ERR_ARG;
-    if (a->flags & ~15) return SNDE_ERR_ARG;
+    if (a->flags & ~31) return SNDE_ERR_ARG;
     if ((a->flags & SNDE_LOSS_GRAD_K) && !(a->flags & SNDE_LOSS_GRAD)) return SNDE_ERR_ARG;
     if (!(a->alpha >= 0.f && a->alpha <= 1.f)) return SNDE_ERR_ARG;
     memset(&d, 0, sizeof(d));

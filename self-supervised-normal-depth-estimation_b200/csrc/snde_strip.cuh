@@ -90,7 +90,7 @@ struct DevLoss {
     DevScale sc[SNDE_MAX_SCALES];
 };
 
-enum { FLAG_GRAD = 1, FLAG_GRAD_K = 2, FLAG_NO_PHOTO = 4, FLAG_NO_SMOOTH = 8 };   // == SNDE_LOSS_* in include/snde.h
+enum { FLAG_GRAD = 1, FLAG_GRAD_K = 2, FLAG_NO_PHOTO = 4, FLAG_NO_SMOOTH = 8, FLAG_DISP = 16 };   // == SNDE_LOSS_* in include/snde.h
 
 
 struct alignas(16) F4 { float x, y, z, w; };
@@ -441,7 +441,7 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
 // ===============================================================================================================
 // geometry warp
 // ===============================================================================================================
-template <bool GRAD, bool GRADK, bool EXTRA, bool FAST>
+template <bool GRAD, bool GRADK, bool EXTRA, bool FAST, bool DISP>
 struct GeoLane {
     const DevLoss &p;
     const DevScale &sc;
@@ -491,6 +491,16 @@ struct GeoLane {
             }
         }
         row_copy_commit();
+    }
+
+    // ---- disparity input (SNDE_LOSS_DISPARITY): the landed row iy of the ring becomes depth = 1/disp (IEEE division, as
+    //      torch.reciprocal; models/baseline.py:835); slots outside the image stay 0 ----
+    SNDE_STRIP_FN void disparity_to_depth(int iy) const {
+        if (iy < 0 || iy >= T.h) return;
+        F2 v = sm.D[iy & 7][lane];
+        v.x = T.in[0] ? SNDE_XDIV(1.f, v.x) : 0.f;
+        v.y = T.in[1] ? SNDE_XDIV(1.f, v.y) : 0.f;
+        sm.D[iy & 7][lane] = v;
     }
 
     // ---- phase A, first half: reproject the lane's two pixels of a row (in the image) and start the 24 gathers;
@@ -675,20 +685,30 @@ struct GeoLane {
             sy_prev = syw;
         }
         if (GRAD && doG && T.in[0]) {
-            // every lane writes only its own inner pixels; later passes over the same owner add to what this lane wrote
+            // Every lane writes only its own inner pixels; later passes over the same owner add to what this lane wrote.
+            // Disparity input: the last pass turns the finished sum into d/d(disparity) = -(g * depth^2), autograd's
+            // reciprocal backward -grad * (result * result).
+            // (DISP: the lean disparity instance; the general EXTRA instance looks at the flag)
+            const bool to_disp = (DISP || (EXTRA && (p.flags & FLAG_DISP))) && k == T.n_pass - 1;
+            F2 dd = F2{0.f, 0.f};
+            if (DISP || EXTRA) dd = sm.D[r & 7][lane];
             if (FAST) {
                 if (T.colI[0]) {     // inner lanes hold two inner pixels (w even)
                     float *dst = gd_base + (r * gd_sh + ix0);
                     F2 o = F2{gd[0], gd[1]};
                     if (k > 0) { const F2 old = *reinterpret_cast<const F2 *>(dst); o.x += old.x; o.y += old.y; }
+                    if (to_disp) { o.x = SNDE_XMUL(-o.x, SNDE_XMUL(dd.x, dd.x)); o.y = SNDE_XMUL(-o.y, SNDE_XMUL(dd.y, dd.y)); }
                     *reinterpret_cast<F2 *>(dst) = o;
                 }
             } else {
+                const float ddq[2] = {dd.x, dd.y};
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     if (!T.colI[q]) continue;
                     float *dst = gd_base + (r * gd_sh + (ix0 + q) * gd_sw);
-                    *dst = k > 0 ? *dst + gd[q] : gd[q];
+                    float o = k > 0 ? *dst + gd[q] : gd[q];
+                    if (to_disp) o = SNDE_XMUL(-o, SNDE_XMUL(ddq[q], ddq[q]));
+                    *dst = o;
                 }
             }
         }
@@ -697,15 +717,16 @@ struct GeoLane {
 
 // GRAD: also back-propagate.  GRADK: also accumulate d/dKinv.  EXTRA: honour the optional explainability masks,
 // warped / error-map outputs and border padding.  FAST: planar tensors with unit x-stride and 8-byte aligned rows
-// (64-bit loads / stores of the lane's pixel pair).
-template <bool GRAD, bool GRADK, bool EXTRA, bool FAST>
+// (64-bit loads / stores of the lane's pixel pair).  DISP: the depth maps hold disparities (lean instance; the EXTRA
+// instance handles the flag at run time).
+template <bool GRAD, bool GRADK, bool EXTRA, bool FAST, bool DISP>
 SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, int bar) {
     const int lane = who & 31;
     StripTask T;
     decode_task(p, task, lane, T);
     const DevScale &sc = p.sc[T.scale];
     const int B = p.B;
-    GeoLane<GRAD, GRADK, EXTRA, FAST> L(p, sc, sm, T, lane);
+    GeoLane<GRAD, GRADK, EXTRA, FAST, DISP> L(p, sc, sm, T, lane);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         L.xt[q] = T.in[q] ? ldg(sc.xtab + (T.ix0 + q)) : 0.f;
@@ -754,6 +775,8 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
         for (int q = 0; q < 2; ++q) { wts[q][0] = wts[q][1] = wts[q][2] = wts[q][3] = 0.f; dgate[q][0] = dgate[q][1] = 0.f; }
         L.prefetch_row(t_begin); L.prefetch_row(t_begin + 1); L.prefetch_row(t_begin + 2);
         row_copy_wait<1>();               // rows t_begin, t_begin+1 have landed
+        const bool disp_in = DISP || (EXTRA && (p.flags & FLAG_DISP) != 0);
+        if (disp_in) { L.disparity_to_depth(t_begin); L.disparity_to_depth(t_begin + 1); }
         if (T.do_photo && t_begin < h) L.a_issue(ldg(sc.ytab + t_begin), sm.D[t_begin & 7][lane], wts, dgate, taps);
         float yt_n = t_begin + 1 < h ? ldg(sc.ytab + (t_begin + 1)) : 0.f;      // meshgrid y of row t+1, fetched a step ahead
 
@@ -785,6 +808,7 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
             //      next barrier publishes it ----
             L.prefetch_row(t + 3);
             row_copy_wait<1>();
+            if (disp_in) L.disparity_to_depth(t + 2);
         }
         row_copy_wait<0>();
 

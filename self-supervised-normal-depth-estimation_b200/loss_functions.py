@@ -87,19 +87,19 @@ def _cached_plan(cfg, poses, K_ms, depth_pyr, tgt_pyr, src_pyr, need, want_K):
     masks = cfg["masks"]
     key = (sig(poses), sig(K_ms), tuple(sig(t) for t in depth_pyr), tuple(sig(t) for t in tgt_pyr), tuple(sig(t) for t in src_pyr),
            cfg["alpha"], tuple(cfg["photo_weights"]), tuple(cfg["smooth_weights"]), need, want_K, cfg["padding_mode"],
-           None if masks is None else tuple((sig(a), sig(b)) for a, b in masks), cfg["no_photo"], cfg["no_smooth"])
+           None if masks is None else tuple((sig(a), sig(b)) for a, b in masks), cfg["no_photo"], cfg["no_smooth"], cfg["disparity"])
     plan = _PLAN_CACHE.get(key)
     if plan is None:
         if not poses.is_contiguous():
             # the plan would hold private contiguous copies: not reusable
             return ops.FusedLossPlan(tgt_pyr, src_pyr, depth_pyr, poses, K_ms, cfg["alpha"], cfg["photo_weights"], cfg["smooth_weights"],
                                      want_grad=need, want_grad_K=want_K, padding_mode=cfg["padding_mode"], masks=masks,
-                                     no_photo=cfg["no_photo"], no_smooth=cfg["no_smooth"])
+                                     no_photo=cfg["no_photo"], no_smooth=cfg["no_smooth"], disparity=cfg["disparity"])
         if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
             _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
         plan = ops.FusedLossPlan(tgt_pyr, src_pyr, depth_pyr, poses, K_ms, cfg["alpha"], cfg["photo_weights"], cfg["smooth_weights"],
                                  want_grad=need, want_grad_K=want_K, padding_mode=cfg["padding_mode"], masks=masks,
-                                 no_photo=cfg["no_photo"], no_smooth=cfg["no_smooth"])
+                                 no_photo=cfg["no_photo"], no_smooth=cfg["no_smooth"], disparity=cfg["disparity"])
         _PLAN_CACHE[key] = plan
     else:
         plan.refresh_intrinsics(K_ms)            # same buffer, possibly new values
@@ -143,15 +143,18 @@ class _FusedLoss(torch.autograd.Function):
 def geonet_loss(tgt_pyr: Sequence[torch.Tensor], src_pyr: Sequence[torch.Tensor], depth_pyr: Sequence[torch.Tensor],
                 poses: torch.Tensor, K_ms: torch.Tensor, alpha: float = 0.85, loss_weight_rigid_warp: float = 1.0,
                 loss_weight_disparity_smooth: float = 0.5, padding_mode: str = "zeros", masks=None,
-                no_photo: bool = False, no_smooth: bool = False):
+                no_photo: bool = False, no_smooth: bool = False, disparity: bool = False):
     """Everything GeoNetModel.build_rigid_warp_flow + build_losses compute (models/baseline.py:867-970,
     1115-1161) in one fused pass.  tgt_pyr[s] (B,3,h,w), src_pyr[s] (S*B,3,h,w) source-major (any strides, e.g.
     the reference's NHWC views permuted back), depth_pyr[s] (B*(1+S),h,w), poses (B,S,6), K_ms (B,scales,3,3).
+    disparity=True: depth_pyr holds the networks' DISPARITIES; the kernel forms depth = 1/disp itself (baseline.py:835) and
+    the gradients come back with respect to the disparities (section 8(f2): saves the caller two element-wise passes).
     Returns (loss_total, detail) with detail = [total, rigid_warp, disp_smooth, then per scale mean fwd err,
     mean bwd err, smooth_loss]."""
     ns = len(tgt_pyr)
     S = poses.shape[1]
     cfg = dict(ns=ns, alpha=float(alpha), padding_mode=padding_mode, masks=masks, no_photo=no_photo, no_smooth=no_smooth,
+               disparity=bool(disparity),
                photo_weights=[loss_weight_rigid_warp * S / 2] * ns,
                smooth_weights=[loss_weight_disparity_smooth / 2 ** s for s in range(ns)])
     return _FusedLoss.apply(cfg, poses, K_ms, *depth_pyr, *tgt_pyr, *src_pyr)
@@ -168,7 +171,7 @@ def photometric_reconstruction_loss(tgt_pyr, src_pyr, intrinsics_ms, depth_pyr, 
 
 
 def geonet_loss_from_frames(tgt_u8, src_u8, depth_pyr, poses, intrinsics, alpha: float = 0.85, loss_weight_rigid_warp: float = 1.0,
-                            loss_weight_disparity_smooth: float = 0.5):
+                            loss_weight_disparity_smooth: float = 0.5, disparity: bool = False):
     """The step as the reference's trainer sees it (models/baseline.py:746-792 + 867-986 + 1115-1161): uint8 frames as the
     DataLoader delivers them -- tgt_u8 (B,3,H,W), src_u8 (B,3*S,H,W) -- are normalised and turned into pyramids on the
     device (one kernel each), intrinsics (B,3,3) into their per-scale copies, then the fused loss runs.
@@ -203,4 +206,5 @@ def geonet_loss_from_frames(tgt_u8, src_u8, depth_pyr, poses, intrinsics, alpha:
     torch.mul(intrinsics.float().unsqueeze(0), M, out=K_sb)
     K_sb += E
     K_ms = K_sb.permute(1, 0, 2, 3)                 # (B,scales,3,3) view; K_ms[:, s] is contiguous
-    return geonet_loss(tgt_pyr, src_pyr, depth_pyr, poses, K_ms, alpha, loss_weight_rigid_warp, loss_weight_disparity_smooth)
+    return geonet_loss(tgt_pyr, src_pyr, depth_pyr, poses, K_ms, alpha, loss_weight_rigid_warp, loss_weight_disparity_smooth,
+                       disparity=disparity)

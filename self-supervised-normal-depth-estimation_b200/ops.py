@@ -69,7 +69,7 @@ class FusedLossPlan:
                  poses: torch.Tensor, K_ms: torch.Tensor, alpha: float = 0.85, photo_weights: Optional[Sequence[float]] = None,
                  smooth_weights: Optional[Sequence[float]] = None, want_grad: bool = True, want_grad_K: bool = False,
                  padding_mode: str = "zeros", masks: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]] = None,
-                 want_maps: bool = False, no_photo: bool = False, no_smooth: bool = False):
+                 want_maps: bool = False, no_photo: bool = False, no_smooth: bool = False, disparity: bool = False):
         ns = len(tgt_pyr)
         _require_cuda(poses, K_ms, *tgt_pyr, *src_pyr, *depth_pyr)
         B, S = poses.shape[0], poses.shape[1]
@@ -114,7 +114,8 @@ class FusedLossPlan:
                 self.maps.append(m)
             scales.append(sc)
         flags = (_abi.SNDE_LOSS_GRAD if want_grad else 0) | (_abi.SNDE_LOSS_GRAD_K if want_grad_K else 0) \
-            | (_abi.SNDE_LOSS_NO_PHOTO if no_photo else 0) | (_abi.SNDE_LOSS_NO_SMOOTH if no_smooth else 0)
+            | (_abi.SNDE_LOSS_NO_PHOTO if no_photo else 0) | (_abi.SNDE_LOSS_NO_SMOOTH if no_smooth else 0) \
+            | (_abi.SNDE_LOSS_DISPARITY if disparity else 0)
         pad = {"zeros": _abi.SNDE_PAD_ZEROS, "border": _abi.SNDE_PAD_BORDER}[padding_mode]
         self.args = _abi.make_loss_args(B, S, float(alpha), flags, pad, self.poses.data_ptr(), scales, self.loss_out.data_ptr(),
                                         self.grad_poses.data_ptr() if want_grad else None,

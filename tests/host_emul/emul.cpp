@@ -39,10 +39,10 @@ void sync_on(SyncObj &s, int n) {
     while (s.gen == g) yield_to_scheduler();
 }
 
-template <bool GRAD, bool GRADK, bool EXTRA, bool FAST>
+template <bool GRAD, bool GRADK, bool EXTRA, bool FAST, bool DISP = false>
 void run_role(int who) {
     HostPair &w = g_pair;
-    if (who < 32) geo_role<GRAD, GRADK, EXTRA, FAST>(*w.p, w.task, who, *w.sm, 1);
+    if (who < 32) geo_role<GRAD, GRADK, EXTRA, FAST, DISP>(*w.p, w.task, who, *w.sm, 1);
     else ssim_role<GRAD, EXTRA>(*w.p, w.task, who, *w.sm, 1);
 }
 
@@ -54,6 +54,7 @@ void fiber_main(int who) {
         case 2: run_role<false, false, false, false>(who); break;
         case 3: run_role<true, true, true, false>(who); break;
         case 4: run_role<true, false, false, true>(who); break;
+        case 6: run_role<true, false, false, true, true>(who); break;
         default: run_role<true, false, false, false>(who); break;
     }
     w.done[who] = true;
@@ -119,7 +120,9 @@ extern "C" __attribute__((visibility("default"))) int emul_loss_fwdbwd(const Snd
         extra = extra || in.mask_fwd.ptr || in.mask_bwd.ptr || in.warped_fwd.ptr || in.warped_bwd.ptr || in.err_fwd.ptr || in.err_bwd.ptr;
         fast = fast && d.sc[s].fast;
     }
-    const int variant = !grad ? (extra ? 0 : (fast ? 1 : 2)) : (extra ? 3 : (fast ? 4 : 5));
+    const bool disp = (a->flags & SNDE_LOSS_DISPARITY) != 0;
+    if (disp && !(grad && fast && !extra)) extra = true;
+    const int variant = !grad ? (extra ? 0 : (fast ? 1 : 2)) : (extra ? 3 : (disp ? 6 : (fast ? 4 : 5)));
     PairSmem *sm = new PairSmem;
     for (int64_t t = 0; t < tasks; ++t) {
         memset(sm, 0xff, sizeof(PairSmem));    // NaN-fill: catches reads of unwritten shared memory

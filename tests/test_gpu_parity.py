@@ -461,3 +461,23 @@ def test_geonet_loss_from_frames_equals_reference_prep_then_loss():
     for a, b in zip(depth, depth2):
         assert rel_l2(a.grad.cpu().numpy(), b.grad.cpu().numpy()) < 1e-5
     assert rel_l2(poses.grad.cpu().numpy(), poses2.grad.cpu().numpy()) < 1e-5
+
+
+def test_disparity_input_matches_autograd_through_reciprocal():
+    """section 8(f2): disparity=True == (depth = 1/disp in torch) -> fused loss -> autograd back to the disparity"""
+    from snde_b200.loss_functions import geonet_loss
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**CASES["small_smooth"]).to(DEV)
+    disp0 = [1.0 / d for d in inp.depth_pyr]
+    disp_a = [x.clone().requires_grad_(True) for x in disp0]
+    poses_a = inp.poses.clone().requires_grad_(True)
+    ta, _ = geonet_loss(inp.tgt_pyr, inp.src_pyr, [1.0 / x for x in disp_a], poses_a, inp.K_ms)       # the reference's way
+    ta.backward()
+    disp_b = [x.clone().requires_grad_(True) for x in disp0]
+    poses_b = inp.poses.clone().requires_grad_(True)
+    tb, _ = geonet_loss(inp.tgt_pyr, inp.src_pyr, disp_b, poses_b, inp.K_ms, disparity=True)
+    tb.backward()
+    assert abs(ta.item() - tb.item()) <= 1e-7 * abs(ta.item())
+    for a, b in zip(disp_a, disp_b):
+        assert torch.equal(a.grad, b.grad)
+    assert rel_l2(poses_b.grad.cpu().numpy(), poses_a.grad.cpu().numpy()) < 1e-6

@@ -164,3 +164,25 @@ def test_emulated_odd_sizes(oracle32):
     assert e1["variant"] == 5
     for s in range(inp.num_scales):
         assert np.array_equal(e1["grad_depth"][s], e["grad_depth"][s])
+
+
+def test_emulated_disparity_input():
+    """SNDE_LOSS_DISPARITY: depth = 1/disp inside the strip program, gradient w.r.t. the disparity = -(g * depth^2)"""
+    import torch
+    from snde_b200.synthetic import LossInputs, make_inputs
+    inp = make_inputs(**CASES["small_smooth"])
+    disp = [1.0 / d for d in inp.depth_pyr]
+    depth = [1.0 / x for x in disp]                                  # what the reference forms (baseline.py:835)
+    a = emul.run_loss(LossInputs(inp.tgt_pyr, inp.src_pyr, depth, inp.poses, inp.K, inp.K_ms), flags=1)
+    b = emul.run_loss(LossInputs(inp.tgt_pyr, inp.src_pyr, disp, inp.poses, inp.K, inp.K_ms), flags=1 | 16)
+    assert a["loss_total"] == b["loss_total"]
+    for s in range(inp.num_scales):
+        d = depth[s].numpy()
+        want = (-a["grad_depth"][s]) * (d * d)
+        assert np.array_equal(b["grad_depth"][s], want.astype(np.float32))
+    assert np.array_equal(a["grad_poses"], b["grad_poses"])
+    assert b["variant"] == 6
+    c = emul.run_loss(LossInputs(inp.tgt_pyr, inp.src_pyr, disp, inp.poses, inp.K, inp.K_ms), flags=3 | 16)    # general instance, flag at run time
+    assert c["variant"] == 3
+    for s in range(inp.num_scales):
+        assert np.array_equal(c["grad_depth"][s], b["grad_depth"][s])
