@@ -1,2 +1,1 @@
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3
-python bench.py --steps 500 --warmup 20 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print("default lib", round(d["ms_per_step"]*1e3,1), "us  loss", d["config"]["loss_check"])'

@@ -481,3 +481,29 @@ def test_disparity_input_matches_autograd_through_reciprocal():
     for a, b in zip(disp_a, disp_b):
         assert torch.equal(a.grad, b.grad)
     assert rel_l2(poses_b.grad.cpu().numpy(), poses_a.grad.cpu().numpy()) < 1e-6
+
+
+def test_odd_sizes_and_unaligned_views_on_hardware(oracle32):
+    """odd width / height and a depth slice with an odd storage offset: the generic instances (4-byte asynchronous row
+    copies, scalar stores) on the GPU, against the oracle"""
+    from oracle.compose import geonet_loss
+    from snde_b200 import ops
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(B=2, S=2, H=37, W=67, num_scales=2, seed=11, smooth=True, motion="large")
+    d = inp.to(DEV)
+    # depth maps as slices of larger buffers with an odd element offset (the reference slices depth[s][:B], baseline.py:905)
+    depth = []
+    for t in d.depth_pyr:
+        big = torch.zeros(t.numel() + 3, device=DEV)
+        big[3:] = t.reshape(-1)
+        depth.append(big[3:].view(t.shape))
+    o = geonet_loss(oracle32, **oracle_inputs(inp))
+    for want_K in (False, True):
+        plan = ops.FusedLossPlan(d.tgt_pyr, d.src_pyr, depth, d.poses, d.K_ms, want_grad=True, want_grad_K=want_K)
+        plan.run()
+        torch.cuda.synchronize()
+        assert abs(plan.loss_out[0].item() - o["loss_total"]) < 1e-5 * abs(o["loss_total"])
+        for s in range(inp.num_scales):
+            ok, rel, frac = close_except_flips(plan.grad_depth[s].cpu().numpy(), o["grad_depth"][s], max_flip_frac=2e-3)
+            assert ok, (s, rel, frac)
+        assert rel_l2(plan.grad_poses.cpu().numpy(), o["grad_poses"]) < 1e-4
