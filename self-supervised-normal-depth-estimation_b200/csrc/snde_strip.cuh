@@ -185,6 +185,9 @@ SNDE_STRIP_FN F2 ldg2(const float *p) { const float2 v = __ldg(reinterpret_cast<
 // every use, so that base[int_offset] costs one IMAD.WIDE instead of a four-instruction 64-bit add-and-shift.
 #define SNDE_PIN_PTR(p) asm volatile("" : "+l"(p))
 #define SNDE_SCHED_FENCE() asm volatile("" ::: "memory")
+// keep a per-task float in a register (the compiler would re-load it from the constant bank through two dependent
+// LDCs at every use)
+#define SNDE_PIN_F32(x) asm volatile("" : "+f"(x))
 #else
 // host emulation (tests/host_emul/emul.cpp): 64 fibers per pair; exchange slots are double-buffered
 float *host_slots(int who, int parity);             // 64 floats per fiber and parity
@@ -251,6 +254,7 @@ SNDE_STRIP_FN void row_copy_wait() {}
 SNDE_STRIP_FN F2 ldg2(const float *p) { return F2{p[0], p[1]}; }
 #define SNDE_PIN_PTR(p) ((void)0)
 #define SNDE_SCHED_FENCE() ((void)0)
+#define SNDE_PIN_F32(x) ((void)0)
 #endif
 
 // horizontal 3-sums of one row for the lane's two columns (left column = left neighbour + (a + b), right column =
@@ -327,7 +331,8 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
     StripTask T;
     decode_task(p, task, lane, T);
     const DevScale &sc = p.sc[T.scale];
-    const float alpha = p.alpha, oma = p.oma, g1 = p.oma * sc.gphoto;
+    float alpha = p.alpha, oma = p.oma, g1 = p.oma * sc.gphoto;
+    SNDE_PIN_F32(alpha); SNDE_PIN_F32(oma); SNDE_PIN_F32(g1);
     float ngSm[2];            // -dL/dS = 0.5*alpha*gphoto where the column takes part in phase B, else 0
 #pragma unroll
     for (int q = 0; q < 2; ++q) ngSm[q] = T.colB[q] ? -(-0.5f * p.alpha * sc.gphoto) : 0.f;
