@@ -1,5 +1,5 @@
-// snde_fused.cu -- the fused loss (matrix prep, tile kernel, finalize) and the small host helpers of the C ABI
-// declared in include/snde.h.  Built with -fmad=true: the tile program states its exact-order arithmetic explicitly
+// snde_fused.cu -- the fused loss (matrix prep, strip kernel, finalize) and the small host helpers of the C ABI
+// declared in include/snde.h.  Built with -fmad=true: the strip program states its exact-order arithmetic explicitly
 // (fmaf / SNDE_X* ops in snde_math.cuh), everything else may be contracted.  See build.py.
 #include <cuda_runtime.h>
 #include <stdio.h>

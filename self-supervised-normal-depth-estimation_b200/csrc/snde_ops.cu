@@ -265,7 +265,7 @@ extern "C" int snde_bilinear_sampler_bwd(int N, int C, int hs, int ws, SndeImage
 
 // ---- image_similarity / DSSIM (materialising, reference-signature version) ----
 // one thread per (n, y, x); 5x5 neighbourhoods come straight from global memory (L1/L2 resident).
-// The fused tile kernel is the fast path; this one exists so the reference's own call sequence runs.
+// The fused strip kernel is the fast path; this one exists so the reference's own call sequence runs.
 __device__ __forceinline__ float img_or_zero(const LImage &im, long long n, int c, int y, int x, int h, int w) {
     return (y >= 0 && y < h && x >= 0 && x < w) ? ld_img(im, n, c, y, x) : 0.f;
 }

@@ -123,7 +123,7 @@ class FusedLossPlan:
         self._fn = _abi.lib().snde_loss_fwdbwd
         self._ref = C.byref(self.args)
         self.num_tiles = int(_abi.lib().snde_loss_num_tiles(self._ref))
-        self.kernel_launches = 3   # prep, tile, finalize (+ one memset node)
+        self.kernel_launches = 3   # prep, strip, finalize (+ one memset node)
 
     def refresh_intrinsics(self, K_ms: torch.Tensor) -> None:
         """Re-copy the per-scale intrinsics (the plan keeps contiguous (B,3,3) copies of the strided K_ms[:, s])."""
