@@ -245,7 +245,7 @@ def main():
     out_host = [torch.empty_like(t).pin_memory() for t in h_dep] + [torch.empty_like(host.poses).pin_memory(), torch.empty(3 + 3 * cfg["num_scales"]).pin_memory()]
     d2h = sum(t.numel() * 4 for t in out_host)
 
-    # Two device input sets and three streams: the H2D copy of step i+1, the fused loss of step i and the D2H read of
+    # Three device input sets and three streams: the H2D copy of step i+1, the fused loss of step i and the D2H read of
     # step i-1 overlap (every byte still moves every step, inside the timed region).
     NBUF = 2
     dev_in = [dict(tgt=torch.empty_like(h_tgt, device=dev), src=torch.empty_like(h_src, device=dev),
@@ -254,7 +254,11 @@ def main():
     s_h2d, s_run, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     ev_in = [torch.cuda.Event() for _ in range(NBUF)]      # inputs of set j are on the device
     ev_free = [torch.cuda.Event() for _ in range(NBUF)]    # set j has been consumed
-    ev_out = torch.cuda.Event()
+    ev_res = [torch.cuda.Event() for _ in range(NBUF)]     # results of set j are in their staging buffers
+    ev_read = [torch.cuda.Event() for _ in range(NBUF)]    # ... and have been read back
+    # results leave through persistent device staging buffers: the autograd-allocated gradient tensors are released in
+    # stream order on the compute stream (no cross-stream allocator traffic), the D2H copy runs on its own stream
+    stage = [[torch.empty_like(t, device=dev) for t in out_host] for _ in range(NBUF)]
     step_no = [0]
 
     def e2e_step():
@@ -272,21 +276,21 @@ def main():
             ev_in[j].record(s_h2d)
         with torch.cuda.stream(s_run):
             s_run.wait_event(ev_in[j])
-            s_run.wait_event(ev_out)                           # the previous step's results have left their buffers
             dep = [t.detach().requires_grad_(True) for t in d["dep"]]
             poses = d["poses"].detach().requires_grad_(True)
             total, detail = geonet_loss_from_frames(d["tgt"], d["src"], dep, poses, d["K"])
             total.backward()
-            grads = [t.grad for t in dep] + [poses.grad, detail]
+            s_run.wait_event(ev_read[j])                       # the staging set of two steps ago has been read back
+            torch._foreach_copy_(stage[j], [t.grad for t in dep] + [poses.grad, detail])
             ev_free[j].record(s_run)
+            ev_res[j].record(s_run)
         with torch.cuda.stream(s_d2h):
-            s_d2h.wait_event(ev_free[j])
-            for o, g in zip(out_host, grads):
+            s_d2h.wait_event(ev_res[j])
+            for o, g in zip(out_host, stage[j]):
                 o.copy_(g, non_blocking=True)
-                g.record_stream(s_d2h)
-            ev_out.record(s_d2h)
+            ev_read[j].record(s_d2h)
 
-    e2e_steps = 0 if args.no_e2e else max(5, min(args.steps, 30))
+    e2e_steps = 0 if args.no_e2e else max(5, min(args.steps, 100))
     for _ in range(3 if e2e_steps else 0):
         e2e_step()
     barrier()
