@@ -35,3 +35,14 @@ def d2h():
 for name, fn in (("H2D 42.5 MB", h2d), ("compute (public API, device inputs)", compute), ("D2H 27 MB", d2h)):
     gpu_ms, host_ms = timed(fn)
     print(f"{name:40s} gpu {gpu_ms:.3f} ms/step   host issue {host_ms:.3f} ms/step")
+
+if "--profile" in sys.argv:
+    import cProfile, pstats
+    pr = cProfile.Profile()
+    for _ in range(5): compute()
+    torch.cuda.synchronize()
+    pr.enable()
+    for _ in range(50): compute()
+    pr.disable()
+    torch.cuda.synchronize()
+    st = pstats.Stats(pr); st.sort_stats("cumulative").print_stats(28)
