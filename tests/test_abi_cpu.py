@@ -134,3 +134,19 @@ def test_product_never_imports_oracle():
         txt = f.read_text()
         assert not re.search(r"^\s*(from|import)\s+(oracle|emul|tests)\b", txt, re.M), f
         assert "snde_oracle" not in txt and "host_emul/emul.cpp" not in txt.replace("tests/host_emul/emul.cpp", ""), f
+
+
+def test_hot_kernel_instance_has_no_register_spills(abi):
+    """The lean <GRAD, FAST> strip kernel sits at the 168-register limit of 3 CTAs x 128 threads per SM; a handful of
+    spilled registers in either warp's loop costs ~20 % of the run time (profiles/README.md).  ptxas' report of the
+    in-tree build must show none."""
+    from snde_b200 import build
+    log_path = os.path.join(os.path.dirname(abi.LIB_PATH), "build", os.path.basename(abi.LIB_PATH).replace(".so", "_") + "snde_fused.ptxas.log")
+    if not os.path.exists(log_path):
+        build.build(force=True)
+    log = open(log_path).read()
+    m = re.search(r"Function properties for _Z17loss_strip_kernelILb1ELb0ELb0ELb1ELb0EE\w+\s*\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\s*\n[^\n]*Used (\d+) registers", log)
+    assert m, "lean kernel instance not found in the ptxas report"
+    stack, st, ld, regs = map(int, m.groups())
+    assert st == 0 and ld == 0, (st, ld)
+    assert regs <= 168
