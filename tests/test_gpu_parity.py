@@ -507,3 +507,29 @@ def test_odd_sizes_and_unaligned_views_on_hardware(oracle32):
             ok, rel, frac = close_except_flips(plan.grad_depth[s].cpu().numpy(), o["grad_depth"][s], max_flip_frac=2e-3)
             assert ok, (s, rel, frac)
         assert rel_l2(plan.grad_poses.cpu().numpy(), o["grad_poses"]) < 1e-4
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_shapes_on_hardware(oracle32, seed):
+    """random small shapes (w below / just over a strip, h below a segment, S from 1 to 4, odd sizes) against the oracle"""
+    from oracle.compose import geonet_loss
+    from snde_b200 import ops
+    from snde_b200.synthetic import make_inputs
+    rng = np.random.default_rng(200 + seed)
+    B, S = int(rng.integers(1, 4)), int(rng.integers(1, 5))
+    ns = int(rng.integers(1, 4))
+    H = int(rng.integers(8, 90)); W = int(rng.choice([16, 58, 60, 61, 62, 64, 66, 118, 121, 124, 200]))
+    H = max(H, 4 * 2 ** (ns - 1))
+    inp = make_inputs(B=B, S=S, H=H, W=W, num_scales=ns, seed=seed, smooth=True, motion=("large" if seed % 2 else "small"))
+    d = inp.to(DEV)
+    plan = ops.FusedLossPlan(d.tgt_pyr, d.src_pyr, d.depth_pyr, d.poses, d.K_ms, want_grad=True, want_grad_K=bool(seed % 3 == 0))
+    plan.run()
+    torch.cuda.synchronize()
+    o = geonet_loss(oracle32, **oracle_inputs(inp))
+    assert abs(plan.loss_out[0].item() - o["loss_total"]) < 1e-5 * abs(o["loss_total"]), (B, S, H, W, ns)
+    for s in range(inp.num_scales):
+        g = plan.grad_depth[s].cpu().numpy()
+        assert not np.isnan(g).any()
+        ok, rel, frac = close_except_flips(g, o["grad_depth"][s], max_flip_frac=5e-3)
+        assert ok, (s, rel, frac, (B, S, H, W, ns))
+    assert rel_l2(plan.grad_poses.cpu().numpy(), o["grad_poses"]) < 2e-4

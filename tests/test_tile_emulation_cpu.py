@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import emul
-from cases import CASES, SMALL, load_golden, oracle_inputs, rel_l2
+from cases import CASES, SMALL, close_except_flips, load_golden, oracle_inputs, rel_l2
 
 
 def _nhwc(a):
@@ -186,3 +186,27 @@ def test_emulated_disparity_input():
     assert c["variant"] == 3
     for s in range(inp.num_scales):
         assert np.array_equal(c["grad_depth"][s], b["grad_depth"][s])
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_emulated_random_shapes(oracle32, seed):
+    """random small shapes (strip / segment / halo corner cases: w < 60, w just over a strip, h below a segment,
+    S from 1 to 4, odd sizes, short segments) against the oracle"""
+    from oracle.compose import geonet_loss
+    from snde_b200.synthetic import make_inputs
+    rng = np.random.default_rng(100 + seed)
+    B, S = int(rng.integers(1, 3)), int(rng.integers(1, 5))
+    ns = int(rng.integers(1, 3))
+    H = int(rng.integers(6, 40)) * (2 ** (ns - 1)) // (2 ** (ns - 1)) + int(rng.integers(0, 2))
+    W = int(rng.choice([8, 30, 58, 60, 61, 62, 64, 66, 118, 121, 124]))
+    H = max(H, 4 * 2 ** (ns - 1)); W = max(W, 4 * 2 ** (ns - 1))
+    inp = make_inputs(B=B, S=S, H=H, W=W, num_scales=ns, seed=seed, smooth=True, motion=("large" if seed % 2 else "small"))
+    seg = int(rng.choice([0, 4, 7, 16]))
+    e = emul.run_loss(inp, flags=int(rng.choice([1, 3])), seg_rows=seg, fine_rows=int(rng.choice([0, 3])), fine_permille=400)
+    o = geonet_loss(oracle32, **oracle_inputs(inp))
+    assert abs(e["loss_total"] - o["loss_total"]) < 2e-6 * abs(o["loss_total"]), (B, S, H, W, ns, seg)
+    for s in range(inp.num_scales):
+        assert not np.isnan(e["grad_depth"][s]).any()
+        ok, rel, frac = close_except_flips(e["grad_depth"][s], o["grad_depth"][s], max_flip_frac=5e-3)
+        assert ok, (s, rel, frac, (B, S, H, W, ns, seg))
+    assert rel_l2(e["grad_poses"], o["grad_poses"]) < 2e-4
