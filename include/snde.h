@@ -163,6 +163,16 @@ SNDE_API int snde_bilinear_sampler_bwd(int N, int C, int hs, int ws, SndeImage i
                               int add_grid, const float *xtab, const float *ytab, int padding_mode,
                               const float *gout, float *gcoords, SndeImageOut gimg, void *stream);
 
+/* Deterministic variant of the image-gradient scatter of snde_bilinear_sampler_bwd (the float atomics of the default
+ * mode land in an arbitrary order, so its last bits vary from run to run).  Two passes: every contribution w*g is
+ * added as a 64-bit fixed-point integer -- integer addition is associative, the sum does not depend on the order --
+ * with a scale derived on the device from max|gout| (quantum = 2^-38 of it, room for 2^24 contributions per pixel);
+ * the second pass converts the sums and adds them to gimg.  scratch: device, (N*C*hs*ws + 1) int64, overwritten.
+ * gcoords is written exactly as by the default mode. */
+SNDE_API int snde_bilinear_sampler_bwd_deterministic(int N, int C, int hs, int ws, SndeImage img, int ht, int wt, const float *coords,
+                                            int add_grid, const float *xtab, const float *ytab, int padding_mode,
+                                            const float *gout, float *gcoords, SndeImageOut gimg, long long *scratch, void *stream);
+
 /* image_similarity(alpha,x,y) = alpha*DSSIM(x,y) + (1-alpha)*|x-y| (loss_functions.py:4-6, utils_edited.py:121-141).
  * alpha = 1 gives DSSIM.  x,y (N,3,h,w) strided -> err (N,h,w,3) contiguous NHWC */
 SNDE_API int snde_image_similarity_fwd(int N, int h, int w, float alpha, SndeImage x, SndeImage y, float *err, void *stream);

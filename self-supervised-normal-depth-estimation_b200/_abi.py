@@ -75,6 +75,9 @@ SIGNATURES = {
     "snde_bilinear_sampler_bwd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, SndeImage, C.c_int, C.c_int, C.c_void_p,
                                             C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, SndeImage,
                                             C.c_void_p]),
+    "snde_bilinear_sampler_bwd_deterministic": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, SndeImage, C.c_int, C.c_int, C.c_void_p,
+                                                          C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, SndeImage,
+                                                          C.c_void_p, C.c_void_p]),
     "snde_image_similarity_fwd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, SndeImage, SndeImage, C.c_void_p, C.c_void_p]),
     "snde_image_similarity_bwd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, SndeImage, SndeImage, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p]),

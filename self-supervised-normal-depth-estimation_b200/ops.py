@@ -208,6 +208,11 @@ def sampler_fwd(imgs_nhwc, coords, add_grid: bool, padding_mode: str, want_valid
     return out, valid
 
 
+# image-gradient scatter mode of bilinear_sampler / flow_warp / inverse_warp backward: False = float atomics (fast, last bits vary
+# from run to run), True = the deterministic two-pass mode (64-bit fixed-point accumulation, bit-identical every run)
+DETERMINISTIC_IMAGE_GRADIENT = False
+
+
 def sampler_bwd(imgs_nhwc, coords, add_grid: bool, padding_mode: str, gout, want_gimg: bool):
     N, hs, ws, Cc = imgs_nhwc.shape
     _, ht, wt, _ = coords.shape
@@ -218,6 +223,12 @@ def sampler_bwd(imgs_nhwc, coords, add_grid: bool, padding_mode: str, gout, want
     xt = grid_table(wt, dev).data_ptr() if add_grid else None
     yt = grid_table(ht, dev).data_ptr() if add_grid else None
     gview = img_nhwc(gimg) if want_gimg else _abi.SndeImage()
+    if want_gimg and DETERMINISTIC_IMAGE_GRADIENT:
+        scratch = torch.empty(N * Cc * hs * ws + 1, dtype=torch.int64, device=dev)
+        _abi.check(_abi.lib().snde_bilinear_sampler_bwd_deterministic(N, Cc, hs, ws, img_nhwc(imgs_nhwc), ht, wt, coords.data_ptr(),
+                                                                       int(add_grid), xt, yt, _pad(padding_mode), gout.data_ptr(),
+                                                                       gcoords.data_ptr(), gview, scratch.data_ptr(), _stream()))
+        return gcoords, gimg
     _abi.check(_abi.lib().snde_bilinear_sampler_bwd(N, Cc, hs, ws, img_nhwc(imgs_nhwc), ht, wt, coords.data_ptr(), int(add_grid),
                                                      xt, yt, _pad(padding_mode), gout.data_ptr(), gcoords.data_ptr(), gview,
                                                      _stream()))

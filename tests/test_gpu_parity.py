@@ -533,3 +533,40 @@ def test_random_shapes_on_hardware(oracle32, seed):
         ok, rel, frac = close_except_flips(g, o["grad_depth"][s], max_flip_frac=5e-3)
         assert ok, (s, rel, frac, (B, S, H, W, ns))
     assert rel_l2(plan.grad_poses.cpu().numpy(), o["grad_poses"]) < 2e-4
+
+
+def test_deterministic_image_gradient_mode():
+    """the optional two-pass image-gradient scatter: bit-identical from run to run, equal to the atomic mode up to the
+    fp32 summation-order noise, and to the reference's gradient (golden kats)"""
+    from snde_b200 import ops
+    from snde_b200.utils_edited import bilinear_sampler
+    k = load_golden("kats")
+    def run():
+        imgs = _t(k["bs_img"]).requires_grad_(True)
+        coords = _t(k["bs_coords"]).requires_grad_(True)
+        bilinear_sampler(imgs, coords).backward(_t(k["bs_gout"]))
+        return imgs.grad.clone(), coords.grad.clone()
+    g_atomic, c_atomic = run()
+    ops.DETERMINISTIC_IMAGE_GRADIENT = True
+    try:
+        g1, c1 = run()
+        g2, c2 = run()
+        # a bigger, collision-heavy case: many output pixels hit the same few image pixels
+        gen = torch.Generator().manual_seed(5)
+        img = torch.rand(2, 16, 16, 3, generator=gen).to(DEV).requires_grad_(True)
+        crd = (torch.rand(2, 256, 256, 2, generator=gen) * 14.9).to(DEV)
+        gout = torch.randn(2, 256, 256, 3, generator=gen).to(DEV) * 1e-6
+        outs = []
+        for _ in range(3):
+            img.grad = None
+            bilinear_sampler(img, crd).backward(gout)
+            outs.append(img.grad.clone())
+    finally:
+        ops.DETERMINISTIC_IMAGE_GRADIENT = False
+    assert torch.equal(g1, g2) and torch.equal(c1, c_atomic) and torch.equal(c2, c_atomic)
+    assert rel_l2(g1.cpu().numpy(), k["bs_gimg"]) < 1e-5
+    assert rel_l2(g1.cpu().numpy(), g_atomic.cpu().numpy()) < 1e-6
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    img.grad = None
+    bilinear_sampler(img, crd).backward(gout)                   # atomic mode on the same inputs
+    assert rel_l2(outs[0].cpu().numpy(), img.grad.cpu().numpy()) < 1e-5
