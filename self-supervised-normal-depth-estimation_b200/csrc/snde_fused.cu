@@ -208,7 +208,8 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
         return SNDE_OK;
     };
     // EXTRA variants honour masks / warped+error outputs / border padding / intrinsics gradients; FAST ones need planar,
-    // aligned tensors at every scale.  The lean fast one is the hot path.
+    // aligned tensors at every scale (the optional mask / output tensors keep their own strides).  The lean fast one is
+    // the hot path.
     bool extra = gradk || a->padding_mode != SNDE_PAD_ZEROS, fast = true;
     const bool disp = (a->flags & SNDE_LOSS_DISPARITY) != 0;
     for (int s = 0; s < ns; ++s) {
@@ -221,7 +222,7 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     if (!grad) {
         if (extra) rc = launch(loss_strip_kernel<false, false, true, false>, 0);
         else rc = fast ? launch(loss_strip_kernel<false, false, false, true>, 1) : launch(loss_strip_kernel<false, false, false, false>, 2);
-    } else if (extra) rc = launch(loss_strip_kernel<true, true, true, false>, 3);
+    } else if (extra) rc = fast ? launch(loss_strip_kernel<true, true, true, true>, 7) : launch(loss_strip_kernel<true, true, true, false>, 3);
     else if (disp) rc = launch(loss_strip_kernel<true, false, false, true, true>, 6);
     else rc = fast ? launch(loss_strip_kernel<true, false, false, true>, 4) : launch(loss_strip_kernel<true, false, false, false>, 5);
     if (rc) return rc;

@@ -55,6 +55,7 @@ void fiber_main(int who) {
         case 3: run_role<true, true, true, false>(who); break;
         case 4: run_role<true, false, false, true>(who); break;
         case 6: run_role<true, false, false, true, true>(who); break;
+        case 7: run_role<true, true, true, true>(who); break;
         default: run_role<true, false, false, false>(who); break;
     }
     w.done[who] = true;
@@ -122,7 +123,7 @@ extern "C" __attribute__((visibility("default"))) int emul_loss_fwdbwd(const Snd
     }
     const bool disp = (a->flags & SNDE_LOSS_DISPARITY) != 0;
     if (disp && !(grad && fast && !extra)) extra = true;
-    const int variant = !grad ? (extra ? 0 : (fast ? 1 : 2)) : (extra ? 3 : (disp ? 6 : (fast ? 4 : 5)));
+    const int variant = !grad ? (extra ? 0 : (fast ? 1 : 2)) : (extra ? (fast ? 7 : 3) : (disp ? 6 : (fast ? 4 : 5)));
     PairSmem *sm = new PairSmem;
     for (int64_t t = 0; t < tasks; ++t) {
         memset(sm, 0xff, sizeof(PairSmem));    // NaN-fill: catches reads of unwritten shared memory

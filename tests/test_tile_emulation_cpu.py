@@ -142,7 +142,7 @@ def test_emulated_variants_selected():
     inp = make_inputs(**CASES["small_smooth"])
     assert emul.run_loss(inp, flags=1)["variant"] == 4
     assert emul.run_loss(inp, flags=0)["variant"] == 1
-    assert emul.run_loss(inp, flags=3)["variant"] == 3
+    assert emul.run_loss(inp, flags=3)["variant"] == 7          # extras on planar inputs: general + FAST
     nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
     inp2 = LossInputs([nhwc(t) for t in inp.tgt_pyr], [nhwc(t) for t in inp.src_pyr], inp.depth_pyr, inp.poses, inp.K, inp.K_ms)
     assert emul.run_loss(inp2, flags=1)["variant"] == 5
@@ -154,7 +154,7 @@ def test_emulated_odd_sizes(oracle32):
     from snde_b200.synthetic import make_inputs
     inp = make_inputs(B=1, S=2, H=37, W=67, num_scales=2, seed=11, smooth=True, motion="large")
     e = emul.run_loss(inp, flags=3, seg_rows=16)
-    assert e["variant"] == 3
+    assert e["variant"] == 3                                    # odd width: generic strides
     o = geonet_loss(oracle32, **oracle_inputs(inp))
     assert abs(e["loss_total"] - o["loss_total"]) < 1e-6 * abs(o["loss_total"])
     for s in range(inp.num_scales):
@@ -183,7 +183,7 @@ def test_emulated_disparity_input():
     assert np.array_equal(a["grad_poses"], b["grad_poses"])
     assert b["variant"] == 6
     c = emul.run_loss(LossInputs(inp.tgt_pyr, inp.src_pyr, disp, inp.poses, inp.K, inp.K_ms), flags=3 | 16)    # general instance, flag at run time
-    assert c["variant"] == 3
+    assert c["variant"] == 7
     for s in range(inp.num_scales):
         assert np.array_equal(c["grad_depth"][s], b["grad_depth"][s])
 
