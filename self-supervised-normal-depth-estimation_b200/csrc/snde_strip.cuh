@@ -454,6 +454,7 @@ struct GeoLane {
     const StripTask &T;
     int lane;
     float xt[2];
+    P2 xtp;                   // (xt[0], xt[1])
     float mxs[2], mys[2], mxi[2], myi[2];      // 0/1: the horizontal / vertical smoothness pair starting at column q exists (.. and is an inner column)
     // owner
     const float *own_base; int own_sc, own_sh, own_sw;
@@ -510,75 +511,101 @@ struct GeoLane {
 
     // ---- phase A, first half: reproject the lane's two pixels of a row (in the image) and start the 24 gathers;
     //      the loads land in registers that nothing touches until the next step (software prefetch) ----
-    // wts[q] = {wx0, wx1, wy0, wy1} of pixel q (all zero for a pixel that samples nothing); border mode also needs the
-    // derivative gates, kept in dgate[q] = {dx, dy}.
-    SNDE_STRIP_FN void a_issue(float yt, const F2 d, float (&wts)[2][4], float (&dgate)[2][2], float (&taps)[24]) const {
+    // The two pixels run as packed fp32 pairs (lane-wise the scalar chain of reproject_fast / make_taps_valid).
+    // wts = {wx0, wx1, wy0, wy1}, each the pair over the two pixels (all zero for a pixel that samples nothing); border
+    // mode also needs the derivative gates, kept in dgate = {dx, dy}.
+    SNDE_STRIP_FN void a_issue(float yt, const F2 d, P2 (&wts)[4], P2 (&dgate)[2], float (&taps)[24]) const {
         // (lanes whose columns lie outside the image go through the same motions with zero weights on pixel 0)
-        const float dq[2] = {d.x, d.y};
         const float *ob = oth_base;
         SNDE_PIN_PTR(ob);
         const int h = T.h, w = T.w;
-        // Branch-free per pixel: an invalid pixel samples address 0 of the image with four zero weights.
+        ReprojP rp; reproject_fast_p(Ki, P, xtp, yt, p2f(d), rp);
+        P2 xp, yp; flow_coords_p(rp, xtp, yt, xp, yp);
+        const float xq[2] = {p2lo(xp), p2hi(xp)}, yq[2] = {p2lo(yp), p2hi(yp)};
+        int o00[2], dyo[2], dxo[2];
+        bool valid[2];
+        float wq[2][4], gq[2][2];
+        if (EXTRA && p.padding) {                  // border mode samples everywhere; the clamps are per pixel
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            Reproj rp; reproject_fast(Ki, P, xt[q], yt, dq[q], rp);
-            float x, yy; flow_coords(rp, xt[q], yt, x, yy);
-            Taps tp;
-            bool valid;
+            for (int q = 0; q < 2; ++q) {
+                Taps tp; make_taps(xq[q], yq[q], h, w, p.padding, tp);
+                valid[q] = T.in[q];
+                o00[q] = valid[q] ? tp.y0 * oth_sh + tp.x0 * (FAST ? 1 : oth_sw) : 0;
+                // border mode may have clamped both taps onto the same pixel: step 0
+                dyo[q] = (tp.y1 - tp.y0) * oth_sh; dxo[q] = (tp.x1 - tp.x0) * (FAST ? 1 : oth_sw);
+                wq[q][0] = tp.wx0; wq[q][1] = tp.wx1; wq[q][2] = tp.wy0; wq[q][3] = tp.wy1;
+                gq[q][0] = tp.dx; gq[q][1] = tp.dy;
+            }
+        } else {
             // Outside [0,w-1) x [0,h-1) the reference's clamped-corner weights cancel to zero (up to rounding
             // residue that grows with the distance from the image); the fused path writes the exact zero.
-            if (EXTRA && p.padding) { make_taps(x, yy, h, w, p.padding, tp); valid = true; }   // border mode samples everywhere
-            else { make_taps_valid(x, yy, tp); valid = tap_valid(x, yy, h, w, 0) != 0.f; }
-            valid = valid && T.in[q];
-            const int o00 = valid ? tp.y0 * oth_sh + tp.x0 * (FAST ? 1 : oth_sw) : 0;
-            // row / column steps to the second tap: constants, so that the four taps of a channel are two base addresses
-            // with immediate offsets (an invalid pixel reads the 2x2 block at the image origin; h, w >= 2 is checked on
-            // the host).  Border mode may have clamped both taps onto the same pixel: step 0.
-            int dyo = oth_sh, dxo = FAST ? 1 : oth_sw;
-            if (EXTRA && p.padding) { dyo = (tp.y1 - tp.y0) * oth_sh; dxo = (tp.x1 - tp.x0) * (FAST ? 1 : oth_sw); }
-            wts[q][0] = valid ? tp.wx0 : 0.f; wts[q][1] = valid ? tp.wx1 : 0.f; wts[q][2] = valid ? tp.wy0 : 0.f; wts[q][3] = valid ? tp.wy1 : 0.f;
-            dgate[q][0] = tp.dx; dgate[q][1] = tp.dy;
+            // Inside, none of the clamps is active: x0 = floor(x), weights (x0 + 1) - x and x - x0 (make_taps_valid).
+            const float x0f[2] = {floorf(xq[0]), floorf(xq[1])}, y0f[2] = {floorf(yq[0]), floorf(yq[1])};
+            const P2 x0p = p2(x0f[0], x0f[1]), y0p = p2(y0f[0], y0f[1]);
+            const P2 wx0 = p2sub(p2add(x0p, p2s(1.f)), xp), wx1 = p2sub(xp, x0p);
+            const P2 wy0 = p2sub(p2add(y0p, p2s(1.f)), yp), wy1 = p2sub(yp, y0p);
+            wq[0][0] = p2lo(wx0); wq[1][0] = p2hi(wx0); wq[0][1] = p2lo(wx1); wq[1][1] = p2hi(wx1);
+            wq[0][2] = p2lo(wy0); wq[1][2] = p2hi(wy0); wq[0][3] = p2lo(wy1); wq[1][3] = p2hi(wy1);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                valid[q] = tap_valid(xq[q], yq[q], h, w, 0) != 0.f && T.in[q];
+                // an invalid pixel reads the 2x2 block at the image origin (h, w >= 2 is checked on the host)
+                o00[q] = valid[q] ? (int)y0f[q] * oth_sh + (int)x0f[q] * (FAST ? 1 : oth_sw) : 0;
+                // row / column steps to the second tap: constants, so that the four taps of a channel are two base
+                // addresses with immediate offsets
+                dyo[q] = oth_sh; dxo[q] = FAST ? 1 : oth_sw;
+                gq[q][0] = gq[q][1] = 1.f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wts[i] = p2(valid[0] ? wq[0][i] : 0.f, valid[1] ? wq[1][i] : 0.f);
+        dgate[0] = p2(gq[0][0], gq[1][0]); dgate[1] = p2(gq[0][1], gq[1][1]);
+        // Branch-free per pixel: an invalid pixel samples address 0 of the image with four zero weights.  The two tap rows
+        // are walked channel by channel as pinned pointers (one 64-bit add per row and channel).
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float *q0 = ob + o00[q];
+            const float *q1 = q0 + dyo[q];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                const float *q0 = ob + (o00 + ch * oth_sc);
-                const float *q1 = q0 + dyo;
-                taps[12 * q + 4 * ch + 0] = ldg(q0);          // (y0, x0)
-                taps[12 * q + 4 * ch + 1] = ldg(q1);          // (y1, x0)
-                taps[12 * q + 4 * ch + 2] = ldg(q0 + dxo);    // (y0, x1)
-                taps[12 * q + 4 * ch + 3] = ldg(q1 + dxo);    // (y1, x1)
+                SNDE_PIN_PTR(q0); SNDE_PIN_PTR(q1);
+                taps[12 * q + 4 * ch + 0] = ldg(q0);             // (y0, x0)
+                taps[12 * q + 4 * ch + 1] = ldg(q1);             // (y1, x0)
+                taps[12 * q + 4 * ch + 2] = ldg(q0 + dxo[q]);    // (y0, x1)
+                taps[12 * q + 4 * ch + 3] = ldg(q1 + dxo[q]);    // (y1, x1)
+                q0 += oth_sc; q1 += oth_sc;
             }
         }
     }
 
     // ---- phase A, second half (one step later): blend the gathered taps -> warped row (+ tap derivatives) ----
-    SNDE_STRIP_FN void a_finish(int iy, const float (&wts)[2][4], const float (&dgate)[2][2], const float (&taps)[24], bool want_g,
+    SNDE_STRIP_FN void a_finish(int iy, const P2 (&wts)[4], const P2 (&dgate)[2], const float (&taps)[24], bool want_g,
                                 F2 (&y)[3], F2 (&g)[6]) const {
-        float yv[2][3], gv[2][6];
+        const P2 wx0 = wts[0], wx1 = wts[1], wy0 = wts[2], wy1 = wts[3];
+        const P2 w00 = p2mul(wx0, wy0), w01 = p2mul(wx0, wy1), w10 = p2mul(wx1, wy0), w11 = p2mul(wx1, wy1);
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const float wx0 = wts[q][0], wx1 = wts[q][1], wy0 = wts[q][2], wy1 = wts[q][3];
-            const float w00 = wx0 * wy0, w01 = wx0 * wy1, w10 = wx1 * wy0, w11 = wx1 * wy1;
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                const float i00 = taps[12 * q + 4 * ch + 0], i01 = taps[12 * q + 4 * ch + 1];
-                const float i10 = taps[12 * q + 4 * ch + 2], i11 = taps[12 * q + 4 * ch + 3];
-                yv[q][ch] = tap_blend_fma(w00, w01, w10, w11, i00, i01, i10, i11);
-                gv[q][2 * ch] = gv[q][2 * ch + 1] = 0.f;      // (dead unless want_g: the caller does not store them then)
-                if (GRAD && want_g) {
-                    gv[q][2 * ch] = fmaf(wy1, i11 - i01, wy0 * (i10 - i00));
-                    gv[q][2 * ch + 1] = fmaf(wx1, i11 - i10, wx0 * (i01 - i00));
-                    if (EXTRA) { gv[q][2 * ch] *= dgate[q][0]; gv[q][2 * ch + 1] *= dgate[q][1]; }
-                }
+        for (int ch = 0; ch < 3; ++ch) {
+            const P2 i00 = p2(taps[4 * ch + 0], taps[12 + 4 * ch + 0]), i01 = p2(taps[4 * ch + 1], taps[12 + 4 * ch + 1]);
+            const P2 i10 = p2(taps[4 * ch + 2], taps[12 + 4 * ch + 2]), i11 = p2(taps[4 * ch + 3], taps[12 + 4 * ch + 3]);
+            const P2 yv = p2fma(w11, i11, p2fma(w10, i10, p2fma(w01, i01, p2mul(w00, i00))));      // tap_blend_fma
+            y[ch] = f2p(yv);
+            g[2 * ch] = g[2 * ch + 1] = F2{0.f, 0.f};         // (dead unless want_g: the caller does not store them then)
+            if (GRAD && want_g) {
+                P2 gx = p2fma(wy1, p2sub(i11, i01), p2mul(wy0, p2sub(i10, i00)));
+                P2 gy = p2fma(wx1, p2sub(i11, i10), p2mul(wx0, p2sub(i01, i00)));
+                if (EXTRA) { gx = p2mul(gx, dgate[0]); gy = p2mul(gy, dgate[1]); }
+                g[2 * ch] = f2p(gx); g[2 * ch + 1] = f2p(gy);
             }
-            if (EXTRA && wout_base && T.colI[q] && iy >= T.y0 && iy < T.y1) {
+        }
+        if (EXTRA && wout_base && iy >= T.y0 && iy < T.y1) {
+            const float yv[2][3] = {{y[0].x, y[1].x, y[2].x}, {y[0].y, y[1].y, y[2].y}};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (!T.colI[q]) continue;
                 float *o = wout_base + iy * wout_sh + (T.ix0 + q) * wout_sw;
                 o[0] = yv[q][0]; o[wout_sc] = yv[q][1]; o[2 * wout_sc] = yv[q][2];
             }
         }
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) y[ch] = F2{yv[0][ch], yv[1][ch]};
-#pragma unroll
-        for (int i = 0; i < 6; ++i) g[i] = F2{gv[0][i], gv[1][i]};
     }
 
     // ---- row r = t-3 is finished: phase G, smoothness, depth-gradient write ----
@@ -587,36 +614,40 @@ struct GeoLane {
         const bool doG = r >= y0;                  // an inner row (r <= y1-1 by construction of the loop)
         float gd[2] = {0.f, 0.f};
         if (GRAD && T.do_photo && doG && (FAST ? T.colI[0] : (T.colI[0] || T.colI[1]))) {
+            // both pixels as packed pairs (lane-wise reproject_nodiv / reproject_bwd_fast); a FAST lane holds two inner
+            // pixels or none, a generic one may hold a single inner pixel: its other half is computed and dropped
             const float yt2 = ldg(sc.ytab + r);
-            const F2 d2 = sm.D[r & 7][lane];
-            F2 g[6], po[3];
+            const P2 d2 = p2f(sm.D[r & 7][lane]);
+            P2 g[6], po[3];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) g[i] = sm.G[r & 3][i][lane];
+            for (int i = 0; i < 6; ++i) g[i] = p2f(sm.G[r & 3][i][lane]);
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) po[ch] = sm.PO[r & 1][ch][lane];
-            const float dq[2] = {d2.x, d2.y};
-            const float p0[2] = {po[0].x, po[0].y}, p1[2] = {po[1].x, po[1].y}, p2[2] = {po[2].x, po[2].y};
-            const float g0x[2] = {g[0].x, g[0].y}, g0y[2] = {g[1].x, g[1].y}, g1x[2] = {g[2].x, g[2].y}, g1y[2] = {g[3].x, g[3].y};
-            const float g2x[2] = {g[4].x, g[4].y}, g2y[2] = {g[5].x, g[5].y};
+            for (int ch = 0; ch < 3; ++ch) po[ch] = p2f(sm.PO[r & 1][ch][lane]);
+            const P2 gx = p2fma(po[2], g[4], p2fma(po[1], g[2], p2mul(po[0], g[0])));
+            const P2 gy = p2fma(po[2], g[5], p2fma(po[1], g[3], p2mul(po[0], g[1])));
+            ReprojP rp; reproject_nodiv_p(Ki, P, xtp, yt2, d2, rp);
+            P2 gu[3], gcam[3];
+            const P2 gdp = reproject_bwd_fast_p(P, rp, gx, gy, gu, gcam);
+            const float gdq[2] = {p2lo(gdp), p2hi(gdp)};
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 if (!FAST && !T.colI[q]) continue;
-                const float gx = fmaf(p2[q], g2x[q], fmaf(p1[q], g1x[q], p0[q] * g0x[q]));
-                const float gy = fmaf(p2[q], g2y[q], fmaf(p1[q], g1y[q], p0[q] * g0y[q]));
-                Reproj rp; reproject_nodiv(Ki, P, xt[q], yt2, dq[q], rp);
-                float gu[3], gcam[3];
-                gd[q] = reproject_bwd_fast(P, rp, gx, gy, gu, gcam);
+                gd[q] = gdq[q];
+                float guq[3], camq[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { guq[j] = q ? p2hi(gu[j]) : p2lo(gu[j]); camq[j] = q ? p2hi(rp.cam[j]) : p2lo(rp.cam[j]); }
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    dP[j * 4 + 0] = fmaf(gu[j], rp.cam[0], dP[j * 4 + 0]);
-                    dP[j * 4 + 1] = fmaf(gu[j], rp.cam[1], dP[j * 4 + 1]);
-                    dP[j * 4 + 2] = fmaf(gu[j], rp.cam[2], dP[j * 4 + 2]);
-                    dP[j * 4 + 3] += gu[j];
+                    dP[j * 4 + 0] = fmaf(guq[j], camq[0], dP[j * 4 + 0]);
+                    dP[j * 4 + 1] = fmaf(guq[j], camq[1], dP[j * 4 + 1]);
+                    dP[j * 4 + 2] = fmaf(guq[j], camq[2], dP[j * 4 + 2]);
+                    dP[j * 4 + 3] += guq[j];
                 }
                 if (GRADK) {
+                    const float dq = q ? p2hi(d2) : p2lo(d2);
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        const float gray = gcam[j] * dq[q];
+                        const float gray = (q ? p2hi(gcam[j]) : p2lo(gcam[j])) * dq;
                         dK[j * 3 + 0] = fmaf(gray, xt[q], dK[j * 3 + 0]);
                         dK[j * 3 + 1] = fmaf(gray, yt2, dK[j * 3 + 1]);
                         dK[j * 3 + 2] += gray;
@@ -738,6 +769,7 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
         L.mxs[q] = (T.colB[q] && T.ix0 + q + 1 < T.w) ? 1.f : 0.f; L.mys[q] = T.colB[q] ? 1.f : 0.f;
         L.mxi[q] = L.mxs[q] * T.mI[q]; L.myi[q] = L.mys[q] * T.mI[q];
     }
+    L.xtp = p2(L.xt[0], L.xt[1]);
     const bool clsF = T.clsF;
     const int m = T.m, b = T.b;
     const DevImage &own = clsF ? sc.tgt : sc.src;
@@ -745,7 +777,7 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
     const long long depth_n = clsF ? m : (long long)B + m;
     L.dep_base = sc.depth.p + depth_n * sc.depth.sn; L.dep_sh = sc.depth.sh; L.dep_sw = sc.depth.sw;
     L.gd_base = GRAD ? sc.gdepth.p + depth_n * sc.gdepth.sn : nullptr; L.gd_sh = sc.gdepth.sh; L.gd_sw = sc.gdepth.sw;
-    SNDE_PIN_PTR(L.own_base); SNDE_PIN_PTR(L.dep_base);
+    SNDE_PIN_PTR(L.own_base); SNDE_PIN_PTR(L.dep_base); SNDE_PIN_PTR(L.gd_base);
     L.sx_acc = 0.f; L.sy_acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 9; ++i) L.dK[i] = 0.f;
@@ -773,11 +805,12 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
         L.sy_prev = F2{0.f, 0.f};
 
         // prologue: owner rows t_begin .. t_begin+2 on their way into the ring; the gathers of row t_begin started
-        float wts[2][4], dgate[2][2], taps[24];
+        P2 wts[4], dgate[2]; float taps[24];
 #pragma unroll
         for (int i = 0; i < 24; ++i) taps[i] = 0.f;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) { wts[q][0] = wts[q][1] = wts[q][2] = wts[q][3] = 0.f; dgate[q][0] = dgate[q][1] = 0.f; }
+        for (int i = 0; i < 4; ++i) wts[i] = p2s(0.f);
+        dgate[0] = dgate[1] = p2s(0.f);
         L.prefetch_row(t_begin); L.prefetch_row(t_begin + 1); L.prefetch_row(t_begin + 2);
         row_copy_wait<1>();               // rows t_begin, t_begin+1 have landed
         const bool disp_in = DISP || (EXTRA && (p.flags & FLAG_DISP) != 0);
