@@ -42,7 +42,38 @@ template <int MODE> void run(const char *name, int per_iter_inst) {
            winst / (ms * 1e-3) / 148 / (clk * 1e3), clk / 1000);
     cudaFree(out);
 }
+// dependent-issue latency: ONE warp per SM runs a single dependent chain; cycles per instruction = latency
+template <int MODE> __global__ void lat(float *out, int iters, float s) {
+    float a = threadIdx.x * 1e-3f; u64 p = pack(a, a + 1.f);
+    const u64 ps = pack(s, s * 0.5f), pt = pack(1e-3f, 2e-3f);
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (MODE == 0) a = fmaf(a, s, 1e-3f);
+            if (MODE == 1) p = ffma2(p, ps, pt);
+            if (MODE == 2) p = fadd2(p, pt);
+            if (MODE == 3) { a = fmaf(a, s, 1e-3f); float x, y; unpack(p, x, y); p = ffma2(pack(a, y), ps, pt); unpack(p, x, y); a = x; }   // FFMA -> FFMA2 -> FFMA
+            if (MODE == 4) a = __shfl_xor_sync(0xffffffffu, a, 1);
+            if (MODE == 5) { float r; asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); a = r; }
+        }
+    }
+    long long t1 = clock64();
+    float x, y; unpack(p, x, y);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a + x + y;
+    if (threadIdx.x == 0 && blockIdx.x == 0) reinterpret_cast<long long *>(out + 8192)[0] = t1 - t0;
+}
+template <int MODE> void runlat(const char *name, int inst_per_iter) {
+    float *out; cudaMalloc(&out, 148 * 8 * 1024 * 4);
+    const int iters = 4000;
+    lat<MODE><<<148, 32>>>(out, iters, 0.999f); cudaDeviceSynchronize();
+    lat<MODE><<<148, 32>>>(out, iters, 0.999f); cudaDeviceSynchronize();
+    long long clk; cudaMemcpy(&clk, out + 8192, 8, cudaMemcpyDeviceToHost);
+    printf("latency %-24s %6.2f cycles per dependent instruction\n", name, (double)clk / ((double)iters * 16 * inst_per_iter));
+    cudaFree(out);
+}
 int main() {
+    runlat<0>("FFMA", 1); runlat<1>("FFMA2", 1); runlat<2>("FADD2", 1); runlat<3>("FFMA+FFMA2 alternating", 2); runlat<4>("SHFL", 1); runlat<5>("MUFU.RCP", 1);
     run<0>("FFMA", 1); run<1>("FFMA2", 1); run<2>("FADD2", 1); run<3>("FMUL2", 1); run<4>("FFMA+FFMA2", 2); run<5>("SHFL+FADD", 2); run<6>("MUFU.RCP", 1);
     return 0;
 }

@@ -41,6 +41,17 @@
 #ifndef SNDE_STRIP_PAIRS
 #define SNDE_STRIP_PAIRS 2
 #endif
+// 1: the SSIM warp's row step is one basic block (phases B and C run on every row and are masked), so that the
+// scheduler can interleave the three channels; costs registers (tuning switch, measured in profiles/README.md)
+#ifndef SNDE_ISSUE_LATE
+#define SNDE_ISSUE_LATE 0        // 1: the gathers of row t+1 start after the back-projection of row t-3 instead of before (tuning switch)
+#endif
+#ifndef SNDE_GATHER_WALK
+#define SNDE_GATHER_WALK 1       // tap rows walked channel by channel as pinned pointers (tuning switch)
+#endif
+#ifndef SNDE_SSIM_STRAIGHT
+#define SNDE_SSIM_STRAIGHT 0
+#endif
 
 namespace snde {
 
@@ -103,6 +114,7 @@ struct PairSmem {
     F2 Y[4][3][32];                  // warped other image rows, 0 outside the image          geometry -> SSIM
     F2 PO[2][3][32];                 // dL/d(warped) rows (slot = row & 1)                     SSIM -> geometry
     F2 G[4][6][32];                  // d(warped_c)/dx, /dy (geometry warp only)
+    float YT[8];                     // meshgrid y of the ring rows (copied with the row: no global load in the row loop)
     int task; int pad_[3];
 };
 
@@ -383,8 +395,10 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                     hsum_row(xr, yr, from_left[0], from_right[0], from_left[1], from_right[1], H);
                 }
                 // ---------------- phase B (row t-1) ----------------
+                // (SNDE_SSIM_STRAIGHT: a row that is not a phase-B row runs the same arithmetic on finite sums and contributes
+                // exact zeros (ngq = 0) and nothing to the error sum)
                 CS co; cs_zero(co);
-                if (rowB) {
+                if (SNDE_SSIM_STRAIGHT || rowB) {
                     HS tot; hs_add(s1[ch], H, tot);
                     const F2 xc = sm.X[rb & 7][ch][lane], yc = sm.Y[rb & 3][ch][lane];
                     SsimP ss; ssim_sums_p(tot.x, tot.y, tot.xx, tot.yy, tot.xy, ss);
@@ -396,11 +410,11 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const float err = fmaf(alpha, vcq[q], oma * fabsf(dq[q]));
-                        if (row_inner) {
+                        if (rowB && row_inner) {
                             err_acc = fmaf(EXTRA ? err * mk[q] : err, T.mI[q], err_acc);
                             if (EXTRA && eout_base && T.colI[q]) eout_base[ch * eout_sc + rb * eout_sh + (T.ix0 + q) * eout_sw] = err;
                         }
-                        ngq[q] = (vq[q] == vcq[q]) ? (EXTRA ? ngSm[q] * mk[q] : ngSm[q]) : 0.f;       // the clamp passes gradient inside [0,1] only
+                        ngq[q] = (rowB && vq[q] == vcq[q]) ? (EXTRA ? ngSm[q] * mk[q] : ngSm[q]) : 0.f;       // the clamp passes gradient inside [0,1] only
                     }
                     if (GRAD) ssim_sums_bwd_p(ss, tot.x, tot.y, p2(ngq[0], ngq[1]), co.a, co.b, co.c);
                 }
@@ -420,14 +434,15 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                         Hc.c = p2(from_left[2] + tc, tc + from_right[2]);
                     }
                     // ---------------- phase C (row t-2): dL/d(warped) ----------------
-                    if (doC) {
+                    // (computed every step, stored when the row exists: see phase B)
+                    if (SNDE_SSIM_STRAIGHT || doC) {
                         CS bs; cs_add(c1[ch], Hc, bs);
                         const F2 xf = sm.X[rc & 7][ch][lane], yf = sm.Y[rc & 3][ch][lane];
                         const P2 xv = p2f(xf), yv = p2f(yf);
                         const float d0 = xf.x - yf.x, d1 = xf.y - yf.y;
                         const float l0 = d0 > 0.f ? gl[0] : (d0 < 0.f ? -gl[0] : 0.f), l1 = d1 > 0.f ? gl[1] : (d1 < 0.f ? -gl[1] : 0.f);
                         const P2 po = p2sub(p2fma(p2add(yv, yv), bs.b, p2fma(xv, bs.c, bs.a)), p2(l0, l1));
-                        sm.PO[rc & 1][ch][lane] = f2p(po);
+                        if (doC) sm.PO[rc & 1][ch][lane] = f2p(po);
                     }
                     cs_add(c2[ch], Hc, c1[ch]);   // c1 <- Hc(t-2) + Hc(t-1)
                     c2[ch] = Hc;
@@ -496,6 +511,9 @@ struct GeoLane {
                 row_copy_async<4>(&sm.D[iy & 7][lane].x + k2, dep_base + (y * dep_sh + ix * dep_sw), take);
             }
         }
+        // the row's meshgrid y rides along (lane 0): a global load inside the row loop would share a scoreboard with the
+        // gathers and make the warp wait for all of them
+        if (lane == 0) row_copy_async<4>(&sm.YT[iy & 7], sc.ytab + y, row_in);
         row_copy_commit();
     }
 
@@ -564,16 +582,25 @@ struct GeoLane {
         // are walked channel by channel as pinned pointers (one 64-bit add per row and channel).
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
+#if SNDE_GATHER_WALK
             const float *q0 = ob + o00[q];
             const float *q1 = q0 + dyo[q];
+#endif
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
+#if SNDE_GATHER_WALK
                 SNDE_PIN_PTR(q0); SNDE_PIN_PTR(q1);
+#else
+                const float *q0 = ob + (o00[q] + ch * oth_sc);
+                const float *q1 = q0 + dyo[q];
+#endif
                 taps[12 * q + 4 * ch + 0] = ldg(q0);             // (y0, x0)
                 taps[12 * q + 4 * ch + 1] = ldg(q1);             // (y1, x0)
                 taps[12 * q + 4 * ch + 2] = ldg(q0 + dxo[q]);    // (y0, x1)
                 taps[12 * q + 4 * ch + 3] = ldg(q1 + dxo[q]);    // (y1, x1)
+#if SNDE_GATHER_WALK
                 q0 += oth_sc; q1 += oth_sc;
+#endif
             }
         }
     }
@@ -613,10 +640,14 @@ struct GeoLane {
         const int y0 = T.y0, ix0 = T.ix0;
         const bool doG = r >= y0;                  // an inner row (r <= y1-1 by construction of the loop)
         float gd[2] = {0.f, 0.f};
+        // later passes over the same owner add to what this lane wrote in the earlier ones: fetch that first, so that the
+        // load is hidden behind the whole row step instead of sitting right in front of the store
+        F2 gd_old = F2{0.f, 0.f};
+        if (FAST && GRAD && k > 0 && doG && T.colI[0]) gd_old = *reinterpret_cast<const F2 *>(gd_base + (r * gd_sh + ix0));
         if (GRAD && T.do_photo && doG && (FAST ? T.colI[0] : (T.colI[0] || T.colI[1]))) {
             // both pixels as packed pairs (lane-wise reproject_nodiv / reproject_bwd_fast); a FAST lane holds two inner
             // pixels or none, a generic one may hold a single inner pixel: its other half is computed and dropped
-            const float yt2 = ldg(sc.ytab + r);
+            const float yt2 = sm.YT[r & 7];
             const P2 d2 = p2f(sm.D[r & 7][lane]);
             P2 g[6], po[3];
 #pragma unroll
@@ -732,7 +763,7 @@ struct GeoLane {
                 if (T.colI[0]) {     // inner lanes hold two inner pixels (w even)
                     float *dst = gd_base + (r * gd_sh + ix0);
                     F2 o = F2{gd[0], gd[1]};
-                    if (k > 0) { const F2 old = *reinterpret_cast<const F2 *>(dst); o.x += old.x; o.y += old.y; }
+                    if (k > 0) { o.x += gd_old.x; o.y += gd_old.y; }
                     if (to_disp) { o.x = SNDE_XMUL(-o.x, SNDE_XMUL(dd.x, dd.x)); o.y = SNDE_XMUL(-o.y, SNDE_XMUL(dd.y, dd.y)); }
                     *reinterpret_cast<F2 *>(dst) = o;
                 }
@@ -799,6 +830,17 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
             for (int i = 0; i < 12; ++i) L.P[i] = ldg(Pn + i);
 #pragma unroll
             for (int i = 0; i < 9; ++i) L.Ki[i] = ldg(Kinv + i);
+            // Touch every entry here: the loads share a scoreboard with the tap gathers, and the compiler waits for that
+            // scoreboard at the first use of a loaded value on every path.  Left to the row loop, that first use sits
+            // right behind the gathers of the next row and makes the warp wait for all of them (measured: 10 % of all
+            // stall samples on one instruction).
+            // (an impossible store keeps the touching sum alive through ptxas)
+            float touch = L.xt[0] + L.xt[1];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) touch += L.P[i];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) touch += L.Ki[i];
+            if (touch == 1.2345e38f) sm.pad_[0] = 1;
         }
 #pragma unroll
         for (int i = 0; i < 12; ++i) L.dP[i] = 0.f;
@@ -813,10 +855,10 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
         dgate[0] = dgate[1] = p2s(0.f);
         L.prefetch_row(t_begin); L.prefetch_row(t_begin + 1); L.prefetch_row(t_begin + 2);
         row_copy_wait<1>();               // rows t_begin, t_begin+1 have landed
+        warp_fence(who);                  // (lane 0 copied their meshgrid y)
         const bool disp_in = DISP || (EXTRA && (p.flags & FLAG_DISP) != 0);
         if (disp_in) { L.disparity_to_depth(t_begin); L.disparity_to_depth(t_begin + 1); }
-        if (T.do_photo && t_begin < h) L.a_issue(ldg(sc.ytab + t_begin), sm.D[t_begin & 7][lane], wts, dgate, taps);
-        float yt_n = t_begin + 1 < h ? ldg(sc.ytab + (t_begin + 1)) : 0.f;      // meshgrid y of row t+1, fetched a step ahead
+        if (T.do_photo && t_begin < h) L.a_issue(sm.YT[t_begin & 7], sm.D[t_begin & 7][lane], wts, dgate, taps);
 
         for (int t = t_begin; t <= t_end + 1; ++t) {
             // ---- finish row t: the warped row goes to the SSIM warp, the tap derivatives stay here ----
@@ -838,10 +880,14 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
             }
             pair_barrier(who, bar);       // owner rows <= t+1 and warped rows <= t are published; dL/d(warped) of row t-3 is ready
             // ---- start row t+1: its gathers fly while the rest of this step runs ----
-            if (T.do_photo && t + 1 <= t_end && t + 1 < h) L.a_issue(yt_n, sm.D[(t + 1) & 7][lane], wts, dgate, taps);
-            yt_n = t + 2 < h ? ldg(sc.ytab + (t + 2)) : 0.f;
+#if !SNDE_ISSUE_LATE
+            if (T.do_photo && t + 1 <= t_end && t + 1 < h) L.a_issue(sm.YT[(t + 1) & 7], sm.D[(t + 1) & 7][lane], wts, dgate, taps);
+#endif
             // ---- row t-3: back-projection, depth gradient ----
             if (t - 3 >= T.y0 - 1) L.finish_row(t - 3, k, who);
+#if SNDE_ISSUE_LATE
+            if (T.do_photo && t + 1 <= t_end && t + 1 < h) L.a_issue(sm.YT[(t + 1) & 7], sm.D[(t + 1) & 7][lane], wts, dgate, taps);
+#endif
             // ---- owner row t+3 starts its way into the ring (its slot held row t-5); row t+2 must have landed before the
             //      next barrier publishes it ----
             L.prefetch_row(t + 3);
