@@ -271,23 +271,23 @@ SNDE_STRIP_FN F2 ldg2(const float *p) { return F2{p[0], p[1]}; }
 
 // horizontal 3-sums of one row for the lane's two columns (left column = left neighbour + (a + b), right column =
 // (a + b) + right neighbour: the association the golden-vector tolerances were measured with)
-struct HS { P2 x, y, xx, yy, xy; };
+// (xx + yy is carried as ONE sum q: SSIM and its backward use the two second moments only through their sum)
+struct HS { P2 x, y, q, xy; };
 struct CS { P2 a, b, c; };
 
 SNDE_STRIP_FN void hsum_row(const F2 xv, const F2 yv, float xm, float xp, float ym, float yp, HS &o) {
     const float tx = xv.x + xv.y, ty = yv.x + yv.y;
-    const float txx = fmaf(xv.y, xv.y, xv.x * xv.x), tyy = fmaf(yv.y, yv.y, yv.x * yv.x), txy = fmaf(xv.y, yv.y, xv.x * yv.x);
+    const float tq = fmaf(yv.y, yv.y, fmaf(yv.x, yv.x, fmaf(xv.y, xv.y, xv.x * xv.x))), txy = fmaf(xv.y, yv.y, xv.x * yv.x);
     o.x = p2(xm + tx, tx + xp);
     o.y = p2(ym + ty, ty + yp);
-    o.xx = p2(fmaf(xm, xm, txx), fmaf(xp, xp, txx));
-    o.yy = p2(fmaf(ym, ym, tyy), fmaf(yp, yp, tyy));
+    o.q = p2(fmaf(ym, ym, fmaf(xm, xm, tq)), fmaf(yp, yp, fmaf(xp, xp, tq)));
     o.xy = p2(fmaf(xm, ym, txy), fmaf(xp, yp, txy));
 }
 SNDE_STRIP_FN void hs_add(const HS &a, const HS &b, HS &o) {
-    o.x = p2add(a.x, b.x); o.y = p2add(a.y, b.y); o.xx = p2add(a.xx, b.xx); o.yy = p2add(a.yy, b.yy); o.xy = p2add(a.xy, b.xy);
+    o.x = p2add(a.x, b.x); o.y = p2add(a.y, b.y); o.q = p2add(a.q, b.q); o.xy = p2add(a.xy, b.xy);
 }
 SNDE_STRIP_FN void cs_add(const CS &a, const CS &b, CS &o) { o.a = p2add(a.a, b.a); o.b = p2add(a.b, b.b); o.c = p2add(a.c, b.c); }
-SNDE_STRIP_FN void hs_zero(HS &o) { o.x = o.y = o.xx = o.yy = o.xy = p2s(0.f); }
+SNDE_STRIP_FN void hs_zero(HS &o) { o.x = o.y = o.q = o.xy = p2s(0.f); }
 SNDE_STRIP_FN void cs_zero(CS &o) { o.a = o.b = o.c = p2s(0.f); }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -401,7 +401,7 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                 if (SNDE_SSIM_STRAIGHT || rowB) {
                     HS tot; hs_add(s1[ch], H, tot);
                     const F2 xc = sm.X[rb & 7][ch][lane], yc = sm.Y[rb & 3][ch][lane];
-                    SsimP ss; ssim_sums_p(tot.x, tot.y, tot.xx, tot.yy, tot.xy, ss);
+                    SsimP ss; ssim_sums_p(tot.x, tot.y, tot.q, tot.xy, ss);
                     const P2 v = p2fma(p2s(-0.5f), ss.S, p2s(0.5f));
                     const float vq[2] = {p2lo(v), p2hi(v)};
                     const float vcq[2] = {clampf(vq[0], 0.f, 1.f), clampf(vq[1], 0.f, 1.f)};
