@@ -120,10 +120,10 @@ __global__ void __launch_bounds__(StripCfg::NT, SNDE_STRIP_CTAS_PER_SM) loss_str
         const int task = __shfl_sync(0xffffffffu, sm.task, 0);
         if (task >= p.total_tasks) break;
 #if defined(SNDE_ONLY_ROLE)            // register-budget probe of one role (never shipped)
-        if (role == SNDE_ONLY_ROLE) { if (SNDE_ONLY_ROLE == 0) geo_role<GRAD, GRADK, EXTRA, FAST, DISP>(p, task, lane, sm, bar); else ssim_role<GRAD, EXTRA>(p, task, lane, sm, bar); }
+        if (role == SNDE_ONLY_ROLE) { if (SNDE_ONLY_ROLE == 0) geo_role<GRAD, GRADK, EXTRA, FAST, DISP>(p, task, lane, sm, bar); else ssim_role<GRAD, EXTRA, FAST, DISP>(p, task, lane, sm, bar); }
 #else
         if (role == 0) geo_role<GRAD, GRADK, EXTRA, FAST, DISP>(p, task, lane, sm, bar);
-        else ssim_role<GRAD, EXTRA>(p, task, lane, sm, bar);
+        else ssim_role<GRAD, EXTRA, FAST, DISP>(p, task, lane, sm, bar);
 #endif
     }
 }

@@ -50,7 +50,7 @@
 #define SNDE_GATHER_WALK 1       // tap rows walked channel by channel as pinned pointers (tuning switch)
 #endif
 #ifndef SNDE_SSIM_STRAIGHT
-#define SNDE_SSIM_STRAIGHT 0
+#define SNDE_SSIM_STRAIGHT 1
 #endif
 
 namespace snde {
@@ -334,15 +334,76 @@ SNDE_STRIP_FN void decode_task(const DevLoss &p, int task, int lane, StripTask &
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Owner rows (image + depth + meshgrid y) on their way into the pair's ring.  Run by the SSIM warp, which has the slack
+// (the geometry warp is the longer of the two): one commit group per row, zeros outside the image.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool FAST>
+struct OwnerRows {
+    const float *own_base; int own_sc, own_sh, own_sw;
+    const float *dep_base; int dep_sh, dep_sw;
+    const float *ytab;
+
+    SNDE_STRIP_FN void init(const DevLoss &p, const DevScale &sc, const StripTask &T) {
+        const DevImage &own = T.clsF ? sc.tgt : sc.src;
+        own_base = own.p + (long long)T.m * own.sn; own_sc = own.sc; own_sh = own.sh; own_sw = own.sw;
+        const long long depth_n = T.clsF ? T.m : (long long)p.B + T.m;
+        dep_base = sc.depth.p + depth_n * sc.depth.sn; dep_sh = sc.depth.sh; dep_sw = sc.depth.sw;
+        ytab = sc.ytab;
+        SNDE_PIN_PTR(own_base); SNDE_PIN_PTR(dep_base);
+    }
+    // owner row iy of the lane's two columns -> ring slot iy & 7, asynchronously (no registers, no copy instruction waits
+    // for it)
+    SNDE_STRIP_FN void prefetch_row(PairSmem &sm, const StripTask &T, int lane, int iy) const {
+        const bool row_in = iy >= 0 && iy < T.h;
+        const int y = row_in ? iy : 0;                        // any valid address when nothing is taken
+        F2 (*xs)[32] = sm.X[iy & 7];
+        if (FAST) {
+            const bool take = row_in && T.in[0];              // w and ix0 are even: the pair is inside or outside together
+            const int q = y * own_sh + (take ? T.ix0 : 0);
+            row_copy_async<8>(&xs[0][lane], own_base + q, take);
+            row_copy_async<8>(&xs[1][lane], own_base + (q + own_sc), take);
+            row_copy_async<8>(&xs[2][lane], own_base + (q + 2 * own_sc), take);
+            row_copy_async<8>(&sm.D[iy & 7][lane], dep_base + (y * dep_sh + (take ? T.ix0 : 0)), take);
+        } else {
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2) {
+                const bool take = row_in && T.in[k2];
+                const int ix = take ? T.ix0 + k2 : 0;
+                const int q = y * own_sh + ix * own_sw;
+                row_copy_async<4>(&xs[0][lane].x + k2, own_base + q, take);
+                row_copy_async<4>(&xs[1][lane].x + k2, own_base + (q + own_sc), take);
+                row_copy_async<4>(&xs[2][lane].x + k2, own_base + (q + 2 * own_sc), take);
+                row_copy_async<4>(&sm.D[iy & 7][lane].x + k2, dep_base + (y * dep_sh + ix * dep_sw), take);
+            }
+        }
+        // the row's meshgrid y rides along (lane 0): a global load inside the geometry warp's row loop would share a
+        // scoreboard with the gathers and make the warp wait for all of them
+        if (lane == 0) row_copy_async<4>(&sm.YT[iy & 7], ytab + y, row_in);
+        row_copy_commit();
+    }
+    // disparity input (SNDE_LOSS_DISPARITY): the landed row iy of the ring becomes depth = 1/disp (IEEE division, as
+    // torch.reciprocal; models/baseline.py:835); slots outside the image stay 0
+    SNDE_STRIP_FN void disparity_to_depth(PairSmem &sm, const StripTask &T, int lane, int iy) const {
+        if (iy < 0 || iy >= T.h) return;
+        F2 v = sm.D[iy & 7][lane];
+        v.x = T.in[0] ? SNDE_XDIV(1.f, v.x) : 0.f;
+        v.y = T.in[1] ? SNDE_XDIV(1.f, v.y) : 0.f;
+        sm.D[iy & 7][lane] = v;
+    }
+};
+
 // ===============================================================================================================
 // SSIM warp
 // ===============================================================================================================
-template <bool GRAD, bool EXTRA>
+template <bool GRAD, bool EXTRA, bool FAST, bool DISP>
 SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, int bar) {
     const int lane = who & 31;
     StripTask T;
     decode_task(p, task, lane, T);
     const DevScale &sc = p.sc[T.scale];
+    OwnerRows<FAST> rows; rows.init(p, sc, T);
+    const bool disp_in = DISP || (EXTRA && (p.flags & FLAG_DISP) != 0);
     float alpha = p.alpha, oma = p.oma, g1 = p.oma * sc.gphoto;
     SNDE_PIN_F32(alpha); SNDE_PIN_F32(oma); SNDE_PIN_F32(g1);
     float ngSm[2];            // -dL/dS = 0.5*alpha*gphoto where the column takes part in phase B, else 0
@@ -367,10 +428,15 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
         for (int ch = 0; ch < 3; ++ch) { hs_zero(s1[ch]); hs_zero(s2[ch]); cs_zero(c1[ch]); cs_zero(c2[ch]); }
         float err_acc = 0.f;
 
+        // prologue: owner rows t_begin .. t_begin+2 on their way into the ring, the first two landed and published
+        rows.prefetch_row(sm, T, lane, T.t_begin); rows.prefetch_row(sm, T, lane, T.t_begin + 1); rows.prefetch_row(sm, T, lane, T.t_begin + 2);
+        row_copy_wait<1>();
+        if (disp_in) { rows.disparity_to_depth(sm, T, lane, T.t_begin); rows.disparity_to_depth(sm, T, lane, T.t_begin + 1); }
+        pair_barrier(who, bar);
+
         for (int t = T.t_begin; t <= T.t_end + 1; ++t) {
             pair_barrier(who, bar);              // row t of the warped image is in shared memory
-            if (t > T.t_end) continue;
-            if (!T.do_photo) continue;
+            if (t <= T.t_end && T.do_photo) {
             const int rb = t - 1, rc = t - 2;
             const bool doB = t >= y0, doC = t >= y0 + 2;
             const bool rowB = doB && rb >= 0 && rb < h;
@@ -448,7 +514,15 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                     c2[ch] = Hc;
                 }
             }
+            }
+            // ---- owner row t+3 starts its way into the ring (its slot held row t-5); row t+2 must have landed before the
+            //      next barrier publishes it ----
+            rows.prefetch_row(sm, T, lane, t + 3);
+            row_copy_wait<1>();
+            if (disp_in) rows.disparity_to_depth(sm, T, lane, t + 2);
         }
+        row_copy_wait<0>();
+        pair_barrier(who, bar);                  // the geometry warp is through with the ring: the next pass / task may refill it
         // ---- publish this pass: error sum of pair n ----
         {
             float v[1] = {err_acc};
@@ -472,8 +546,6 @@ struct GeoLane {
     P2 xtp;                   // (xt[0], xt[1])
     float mxs[2], mys[2], mxi[2], myi[2];      // 0/1: the horizontal / vertical smoothness pair starting at column q exists (.. and is an inner column)
     // owner
-    const float *own_base; int own_sc, own_sh, own_sw;
-    const float *dep_base; int dep_sh, dep_sw;
     float *gd_base; int gd_sh, gd_sw;
     // current other image
     const float *oth_base; int oth_sc, oth_sh, oth_sw;
@@ -485,47 +557,6 @@ struct GeoLane {
 
     SNDE_STRIP_FN GeoLane(const DevLoss &p_, const DevScale &sc_, PairSmem &sm_, const StripTask &T_, int lane_)
         : p(p_), sc(sc_), sm(sm_), T(T_), lane(lane_) {}
-
-    // ---- owner row iy (image + depth) of the lane's two columns -> ring slot iy & 7, asynchronously (no registers, no
-    //      copy instruction waits for it); zeros outside the image.  One commit group per row. ----
-    SNDE_STRIP_FN void prefetch_row(int iy) const {
-        const bool row_in = iy >= 0 && iy < T.h;
-        const int y = row_in ? iy : 0;                        // any valid address when nothing is taken
-        F2 (*xs)[32] = sm.X[iy & 7];
-        if (FAST) {
-            const bool take = row_in && T.in[0];              // w and ix0 are even: the pair is inside or outside together
-            const int q = y * own_sh + (take ? T.ix0 : 0);
-            row_copy_async<8>(&xs[0][lane], own_base + q, take);
-            row_copy_async<8>(&xs[1][lane], own_base + (q + own_sc), take);
-            row_copy_async<8>(&xs[2][lane], own_base + (q + 2 * own_sc), take);
-            row_copy_async<8>(&sm.D[iy & 7][lane], dep_base + (y * dep_sh + (take ? T.ix0 : 0)), take);
-        } else {
-#pragma unroll
-            for (int k2 = 0; k2 < 2; ++k2) {
-                const bool take = row_in && T.in[k2];
-                const int ix = take ? T.ix0 + k2 : 0;
-                const int q = y * own_sh + ix * own_sw;
-                row_copy_async<4>(&xs[0][lane].x + k2, own_base + q, take);
-                row_copy_async<4>(&xs[1][lane].x + k2, own_base + (q + own_sc), take);
-                row_copy_async<4>(&xs[2][lane].x + k2, own_base + (q + 2 * own_sc), take);
-                row_copy_async<4>(&sm.D[iy & 7][lane].x + k2, dep_base + (y * dep_sh + ix * dep_sw), take);
-            }
-        }
-        // the row's meshgrid y rides along (lane 0): a global load inside the row loop would share a scoreboard with the
-        // gathers and make the warp wait for all of them
-        if (lane == 0) row_copy_async<4>(&sm.YT[iy & 7], sc.ytab + y, row_in);
-        row_copy_commit();
-    }
-
-    // ---- disparity input (SNDE_LOSS_DISPARITY): the landed row iy of the ring becomes depth = 1/disp (IEEE division, as
-    //      torch.reciprocal; models/baseline.py:835); slots outside the image stay 0 ----
-    SNDE_STRIP_FN void disparity_to_depth(int iy) const {
-        if (iy < 0 || iy >= T.h) return;
-        F2 v = sm.D[iy & 7][lane];
-        v.x = T.in[0] ? SNDE_XDIV(1.f, v.x) : 0.f;
-        v.y = T.in[1] ? SNDE_XDIV(1.f, v.y) : 0.f;
-        sm.D[iy & 7][lane] = v;
-    }
 
     // ---- phase A, first half: reproject the lane's two pixels of a row (in the image) and start the 24 gathers;
     //      the loads land in registers that nothing touches until the next step (software prefetch) ----
@@ -803,12 +834,9 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
     L.xtp = p2(L.xt[0], L.xt[1]);
     const bool clsF = T.clsF;
     const int m = T.m, b = T.b;
-    const DevImage &own = clsF ? sc.tgt : sc.src;
-    L.own_base = own.p + (long long)m * own.sn; L.own_sc = own.sc; L.own_sh = own.sh; L.own_sw = own.sw;
     const long long depth_n = clsF ? m : (long long)B + m;
-    L.dep_base = sc.depth.p + depth_n * sc.depth.sn; L.dep_sh = sc.depth.sh; L.dep_sw = sc.depth.sw;
     L.gd_base = GRAD ? sc.gdepth.p + depth_n * sc.gdepth.sn : nullptr; L.gd_sh = sc.gdepth.sh; L.gd_sw = sc.gdepth.sw;
-    SNDE_PIN_PTR(L.own_base); SNDE_PIN_PTR(L.dep_base); SNDE_PIN_PTR(L.gd_base);
+    SNDE_PIN_PTR(L.gd_base);
     L.sx_acc = 0.f; L.sy_acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 9; ++i) L.dK[i] = 0.f;
@@ -853,11 +881,7 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
 #pragma unroll
         for (int i = 0; i < 4; ++i) wts[i] = p2s(0.f);
         dgate[0] = dgate[1] = p2s(0.f);
-        L.prefetch_row(t_begin); L.prefetch_row(t_begin + 1); L.prefetch_row(t_begin + 2);
-        row_copy_wait<1>();               // rows t_begin, t_begin+1 have landed
-        warp_fence(who);                  // (lane 0 copied their meshgrid y)
-        const bool disp_in = DISP || (EXTRA && (p.flags & FLAG_DISP) != 0);
-        if (disp_in) { L.disparity_to_depth(t_begin); L.disparity_to_depth(t_begin + 1); }
+        pair_barrier(who, bar);           // the SSIM warp has brought owner rows t_begin, t_begin+1 into the ring
         if (T.do_photo && t_begin < h) L.a_issue(sm.YT[t_begin & 7], sm.D[t_begin & 7][lane], wts, dgate, taps);
 
         for (int t = t_begin; t <= t_end + 1; ++t) {
@@ -888,13 +912,8 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
 #if SNDE_ISSUE_LATE
             if (T.do_photo && t + 1 <= t_end && t + 1 < h) L.a_issue(sm.YT[(t + 1) & 7], sm.D[(t + 1) & 7][lane], wts, dgate, taps);
 #endif
-            // ---- owner row t+3 starts its way into the ring (its slot held row t-5); row t+2 must have landed before the
-            //      next barrier publishes it ----
-            L.prefetch_row(t + 3);
-            row_copy_wait<1>();
-            if (disp_in) L.disparity_to_depth(t + 2);
         }
-        row_copy_wait<0>();
+        pair_barrier(who, bar);           // through with the ring (see the SSIM warp)
 
         // ---- publish this pass: d/dP of pair n (the reduction runs unconditionally: warp-collective code stays uniform) ----
         {

@@ -43,7 +43,7 @@ template <bool GRAD, bool GRADK, bool EXTRA, bool FAST, bool DISP = false>
 void run_role(int who) {
     HostPair &w = g_pair;
     if (who < 32) geo_role<GRAD, GRADK, EXTRA, FAST, DISP>(*w.p, w.task, who, *w.sm, 1);
-    else ssim_role<GRAD, EXTRA>(*w.p, w.task, who, *w.sm, 1);
+    else ssim_role<GRAD, EXTRA, FAST, DISP>(*w.p, w.task, who, *w.sm, 1);
 }
 
 void fiber_main(int who) {
