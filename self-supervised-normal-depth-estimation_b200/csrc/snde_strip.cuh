@@ -43,8 +43,10 @@
 #endif
 // 1: the SSIM warp's row step is one basic block (phases B and C run on every row and are masked), so that the
 // scheduler can interleave the three channels; costs registers (tuning switch, measured in profiles/README.md)
-#ifndef SNDE_ISSUE_LATE
-#define SNDE_ISSUE_LATE 0        // 1: the gathers of row t+1 start after the back-projection of row t-3 instead of before (tuning switch)
+// 1: the geometry warp's row step runs reprojection + gathers of row t+1 and the back-projection of row t-3 as ONE basic
+// block (both unconditionally, idle rows / lanes masked), so that the scheduler can interleave the two dependency chains
+#ifndef SNDE_GEO_STRAIGHT
+#define SNDE_GEO_STRAIGHT 1
 #endif
 #ifndef SNDE_GATHER_WALK
 #define SNDE_GATHER_WALK 1       // tap rows walked channel by channel as pinned pointers (tuning switch)
@@ -563,7 +565,7 @@ struct GeoLane {
     // The two pixels run as packed fp32 pairs (lane-wise the scalar chain of reproject_fast / make_taps_valid).
     // wts = {wx0, wx1, wy0, wy1}, each the pair over the two pixels (all zero for a pixel that samples nothing); border
     // mode also needs the derivative gates, kept in dgate = {dx, dy}.
-    SNDE_STRIP_FN void a_issue(float yt, const F2 d, P2 (&wts)[4], P2 (&dgate)[2], float (&taps)[24]) const {
+    SNDE_STRIP_FN void a_issue(float yt, const F2 d, P2 (&wts)[4], P2 (&dgate)[2], float (&taps)[24], bool row_ok = true) const {
         // (lanes whose columns lie outside the image go through the same motions with zero weights on pixel 0)
         const float *ob = oth_base;
         SNDE_PIN_PTR(ob);
@@ -578,7 +580,7 @@ struct GeoLane {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 Taps tp; make_taps(xq[q], yq[q], h, w, p.padding, tp);
-                valid[q] = T.in[q];
+                valid[q] = T.in[q] && row_ok;
                 o00[q] = valid[q] ? tp.y0 * oth_sh + tp.x0 * (FAST ? 1 : oth_sw) : 0;
                 // border mode may have clamped both taps onto the same pixel: step 0
                 dyo[q] = (tp.y1 - tp.y0) * oth_sh; dxo[q] = (tp.x1 - tp.x0) * (FAST ? 1 : oth_sw);
@@ -597,7 +599,7 @@ struct GeoLane {
             wq[0][2] = p2lo(wy0); wq[1][2] = p2hi(wy0); wq[0][3] = p2lo(wy1); wq[1][3] = p2hi(wy1);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                valid[q] = tap_valid(xq[q], yq[q], h, w, 0) != 0.f && T.in[q];
+                valid[q] = tap_valid(xq[q], yq[q], h, w, 0) != 0.f && T.in[q] && row_ok;
                 // an invalid pixel reads the 2x2 block at the image origin (h, w >= 2 is checked on the host)
                 o00[q] = valid[q] ? (int)y0f[q] * oth_sh + (int)x0f[q] * (FAST ? 1 : oth_sw) : 0;
                 // row / column steps to the second tap: constants, so that the four taps of a channel are two base
@@ -655,7 +657,7 @@ struct GeoLane {
                 g[2 * ch] = f2p(gx); g[2 * ch + 1] = f2p(gy);
             }
         }
-        if (EXTRA && wout_base && iy >= T.y0 && iy < T.y1) {
+        if (EXTRA && wout_base && T.do_photo && iy >= T.y0 && iy < T.y1) {
             const float yv[2][3] = {{y[0].x, y[1].x, y[2].x}, {y[0].y, y[1].y, y[2].y}};
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
@@ -675,26 +677,32 @@ struct GeoLane {
         // load is hidden behind the whole row step instead of sitting right in front of the store
         F2 gd_old = F2{0.f, 0.f};
         if (FAST && GRAD && k > 0 && doG && T.colI[0]) gd_old = *reinterpret_cast<const F2 *>(gd_base + (r * gd_sh + ix0));
-        if (GRAD && T.do_photo && doG && (FAST ? T.colI[0] : (T.colI[0] || T.colI[1]))) {
+        const bool g_on = GRAD && T.do_photo && doG;                          // (uniform over the warp)
+        const bool on[2] = {g_on && T.colI[0], g_on && (FAST ? T.colI[0] : T.colI[1])};
+        if (GRAD && (SNDE_GEO_STRAIGHT || on[0] || on[1])) {
             // both pixels as packed pairs (lane-wise reproject_nodiv / reproject_bwd_fast); a FAST lane holds two inner
-            // pixels or none, a generic one may hold a single inner pixel: its other half is computed and dropped
-            const float yt2 = sm.YT[r & 7];
-            const P2 d2 = p2f(sm.D[r & 7][lane]);
+            // pixels or none, a generic one may hold a single inner pixel.  SNDE_GEO_STRAIGHT: no branch around this -- an
+            // idle pixel (halo lane, row outside the segment, whatever the rings hold there) runs with zero depth, zero
+            // upstream gradient and a zero reciprocal and adds exact zeros to every sum.
+            const float yt2 = g_on ? sm.YT[r & 7] : 0.f;
+            const F2 d2f = sm.D[r & 7][lane];
+            const P2 d2 = p2(on[0] ? d2f.x : 0.f, on[1] ? d2f.y : 0.f);
             P2 g[6], po[3];
 #pragma unroll
             for (int i = 0; i < 6; ++i) g[i] = p2f(sm.G[r & 3][i][lane]);
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) po[ch] = p2f(sm.PO[r & 1][ch][lane]);
-            const P2 gx = p2fma(po[2], g[4], p2fma(po[1], g[2], p2mul(po[0], g[0])));
-            const P2 gy = p2fma(po[2], g[5], p2fma(po[1], g[3], p2mul(po[0], g[1])));
+            const P2 gxa = p2fma(po[2], g[4], p2fma(po[1], g[2], p2mul(po[0], g[0])));
+            const P2 gya = p2fma(po[2], g[5], p2fma(po[1], g[3], p2mul(po[0], g[1])));
+            const P2 gx = p2(on[0] ? p2lo(gxa) : 0.f, on[1] ? p2hi(gxa) : 0.f);
+            const P2 gy = p2(on[0] ? p2lo(gya) : 0.f, on[1] ? p2hi(gya) : 0.f);
             ReprojP rp; reproject_nodiv_p(Ki, P, xtp, yt2, d2, rp);
             P2 gu[3], gcam[3];
-            const P2 gdp = reproject_bwd_fast_p(P, rp, gx, gy, gu, gcam);
+            const P2 gdp = reproject_bwd_fast_p(P, rp, gx, gy, gu, gcam, on[0], on[1]);
             const float gdq[2] = {p2lo(gdp), p2hi(gdp)};
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                if (!FAST && !T.colI[q]) continue;
-                gd[q] = gdq[q];
+                gd[q] = gdq[q];               // (exact zero for an idle pixel)
                 float guq[3], camq[3];
 #pragma unroll
                 for (int j = 0; j < 3; ++j) { guq[j] = q ? p2hi(gu[j]) : p2lo(gu[j]); camq[j] = q ? p2hi(rp.cam[j]) : p2lo(rp.cam[j]); }
@@ -719,7 +727,7 @@ struct GeoLane {
         }
     // smoothness of row r (first pass only).  One step earlier (row y0-1) only the vertical pair weights are
         // formed: they are the "pair above" of the first inner row.
-        if (T.do_smooth && k == 0) {
+        if (T.do_smooth && k == 0 && r >= y0 - 1) {
             const int w = T.w, h = T.h;
             F2 sxw = F2{0.f, 0.f}, syw = F2{0.f, 0.f};
             float nb_x[4] = {0.f, 0.f, 0.f, 0.f};          // right neighbour column: image (3) + depth
@@ -869,6 +877,11 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
 #pragma unroll
             for (int i = 0; i < 9; ++i) touch += L.Ki[i];
             if (touch == 1.2345e38f) sm.pad_[0] = 1;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) L.P[i] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) L.Ki[i] = 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 12; ++i) L.dP[i] = 0.f;
@@ -886,6 +899,21 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
 
         for (int t = t_begin; t <= t_end + 1; ++t) {
             // ---- finish row t: the warped row goes to the SSIM warp, the tap derivatives stay here ----
+#if SNDE_GEO_STRAIGHT
+            {
+                // (unconditional: a row whose gathers were never started has four zero weights -> a zero row, which is what
+                // the pools want below the image; past t_end the row is written and never read)
+                const bool want_g = t >= T.y0 && t < T.y1;
+                F2 yr[3], gr[6];
+                L.a_finish(t, wts, dgate, taps, want_g, yr, gr);
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) sm.Y[t & 3][ch][lane] = yr[ch];
+                if (GRAD && want_g) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) sm.G[t & 3][i][lane] = gr[i];
+                }
+            }
+#else
             if (T.do_photo && t <= t_end) {
                 const bool want_g = t >= T.y0 && t < T.y1;
                 if (t < h) {
@@ -902,15 +930,18 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
                     for (int ch = 0; ch < 3; ++ch) sm.Y[t & 3][ch][lane] = F2{0.f, 0.f};
                 }
             }
-            pair_barrier(who, bar);       // owner rows <= t+1 and warped rows <= t are published; dL/d(warped) of row t-3 is ready
-            // ---- start row t+1: its gathers fly while the rest of this step runs ----
-#if !SNDE_ISSUE_LATE
-            if (T.do_photo && t + 1 <= t_end && t + 1 < h) L.a_issue(sm.YT[(t + 1) & 7], sm.D[(t + 1) & 7][lane], wts, dgate, taps);
 #endif
+            pair_barrier(who, bar);       // owner rows <= t+1 and warped rows <= t are published; dL/d(warped) of row t-3 is ready
+#if SNDE_GEO_STRAIGHT
+            // ---- start row t+1 (its gathers fly while the rest of this step runs) and take row t-3 back through the
+            //      projection, as one basic block ----
+            L.a_issue(sm.YT[(t + 1) & 7], sm.D[(t + 1) & 7][lane], wts, dgate, taps, T.do_photo && t + 1 <= t_end && t + 1 < h);
+            L.finish_row(t - 3, k, who);
+#else
+            // ---- start row t+1: its gathers fly while the rest of this step runs ----
+            if (T.do_photo && t + 1 <= t_end && t + 1 < h) L.a_issue(sm.YT[(t + 1) & 7], sm.D[(t + 1) & 7][lane], wts, dgate, taps);
             // ---- row t-3: back-projection, depth gradient ----
             if (t - 3 >= T.y0 - 1) L.finish_row(t - 3, k, who);
-#if SNDE_ISSUE_LATE
-            if (T.do_photo && t + 1 <= t_end && t + 1 < h) L.a_issue(sm.YT[(t + 1) & 7], sm.D[(t + 1) & 7][lane], wts, dgate, taps);
 #endif
         }
         pair_barrier(who, bar);           // through with the ring (see the SSIM warp)
