@@ -48,6 +48,11 @@
 #ifndef SNDE_GEO_STRAIGHT
 #define SNDE_GEO_STRAIGHT 1
 #endif
+// 1: two copies of the geometry warp's row loop, with and without the smoothness term (no run-time branch around it);
+// measured slower than one copy with a uniform branch (more hot code than the instruction cache likes)
+#ifndef SNDE_SMOOTH_SPLIT
+#define SNDE_SMOOTH_SPLIT 0
+#endif
 #ifndef SNDE_GATHER_WALK
 #define SNDE_GATHER_WALK 1       // tap rows walked channel by channel as pinned pointers (tuning switch)
 #endif
@@ -107,6 +112,8 @@ enum { FLAG_GRAD = 1, FLAG_GRAD_K = 2, FLAG_NO_PHOTO = 4, FLAG_NO_SMOOTH = 8, FL
 
 
 struct alignas(16) F4 { float x, y, z, w; };
+struct SmoothOn { static constexpr bool value = true; };
+struct SmoothOff { static constexpr bool value = false; };
 
 // Shared memory of one warp pair.  Every element is written by one lane and read by the same lane index of either
 // warp (neighbouring columns are exchanged by shuffles inside a warp), so the only synchronisation is the pair barrier.
@@ -669,7 +676,9 @@ struct GeoLane {
     }
 
     // ---- row r = t-3 is finished: phase G, smoothness, depth-gradient write ----
-    SNDE_STRIP_FN void finish_row(int r, int k, int who) {
+    // SMOOTH: this pass also does the owner's smoothness term (the first pass over an owner)
+    template <bool SMOOTH>
+    SNDE_STRIP_FN void finish_row(int r, int k, int who, bool smooth_now = true) {
         const int y0 = T.y0, ix0 = T.ix0;
         const bool doG = r >= y0;                  // an inner row (r <= y1-1 by construction of the loop)
         float gd[2] = {0.f, 0.f};
@@ -725,57 +734,47 @@ struct GeoLane {
                 }
             }
         }
-    // smoothness of row r (first pass only).  One step earlier (row y0-1) only the vertical pair weights are
+        // smoothness of row r (first pass only).  One step earlier (row y0-1) only the vertical pair weights are
         // formed: they are the "pair above" of the first inner row.
-        if (T.do_smooth && k == 0 && r >= y0 - 1) {
-            const int w = T.w, h = T.h;
-            F2 sxw = F2{0.f, 0.f}, syw = F2{0.f, 0.f};
-            float nb_x[4] = {0.f, 0.f, 0.f, 0.f};          // right neighbour column: image (3) + depth
-            F2 xa[3], da = F2{0.f, 0.f};
+        // Straight-line like the back-projection above: the loads and the arithmetic run on every row, a row that does
+        // not exist (outside the image / before the segment) contributes selected zeros.
+        if (SMOOTH && smooth_now) {
+            const int h = T.h;
+            const bool r_in = r >= y0 - 1 && r >= 0 && r < h, below = r_in && r + 1 < h;
+            F2 xa[3], xb[3];
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) xa[ch] = F2{0.f, 0.f};
-            const bool r_in = r >= 0 && r < h;
-            if (r_in) {
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) xa[ch] = sm.X[r & 7][ch][lane];
-                da = sm.D[r & 7][lane];
-            }
+            for (int ch = 0; ch < 3; ++ch) { xa[ch] = sm.X[r & 7][ch][lane]; xb[ch] = sm.X[(r + 1) & 7][ch][lane]; }
+            const F2 da = sm.D[r & 7][lane], db = sm.D[(r + 1) & 7][lane];
+            float nb_x[4];                                  // right neighbour column: image (3) + depth
             {
                 const float to_left[4] = {xa[0].x, xa[1].x, xa[2].x, da.x};
                 take_from_right<4>(who, to_left, nb_x);
             }
-            if (r_in) {
-                const float xq[2][3] = {{xa[0].x, xa[1].x, xa[2].x}, {xa[0].y, xa[1].y, xa[2].y}};
-                const float xn[2][3] = {{xa[0].y, xa[1].y, xa[2].y}, {nb_x[0], nb_x[1], nb_x[2]}};
-                const float dq[2] = {da.x, da.y}, dn[2] = {da.y, nb_x[3]};
-                F2 xb[3], db = F2{0.f, 0.f};
-                const bool below = r + 1 < h;
+            const float xq[2][3] = {{xa[0].x, xa[1].x, xa[2].x}, {xa[0].y, xa[1].y, xa[2].y}};
+            const float xn[2][3] = {{xa[0].y, xa[1].y, xa[2].y}, {nb_x[0], nb_x[1], nb_x[2]}};
+            const float dq[2] = {da.x, da.y}, dn[2] = {da.y, nb_x[3]};
+            const float xd[2][3] = {{xb[0].x, xb[1].x, xb[2].x}, {xb[0].y, xb[1].y, xb[2].y}};
+            const float dd[2] = {db.x, db.y};
+            float vxs[2], vys[2];
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) xb[ch] = below ? sm.X[(r + 1) & 7][ch][lane] : F2{0.f, 0.f};
-                if (below) db = sm.D[(r + 1) & 7][lane];
-                const float xd[2][3] = {{xb[0].x, xb[1].x, xb[2].x}, {xb[0].y, xb[1].y, xb[2].y}};
-                const float dd[2] = {db.x, db.y};
-                float vxs[2], vys[2];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    // pairs that do not exist (image border, halo column) are switched off by 0/1 factors fixed per task
-                    {
-                        const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xn[q][0], xn[q][1], xn[q][2]);
-                        const float v = (dq[q] - dn[q]) * wgt;
-                        const float sgn = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
-                        vxs[q] = sgn * mxs[q];
-                        if (doG) sx_acc = fmaf(fabsf(v), mxi[q], sx_acc);
-                    }
-                    if (below) {
-                        const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xd[q][0], xd[q][1], xd[q][2]);
-                        const float v = (dq[q] - dd[q]) * wgt;
-                        const float sgn = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
-                        vys[q] = sgn * mys[q];
-                        if (doG) sy_acc = fmaf(fabsf(v), myi[q], sy_acc);
-                    } else vys[q] = 0.f;
+            for (int q = 0; q < 2; ++q) {
+                // pairs that do not exist (image border, halo column) are switched off by 0/1 factors fixed per task
+                {
+                    const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xn[q][0], xn[q][1], xn[q][2]);
+                    const float v = (dq[q] - dn[q]) * wgt;
+                    const float sgn = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
+                    vxs[q] = r_in ? sgn * mxs[q] : 0.f;
+                    if (doG && r_in) sx_acc = fmaf(fabsf(v), mxi[q], sx_acc);
                 }
-                sxw = F2{vxs[0], vxs[1]}; syw = F2{vys[0], vys[1]};
+                {
+                    const float wgt = edge_weight3_fast(xq[q][0], xq[q][1], xq[q][2], xd[q][0], xd[q][1], xd[q][2]);
+                    const float v = (dq[q] - dd[q]) * wgt;
+                    const float sgn = v > 0.f ? wgt : (v < 0.f ? -wgt : 0.f);
+                    vys[q] = below ? sgn * mys[q] : 0.f;
+                    if (doG && below) sy_acc = fmaf(fabsf(v), myi[q], sy_acc);
+                }
             }
+            const F2 sxw = F2{vxs[0], vxs[1]}, syw = F2{vys[0], vys[1]};
             // the horizontal pair that ENDS at the lane's left column starts in the left neighbour lane
             float sx_left;
             {
@@ -784,7 +783,7 @@ struct GeoLane {
                 take_from_left<1>(who, to_right, from_left);
                 sx_left = from_left[0];
             }
-            if (GRAD && doG) {
+            if (GRAD) {                                     // (stored for inner rows only)
                 gd[0] += sc.gsx * (sxw.x - sx_left) + sc.gsy * (syw.x - sy_prev.x);
                 gd[1] += sc.gsx * (sxw.y - sxw.x) + sc.gsy * (syw.y - sy_prev.y);
             }
@@ -897,6 +896,8 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
         pair_barrier(who, bar);           // the SSIM warp has brought owner rows t_begin, t_begin+1 into the ring
         if (T.do_photo && t_begin < h) L.a_issue(sm.YT[t_begin & 7], sm.D[t_begin & 7][lane], wts, dgate, taps);
 
+        auto row_loop = [&](auto smooth_tag) {
+        constexpr bool SMOOTH = decltype(smooth_tag)::value;
         for (int t = t_begin; t <= t_end + 1; ++t) {
             // ---- finish row t: the warped row goes to the SSIM warp, the tap derivatives stay here ----
 #if SNDE_GEO_STRAIGHT
@@ -936,14 +937,21 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
             // ---- start row t+1 (its gathers fly while the rest of this step runs) and take row t-3 back through the
             //      projection, as one basic block ----
             L.a_issue(sm.YT[(t + 1) & 7], sm.D[(t + 1) & 7][lane], wts, dgate, taps, T.do_photo && t + 1 <= t_end && t + 1 < h);
-            L.finish_row(t - 3, k, who);
+            L.template finish_row<SMOOTH>(t - 3, k, who, SNDE_SMOOTH_SPLIT || (T.do_smooth && k == 0));
 #else
             // ---- start row t+1: its gathers fly while the rest of this step runs ----
             if (T.do_photo && t + 1 <= t_end && t + 1 < h) L.a_issue(sm.YT[(t + 1) & 7], sm.D[(t + 1) & 7][lane], wts, dgate, taps);
             // ---- row t-3: back-projection, depth gradient ----
-            if (t - 3 >= T.y0 - 1) L.finish_row(t - 3, k, who);
+            if (t - 3 >= T.y0 - 1) L.template finish_row<SMOOTH>(t - 3, k, who, SNDE_SMOOTH_SPLIT || (T.do_smooth && k == 0));
 #endif
         }
+        };
+        // (SNDE_SMOOTH_SPLIT: two copies of the row loop -- the smoothness term belongs to the first pass over an owner only)
+#if SNDE_SMOOTH_SPLIT
+        if (T.do_smooth && k == 0) row_loop(SmoothOn{}); else row_loop(SmoothOff{});
+#else
+        row_loop(SmoothOn{});
+#endif
         pair_barrier(who, bar);           // through with the ring (see the SSIM warp)
 
         // ---- publish this pass: d/dP of pair n (the reduction runs unconditionally: warp-collective code stays uniform) ----
