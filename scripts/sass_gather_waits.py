@@ -15,8 +15,8 @@ while i < len(lines):
             hi = int(m2.group(1), 16)
             res.append((int(m.group(1), 16), m.group(2), (hi >> 46) & 7, (hi >> 52) & 0x3f)); i += 2; continue
     i += 1
-# the geometry row loop: the innermost backward branch around the LDGSTS row prefetch
-pre = [a for a, t, _, _ in res if t.startswith("LDGSTS") or " LDGSTS" in t]
+# the geometry row loop: the innermost backward branch around the tap gathers
+pre = [a for a, t, _, _ in res if "LDG.E.CONSTANT" in t]
 loops = []
 for a, t, _, _ in res:
     if "BRA" in t:

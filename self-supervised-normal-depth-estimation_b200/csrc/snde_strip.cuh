@@ -188,6 +188,11 @@ SNDE_STRIP_FN float warp_sum_scatter(int lane, const float (&in)[N]) {
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 SNDE_STRIP_FN void atomic_add_double(double *dst, double v) { atomicAdd(dst, v); }
+// dst[0..1] += v without reading anything back (no scoreboard to wait on).  Only ever used on elements that this very
+// lane wrote earlier and nobody else touches: one add per element and pass, so the result does not depend on timing.
+SNDE_STRIP_FN void add_pair_noreturn(float *dst, F2 v) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(v.x), "f"(v.y) : "memory");
+}
 SNDE_STRIP_FN void warp_fence(int) { __syncwarp(); }
 // rendezvous of the two warps of a pair (named barrier `bar`, 64 threads); orders their shared-memory traffic
 SNDE_STRIP_FN void pair_barrier(int, int bar) { asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory"); }
@@ -202,6 +207,7 @@ SNDE_STRIP_FN void row_copy_commit() { asm volatile("cp.async.commit_group;" :::
 template <int PENDING>
 SNDE_STRIP_FN void row_copy_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 SNDE_STRIP_FN F2 ldg2(const float *p) { const float2 v = __ldg(reinterpret_cast<const float2 *>(p)); return F2{v.x, v.y}; }
+SNDE_STRIP_FN F2 ldcg2(const float *p) { const float2 v = __ldcg(reinterpret_cast<const float2 *>(p)); return F2{v.x, v.y}; }
 // Pin a pointer in a register pair: stops the compiler from re-deriving it from (struct field + 64-bit offset) at
 // every use, so that base[int_offset] costs one IMAD.WIDE instead of a four-instruction 64-bit add-and-shift.
 #define SNDE_PIN_PTR(p) asm volatile("" : "+l"(p))
@@ -263,6 +269,7 @@ SNDE_STRIP_FN float warp_sum_scatter(int who, const float (&in)[N]) {
     return slot < N ? v[slot] : 0.f;
 }
 SNDE_STRIP_FN void atomic_add_double(double *dst, double v) { *dst += v; }
+SNDE_STRIP_FN void add_pair_noreturn(float *dst, F2 v) { dst[0] += v.x; dst[1] += v.y; }
 SNDE_STRIP_FN void warp_fence(int who) { host_warp_sync(who); }
 SNDE_STRIP_FN void pair_barrier(int who, int) { host_pair_sync(who); }
 template <int BYTES>
@@ -273,6 +280,7 @@ SNDE_STRIP_FN void row_copy_commit() {}
 template <int PENDING>
 SNDE_STRIP_FN void row_copy_wait() {}
 SNDE_STRIP_FN F2 ldg2(const float *p) { return F2{p[0], p[1]}; }
+SNDE_STRIP_FN F2 ldcg2(const float *p) { return F2{p[0], p[1]}; }
 #define SNDE_PIN_PTR(p) ((void)0)
 #define SNDE_SCHED_FENCE() ((void)0)
 #define SNDE_PIN_F32(x) ((void)0)
@@ -682,10 +690,13 @@ struct GeoLane {
         const int y0 = T.y0, ix0 = T.ix0;
         const bool doG = r >= y0;                  // an inner row (r <= y1-1 by construction of the loop)
         float gd[2] = {0.f, 0.f};
-        // later passes over the same owner add to what this lane wrote in the earlier ones: fetch that first, so that the
-        // load is hidden behind the whole row step instead of sitting right in front of the store
+        // Later passes over the same owner add to what this lane wrote in the earlier ones -- by a no-return add, because a
+        // load here would share the gathers' scoreboard and its use would wait for all of them (measured: 7 % of all stall
+        // samples).  Only the pass that turns the finished sum into a disparity gradient has to read it back (from L2:
+        // the adds of the passes in between do not go through L1); that read is issued first thing in the row step.
+        const bool to_disp = (DISP || (EXTRA && (p.flags & FLAG_DISP))) && k == T.n_pass - 1;
         F2 gd_old = F2{0.f, 0.f};
-        if (FAST && GRAD && k > 0 && doG && T.colI[0]) gd_old = *reinterpret_cast<const F2 *>(gd_base + (r * gd_sh + ix0));
+        if (FAST && GRAD && k > 0 && to_disp && doG && T.colI[0]) gd_old = ldcg2(gd_base + (r * gd_sh + ix0));
         const bool g_on = GRAD && T.do_photo && doG;                          // (uniform over the warp)
         const bool on[2] = {g_on && T.colI[0], g_on && (FAST ? T.colI[0] : T.colI[1])};
         if (GRAD && (SNDE_GEO_STRAIGHT || on[0] || on[1])) {
@@ -794,16 +805,18 @@ struct GeoLane {
             // Disparity input: the last pass turns the finished sum into d/d(disparity) = -(g * depth^2), autograd's
             // reciprocal backward -grad * (result * result).
             // (DISP: the lean disparity instance; the general EXTRA instance looks at the flag)
-            const bool to_disp = (DISP || (EXTRA && (p.flags & FLAG_DISP))) && k == T.n_pass - 1;
             F2 dd = F2{0.f, 0.f};
             if (DISP || EXTRA) dd = sm.D[r & 7][lane];
             if (FAST) {
                 if (T.colI[0]) {     // inner lanes hold two inner pixels (w even)
                     float *dst = gd_base + (r * gd_sh + ix0);
                     F2 o = F2{gd[0], gd[1]};
-                    if (k > 0) { o.x += gd_old.x; o.y += gd_old.y; }
-                    if (to_disp) { o.x = SNDE_XMUL(-o.x, SNDE_XMUL(dd.x, dd.x)); o.y = SNDE_XMUL(-o.y, SNDE_XMUL(dd.y, dd.y)); }
-                    *reinterpret_cast<F2 *>(dst) = o;
+                    if (k > 0 && !to_disp) add_pair_noreturn(dst, o);
+                    else {
+                        if (k > 0) { o.x += gd_old.x; o.y += gd_old.y; }
+                        if (to_disp) { o.x = SNDE_XMUL(-o.x, SNDE_XMUL(dd.x, dd.x)); o.y = SNDE_XMUL(-o.y, SNDE_XMUL(dd.y, dd.y)); }
+                        *reinterpret_cast<F2 *>(dst) = o;
+                    }
                 }
             } else {
                 const float ddq[2] = {dd.x, dd.y};
