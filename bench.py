@@ -247,7 +247,7 @@ def main():
 
     # Three device input sets and three streams: the H2D copy of step i+1, the fused loss of step i and the D2H read of
     # step i-1 overlap (every byte still moves every step, inside the timed region).
-    NBUF = 2
+    NBUF = int(os.environ.get("SNDE_E2E_NBUF", "2"))
     dev_in = [dict(tgt=torch.empty_like(h_tgt, device=dev), src=torch.empty_like(h_src, device=dev),
                    dep=[torch.empty_like(t, device=dev) for t in h_dep], poses=torch.empty_like(h_poses, device=dev),
                    K=torch.empty_like(h_K, device=dev)) for _ in range(NBUF)]

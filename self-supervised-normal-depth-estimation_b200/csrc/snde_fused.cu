@@ -16,7 +16,13 @@ using namespace snde;
 #define SNDE_STRIP_CTAS_PER_SM 3
 #endif
 
-#define SNDE_CHECK_LAUNCH() do { if (cudaGetLastError() != cudaSuccess) return SNDE_ERR_CUDA; } while (0)
+// (SNDE_DEBUG in the environment: say which CUDA error it was)
+static inline bool snde_cuda_failed(cudaError_t e, const char *what, int line) {
+    if (e == cudaSuccess) return false;
+    if (getenv("SNDE_DEBUG")) fprintf(stderr, "snde: %s: %s (snde_fused.cu:%d)\n", what, cudaGetErrorString(e), line);
+    return true;
+}
+#define SNDE_CHECK_LAUNCH() do { if (snde_cuda_failed(cudaGetLastError(), "launch", __LINE__)) return SNDE_ERR_CUDA; } while (0)
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -105,6 +111,8 @@ __global__ void __launch_bounds__(64) loss_final_kernel(int B, int S, int ns, in
 // Warps w and w + PAIRS form a pair; which of the two is the geometry warp alternates with the CTA index, so every
 // scheduler (warp index mod 4) hosts both kinds of warp.
 template <bool GRAD, bool GRADK, bool EXTRA, bool FAST, bool DISP = false>
+// (register budget: each of the four schedulers of an SM has its own 16 K registers, so 3 warps per scheduler may use 168
+// registers and 4 warps 128 -- nothing in between: 14 warps of 144 registers do not launch)
 __global__ void __launch_bounds__(StripCfg::NT, SNDE_STRIP_CTAS_PER_SM) loss_strip_kernel(const __grid_constant__ DevLoss p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5;
@@ -205,7 +213,7 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     if (ctas > need) ctas = need;
     auto launch = [&](auto kern, int variant) -> int {
         if (!attr_done[variant][devi]) {
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SNDE_ERR_CUDA;
+            if (snde_cuda_failed(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "shared-memory opt-in", __LINE__)) return SNDE_ERR_CUDA;
             attr_done[variant][devi] = true;
         }
         kern<<<(unsigned)ctas, StripCfg::NT, smem, st>>>(d);
