@@ -491,11 +491,13 @@ def test_geonet_loss_from_frames_equals_reference_prep_then_loss():
     assert rel_l2(poses.grad.cpu().numpy(), poses2.grad.cpu().numpy()) < 1e-5
 
 
-def test_disparity_input_matches_autograd_through_reciprocal():
-    """section 8(f2): disparity=True == (depth = 1/disp in torch) -> fused loss -> autograd back to the disparity"""
+@pytest.mark.parametrize("case", [CASES["small_smooth"], dict(B=2, S=3, H=40, W=128, num_scales=2, seed=4, smooth=True, motion="small")])
+def test_disparity_input_matches_autograd_through_reciprocal(case):
+    """section 8(f2): disparity=True == (depth = 1/disp in torch) -> fused loss -> autograd back to the disparity.
+    S = 3: a middle pass adds its gradient without reading back, the last pass reads the sum back and transforms it."""
     from snde_b200.loss_functions import geonet_loss
     from snde_b200.synthetic import make_inputs
-    inp = make_inputs(**CASES["small_smooth"]).to(DEV)
+    inp = make_inputs(**case).to(DEV)
     disp0 = [1.0 / d for d in inp.depth_pyr]
     disp_a = [x.clone().requires_grad_(True) for x in disp0]
     poses_a = inp.poses.clone().requires_grad_(True)
