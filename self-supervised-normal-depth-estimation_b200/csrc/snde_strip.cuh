@@ -295,10 +295,13 @@ struct CS { P2 a, b, c; };
 SNDE_STRIP_FN void hsum_row(const F2 xv, const F2 yv, float xm, float xp, float ym, float yp, HS &o) {
     const float tx = xv.x + xv.y, ty = yv.x + yv.y;
     const float tq = fmaf(yv.y, yv.y, fmaf(yv.x, yv.x, fmaf(xv.y, xv.y, xv.x * xv.x))), txy = fmaf(xv.y, yv.y, xv.x * yv.x);
-    o.x = p2(xm + tx, tx + xp);
-    o.y = p2(ym + ty, ty + yp);
-    o.q = p2(fmaf(ym, ym, fmaf(xm, xm, tq)), fmaf(yp, yp, fmaf(xp, xp, tq)));
-    o.xy = p2(fmaf(xm, ym, txy), fmaf(xp, yp, txy));
+    // the two neighbour columns as one pair (left, right): one packed operation per output, the lane's own part a broadcast
+    // operand.  Lane-wise this is (xm + tx, tx + xp), (fma(ym, ym, fma(xm, xm, tq)), ...) as before: addition commutes exactly.
+    const P2 mx = p2(xm, xp), my = p2(ym, yp);
+    o.x = p2add(mx, p2s(tx));
+    o.y = p2add(my, p2s(ty));
+    o.q = p2fma(my, my, p2fma(mx, mx, p2s(tq)));
+    o.xy = p2fma(mx, my, p2s(txy));
 }
 SNDE_STRIP_FN void hs_add(const HS &a, const HS &b, HS &o) {
     o.x = p2add(a.x, b.x); o.y = p2add(a.y, b.y); o.q = p2add(a.q, b.q); o.xy = p2add(a.xy, b.xy);
@@ -512,9 +515,9 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                         float from_left[3], from_right[3];
                         neighbor_exchange<3>(who, to_right, to_left, from_left, from_right);
                         const float ta = al + ah, tb = bl + bh, tc = cl + chh;
-                        Hc.a = p2(from_left[0] + ta, ta + from_right[0]);
-                        Hc.b = p2(from_left[1] + tb, tb + from_right[1]);
-                        Hc.c = p2(from_left[2] + tc, tc + from_right[2]);
+                        Hc.a = p2add(p2(from_left[0], from_right[0]), p2s(ta));
+                        Hc.b = p2add(p2(from_left[1], from_right[1]), p2s(tb));
+                        Hc.c = p2add(p2(from_left[2], from_right[2]), p2s(tc));
                     }
                     // ---------------- phase C (row t-2): dL/d(warped) ----------------
                     // (computed every step, stored when the row exists: see phase B)
