@@ -150,3 +150,28 @@ def test_hot_kernel_instance_has_no_register_spills(abi):
     stack, st, ld, regs = map(int, m.groups())
     assert st == 0 and ld == 0, (st, ld)
     assert regs <= 168
+
+
+def test_hot_kernel_instance_waits_for_its_gathers_only_at_the_blend(abi):
+    """ptxas signals every global load of the geometry warp on one scoreboard; an instruction that waits on it waits for all
+    24 tap gathers of the next row.  The only legitimate one is the blend at the top of the next row step -- a second
+    one (the first use of a loop-invariant load, a read-modify-write) once cost 7-11 % of the run time each
+    (profiles/README.md).  Static check of the in-tree build's SASS control bits."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not installed")
+    from snde_b200 import build
+    obj = os.path.join(os.path.dirname(abi.LIB_PATH), "build", os.path.basename(abi.LIB_PATH).replace(".so", "_") + "snde_fused.o")
+    if not os.path.exists(obj):
+        build.build(force=True)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    try:
+        from sass_gather_waits import analyse
+    finally:
+        sys.path.pop(0)
+    lo, hi, sbs, waits = analyse(obj, "_Z17loss_strip_kernelILb1ELb0ELb0ELb1ELb0EEvN4snde7DevLossE")
+    assert sum(sbs.values()) == 24, sbs                       # the gathers are the only global loads of the loop
+    assert len(waits) == 1, waits
+    assert waits[0][0] - lo < 0x200, waits                    # ... and it sits at the top of the row step
+
