@@ -341,7 +341,7 @@ def main():
             "gpu_launches": 3 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_step": algo_bytes, "traffic_source": traffic_src,
-                         "note": "duration = whole step (memset + prep + strip kernel + finalize); the strip kernel is 98% of it "
+                         "note": "duration = whole step (prep + strip kernel + finalize); the strip kernel is 98% of it "
                                  "(profiles/). Bytes per SURVEY 8(d): 60 B/warped px + 36 B/smooth px, as for separate fwd and bwd "
                                  "passes; the single-pass kernel moves less and is bound by instruction issue and dependent-issue latency (DESIGN.md section 5)."},
         }

@@ -62,9 +62,14 @@ extern "C" int snde_fill_grid_table(int n, float *out) {
 }
 
 
+// (also zeroes the accumulators and the task counter of the call, [zero, zero + zero_words) in 16-byte words: one graph node
+// less than a separate memset)
 __global__ void __launch_bounds__(128) loss_prep_kernel(int B, int S, int ns, const float *__restrict__ poses, PrepParams kp,
-                                                        float *__restrict__ P, float *__restrict__ Kinv) {
-    loss_prep_thread(blockIdx.x * blockDim.x + threadIdx.x, B, S, ns, poses, kp, P, Kinv);
+                                                        float *__restrict__ P, float *__restrict__ Kinv, uint4 *__restrict__ zero,
+                                                        int zero_words) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int j = i; j < zero_words; j += gridDim.x * blockDim.x) zero[j] = make_uint4(0u, 0u, 0u, 0u);
+    loss_prep_thread(i, B, S, ns, poses, kp, P, Kinv);
 }
 
 // block b < B: one thread per (source k, scale s) runs the double-precision backward of the matrix prep, then the
@@ -197,10 +202,11 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     cudaStream_t st = as_stream(stream_);
     const int B = a->B, S = a->S, ns = a->num_scales, N = B * S;
     unsigned char *ws = (unsigned char *)a->workspace;
-    if (cudaMemsetAsync(ws + lay.gP, 0, lay.end - lay.gP, st) != cudaSuccess) return SNDE_ERR_CUDA;
     PrepParams kp; FinalParams fp;
     build_prep_final(a, kp, fp);
-    loss_prep_kernel<<<(ns * N + 127) / 128, 128, 0, st>>>(B, S, ns, a->poses, kp, (float *)(ws + lay.P), (float *)(ws + lay.Kinv));
+    // [gP, end) is a whole number of 16-byte words (every offset of the layout is rounded up to 16)
+    loss_prep_kernel<<<(ns * N + 127) / 128, 128, 0, st>>>(B, S, ns, a->poses, kp, (float *)(ws + lay.P), (float *)(ws + lay.Kinv),
+                                                       (uint4 *)(ws + lay.gP), (int)((lay.end - lay.gP) / 16));
     SNDE_CHECK_LAUNCH();
     const size_t smem = sizeof(PairSmem) * StripCfg::PAIRS;
     const bool grad = a->flags & SNDE_LOSS_GRAD, gradk = a->flags & SNDE_LOSS_GRAD_K;
