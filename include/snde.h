@@ -123,7 +123,7 @@ typedef struct SndeLossArgs {
 /* sizeof(SndeLossArgs) as compiled: lets an FFI binding verify its struct layout */
 SNDE_API size_t snde_sizeof_loss_args(void);
 SNDE_API size_t snde_loss_workspace_bytes(int B, int S, int num_scales);
-/* launches: 1 memset + 3 kernels (matrix prep, persistent fused strip kernel over every scale/direction/strip, finalize) */
+/* launches: 3 kernels (matrix prep + zeroing of the accumulators, persistent fused strip kernel over every scale/direction/strip, finalize) */
 SNDE_API int snde_loss_fwdbwd(const SndeLossArgs *args, void *stream);
 /* number of strip tasks (owner x 60-column strip x row segment) the fused kernel works through for these shapes on a
  * B200 (host only; used by tests/bench) */
