@@ -10,8 +10,8 @@ the CUDA path (tests/test_gpu_*.py).  /root/reference does not exist on the GPU 
 nothing but this script reads it.
 
 Reference entry points exercised (all fp32, CPU):
-  utils/utils_edited.py : meshgrid, pose_vec2mat, compute_rigid_flow, flow_warp,
-                          bilinear_sampler, DSSIM, compute_multi_scale_intrinsics, scale_pyramid
+  utils/utils_edited.py : meshgrid, pose_vec2mat, compute_rigid_flow, flow_warp, bilinear_sampler, DSSIM (kats, cases);
+                          scale_pyramid, compute_multi_scale_intrinsics, euler2mat, pixel2cam, cam2pixel (glue_kats)
   models/loss_functions.py : image_similarity, smooth_loss
 composed exactly as models/baseline.py:895-970 (build_rigid_warp_flow) and :1125-1161
 (build_losses) compose them.
@@ -157,9 +157,58 @@ def kats(U, L):
     print("kats written:", len(out), "arrays")
 
 
+def glue_kats(U, L):
+    """Round 2: known answers for the caller-side glue the drop-in modules restate in torch:
+    scale_pyramid, compute_multi_scale_intrinsics, euler2mat, pose_vec2mat, meshgrid, pixel2cam, cam2pixel -- each one
+    really called on the imported reference."""
+    out = {}
+    g = torch.Generator().manual_seed(21)
+    img = torch.rand(3, 3, 48, 80, generator=g) * 2 - 1
+    out["sp_img"] = img.numpy()
+    for s, lvl in enumerate(U.scale_pyramid(img, 4)):                    # NHWC views of NCHW memory
+        out[f"sp_level_{s}"] = np.ascontiguousarray(lvl.numpy())
+    K = torch.tensor([[241.67, 0.0, 204.17], [0.0, 246.28, 59.0], [0.0, 0.0, 1.0]]).repeat(3, 1, 1)
+    K = K * (1 + 0.1 * torch.rand(3, 1, 1, generator=g))
+    K[:, 2, 2] = 1.0
+    out["msi_K"] = K.numpy()
+    out["msi_out"] = U.compute_multi_scale_intrinsics(K, 4).numpy()
+    ang = torch.randn(5, 3, generator=g) * 0.7
+    out["e2m_zyx"] = ang.numpy()
+    out["e2m_out"] = U.euler2mat(ang[:, 0], ang[:, 1], ang[:, 2]).squeeze(1).numpy()
+    for b, h, w, hom in ((2, 6, 9, True), (1, 5, 7, False)):
+        out[f"mg_{h}x{w}_{int(hom)}"] = np.ascontiguousarray(U.meshgrid(b, h, w, hom).numpy())
+    b, h, w = 2, 6, 9
+    depth = 1.0 / (torch.rand(b, h, w, generator=g) * 9 + 0.5)
+    Kc = torch.tensor([[0.58 * w, 0.1, 0.5 * w], [0, 1.92 * h, 0.5 * h], [0, 0, 1]]).repeat(b, 1, 1)
+    pix = U.meshgrid(b, h, w)
+    cam = U.pixel2cam(depth, pix, Kc)
+    out.update(p2c_depth=depth.numpy(), p2c_K=Kc.numpy(), p2c_out=cam.numpy())
+    cam3 = U.pixel2cam(depth, pix, Kc, False)
+    out["p2c_out_nohom"] = cam3.numpy()
+    vec = torch.randn(b, 6, generator=g) * torch.tensor([0.1, 0.1, 0.1, 0.05, 0.05, 0.05])
+    K4 = torch.zeros(b, 4, 4); K4[:, :3, :3] = Kc; K4[:, 3, 3] = 1.0
+    proj = torch.matmul(K4, U.pose_vec2mat(vec))
+    out.update(c2p_vec=vec.numpy(), c2p_proj=proj.numpy(), c2p_out=np.ascontiguousarray(U.cam2pixel(cam, proj).numpy()))
+    np.savez_compressed(os.path.join(HERE, "glue_kats.npz"), **out)
+    print("glue_kats written:", len(out), "arrays")
+
+
+def full_size_cases(U, L):
+    """Round 2: the BASELINE shapes at their FULL bench sizes through the reference itself (scalars, pose gradients and
+    position-sensitive checksums of the depth gradients): config 2 (B=32), config 3 shape (NYU, B=8) and config 4's per-GPU
+    shard (376x1248, S=4, B=8: N*h*w = 15.0 M stays below the reference's 2^24 float-index limit)."""
+    run_case(U, L, "config2_smooth", False, B=32, S=2, H=128, W=416, num_scales=4, seed=12, smooth=True, motion="small")
+    run_case(U, L, "nyu_b8_smooth", False, B=8, S=2, H=480, W=640, num_scales=4, seed=13, smooth=True, motion="small", intrinsics="nyu")
+    run_case(U, L, "hires_b8_smooth", False, B=8, S=4, H=376, W=1248, num_scales=4, seed=14, smooth=True, motion="small")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     U, L = import_reference()
+    if "--round2" in sys.argv:          # only the fixtures added in round 2 (the round-1 files stay byte-identical)
+        glue_kats(U, L)
+        full_size_cases(U, L)
+        sys.exit(0)
     kats(U, L)
     # small cases with every intermediate kept (a few hundred KB each)
     run_case(U, L, "small_smooth", True, B=2, S=2, H=32, W=64, num_scales=3, seed=1, smooth=True, motion="small")
@@ -168,3 +217,5 @@ if __name__ == "__main__":
     # BASELINE config 1 (the reference's CPU-runnable case), scalars + checksums only
     run_case(U, L, "config1_noise", False, B=4, S=2, H=128, W=416, num_scales=4, seed=0, smooth=False, motion="small")
     run_case(U, L, "config1_smooth", False, B=4, S=2, H=128, W=416, num_scales=4, seed=0, smooth=True, motion="small")
+    glue_kats(U, L)
+    full_size_cases(U, L)

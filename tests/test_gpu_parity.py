@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from cases import CASES, SMALL, close_except_flips, load_golden, oracle_inputs, rel_l2
+from cases import CASES, FULL, SMALL, check_depth_grads, close_except_flips, load_golden, oracle_inputs, pose_grad_tolerance, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -39,7 +39,7 @@ def _fused(inp, want_maps=False, **kw):
 # fused loss
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", SMALL)
-def test_fused_vs_oracle_and_golden_small(oracle32, name):
+def test_fused_vs_oracle_and_golden_small(oracle32, oracle64, name):
     from oracle.compose import geonet_loss
     from snde_b200.synthetic import make_inputs
     inp = make_inputs(**CASES[name])
@@ -59,16 +59,16 @@ def test_fused_vs_oracle_and_golden_small(oracle32, name):
         assert rel_l2(e["warped_bwd"][s], g[f"bwd_warp_{s}"]) < wtol
         assert rel_l2(e["err_fwd"][s], g[f"fwd_err_{s}"]) < 10 * wtol
         assert rel_l2(e["err_bwd"][s], g[f"bwd_err_{s}"]) < 10 * wtol
-        for ref in (o["grad_depth"][s], g[f"grad_depth_{s}"]):
-            ok, rel, frac = close_except_flips(e["grad_depth"][s], ref, max_flip_frac=2e-3)
-            assert ok, (s, rel, frac)
+    o64 = geonet_loss(oracle64, **oracle_inputs(inp))
+    check_depth_grads(e["grad_depth"], o["grad_depth"], o64["grad_depth"], tag=name + " vs oracle")
+    check_depth_grads(e["grad_depth"], [g[f"grad_depth_{s}"] for s in range(inp.num_scales)], o64["grad_depth"], tag=name + " vs golden")
     assert rel_l2(e["grad_poses"], o["grad_poses"]) < 1e-4
     assert rel_l2(e["grad_poses"], g["grad_poses"]) < 1e-4
     assert rel_l2(e["grad_K_ms"], o["grad_K_ms"]) < 1e-4
 
 
 @pytest.mark.parametrize("name", ["config1_smooth", "config1_noise"])
-def test_fused_config1_vs_oracle_and_golden(oracle32, name):
+def test_fused_config1_vs_oracle_and_golden(oracle32, oracle64, name):
     """BASELINE config 1 (128x416, B=4, S=2, 4 scales)"""
     from oracle.compose import geonet_loss
     from snde_b200.synthetic import make_inputs
@@ -82,18 +82,21 @@ def test_fused_config1_vs_oracle_and_golden(oracle32, name):
     np.testing.assert_allclose(e["fwd_mean"], g["fwd_mean"], rtol=1e-5)
     np.testing.assert_allclose(e["bwd_mean"], g["bwd_mean"], rtol=1e-5)
     np.testing.assert_allclose(e["smooth"], g["smooth"], rtol=1e-5)
+    o64 = geonet_loss(oracle64, **oracle_inputs(inp))
+    check_depth_grads(e["grad_depth"], o["grad_depth"], o64["grad_depth"], rtol=1e-4, tag=name)
     for s in range(4):
-        # white-noise frames: sub-threshold discontinuity effects stay in the residual (reference floor 3.4e-5 on the image)
-        ok, rel, frac = close_except_flips(e["grad_depth"][s], o["grad_depth"][s], rtol=1e-3 if noisy else 1e-4,
-                                           max_flip_frac=2e-3 if noisy else 1e-4)
-        assert ok, (s, rel, frac)
         gd = e["grad_depth"][s].astype(np.float64)
         assert abs(np.sqrt((gd ** 2).sum()) - g[f"grad_depth_{s}_l2"]) < 1e-4 * g[f"grad_depth_{s}_l2"]
-    assert rel_l2(e["grad_poses"], o["grad_poses"]) < (2e-2 if noisy else 1e-3)
-    assert rel_l2(e["grad_poses"], g["grad_poses"]) < (2e-2 if noisy else 1e-3)
+    # pose gradients: 1e-4 against the reference-order oracle on every kind of frame.  Against the reference's own numbers
+    # 1e-4 on band-limited frames; on white-noise frames the reference's fp32 sums are themselves 5e-3 away from the
+    # oracle's (different summation order over 1.1 M pixels of noise): there the bound is 1.5 x that measured deviation.
+    r_o, r_g, port_dev = rel_l2(e["grad_poses"], o["grad_poses"]), rel_l2(e["grad_poses"], g["grad_poses"]), rel_l2(o["grad_poses"], g["grad_poses"])
+    print(f"[pose-grad {name}] vs oracle {r_o:.2e}, vs reference golden {r_g:.2e} (oracle vs golden {port_dev:.2e})")
+    assert r_o < 1e-4
+    assert r_g < (max(1e-4, 1.5 * port_dev) if noisy else 1e-4)
 
 
-def test_fused_masks_border_and_flags(oracle32):
+def test_fused_masks_border_and_flags(oracle32, oracle64):
     from oracle.compose import geonet_loss
     from snde_b200.synthetic import make_inputs
     inp = make_inputs(**CASES["small_smooth"])
@@ -105,9 +108,7 @@ def test_fused_masks_border_and_flags(oracle32):
     e = _fused(inp, masks=[(_t(a), _t(b)) for a, b in masks])
     o = geonet_loss(oracle32, **oracle_inputs(inp), masks=masks)
     assert abs(e["loss_total"] - o["loss_total"]) < 1e-5 * abs(o["loss_total"])
-    for s in range(inp.num_scales):
-        ok, rel, frac = close_except_flips(e["grad_depth"][s], o["grad_depth"][s], max_flip_frac=2e-3)
-        assert ok, (s, rel, frac)
+    check_depth_grads(e["grad_depth"], o["grad_depth"], geonet_loss(oracle64, **oracle_inputs(inp), masks=masks)["grad_depth"], tag="masks")
     ep, es, et = _fused(inp, no_smooth=True), _fused(inp, no_photo=True), _fused(inp)
     assert abs(ep["loss_total"] + es["loss_total"] - et["loss_total"]) < 1e-5
     for s in range(inp.num_scales):
@@ -232,7 +233,7 @@ def test_compute_rigid_flow(rev):
 
 
 @pytest.mark.parametrize("name", SMALL)
-def test_reference_call_sequence_matches_golden(name):
+def test_reference_call_sequence_matches_golden(oracle64, name):
     """The reference's own composition (models/baseline.py:895-970, 1125-1161) written with the drop-in names."""
     from snde_b200.loss_functions import image_similarity, smooth_loss
     from snde_b200.synthetic import make_inputs
@@ -257,9 +258,9 @@ def test_reference_call_sequence_matches_golden(name):
     total = rigid + smooth
     total.backward()
     assert abs(total.item() - g["loss_total"]) < 1e-5 * abs(g["loss_total"])
-    for s in range(ns):
-        ok, rel, frac = close_except_flips(depth[s].grad.cpu().numpy(), g[f"grad_depth_{s}"], max_flip_frac=2e-3)
-        assert ok, (s, rel, frac)
+    from oracle.compose import geonet_loss
+    o64 = geonet_loss(oracle64, **oracle_inputs(make_inputs(**CASES[name])))
+    check_depth_grads([depth[s].grad.cpu().numpy() for s in range(ns)], [g[f"grad_depth_{s}"] for s in range(ns)], o64["grad_depth"], tag="by-name " + name)
     assert rel_l2(poses.grad.cpu().numpy(), g["grad_poses"]) < 1e-4
 
 
@@ -289,6 +290,70 @@ def test_inverse_warp_and_border_mode():
     ref = F.grid_sample(inp.src_pyr[0], grid, mode="bilinear", padding_mode="border", align_corners=True).permute(0, 2, 3, 1)
     assert (wb - ref).abs().max() < 2e-5
     assert torch.equal(vb, ((x >= 0) & (x <= 39) & (y >= 0) & (y <= 23)).float())
+
+
+@pytest.mark.parametrize("name", SMALL + ["config1_smooth"])
+def test_photometric_reconstruction_loss_matches_reference_loss_rigid_warp(oracle32, oracle64, name):
+    """The north-star entry point: == the reference's loss_rigid_warp (models/baseline.py:960-970 composed by :1126-1129),
+    both directions, all scales; gradients == the photometric part of loss_total.backward()."""
+    from oracle.compose import geonet_loss
+    from snde_b200.loss_functions import photometric_reconstruction_loss
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**CASES[name])
+    g = load_golden(name)
+    d = inp.to(DEV)
+    depth = [t.clone().requires_grad_(True) for t in d.depth_pyr]
+    poses = d.poses.clone().requires_grad_(True)
+    loss = photometric_reconstruction_loss(d.tgt_pyr, d.src_pyr, d.K_ms, depth, poses)
+    assert loss.dim() == 0
+    assert abs(loss.item() - g["loss_rigid_warp"]) < 1e-5 * abs(g["loss_rigid_warp"])
+    loss.backward()
+    o = geonet_loss(oracle32, **oracle_inputs(inp), w_smooth=0.0)
+    o64 = geonet_loss(oracle64, **oracle_inputs(inp), w_smooth=0.0)
+    assert abs(loss.item() - o["loss_total"]) < 1e-5 * abs(o["loss_total"])
+    check_depth_grads([t.grad.cpu().numpy() for t in depth], o["grad_depth"], o64["grad_depth"], tag="photometric " + name)
+    assert rel_l2(poses.grad.cpu().numpy(), o["grad_poses"]) < 1e-4
+    # weight scales the loss and its gradients linearly; alpha = 0 leaves the L1 term alone
+    with torch.no_grad():
+        l2 = photometric_reconstruction_loss(d.tgt_pyr, d.src_pyr, d.K_ms, d.depth_pyr, d.poses, weight=2.5)
+        l1 = photometric_reconstruction_loss(d.tgt_pyr, d.src_pyr, d.K_ms, d.depth_pyr, d.poses, alpha=0.0)
+    assert abs(l2.item() - 2.5 * loss.item()) < 1e-5 * abs(l2.item())
+    oa = geonet_loss(oracle32, **oracle_inputs(inp), w_smooth=0.0, alpha=0.0, want_grad=False)
+    assert abs(l1.item() - oa["loss_total"]) < 1e-5 * abs(oa["loss_total"])
+
+
+def test_photometric_reconstruction_loss_with_explainability_mask(oracle32, oracle64):
+    """explainability_mask multiplies the per-pixel error before the mean (no reference implementation exists: PoseNet has
+    no mask head, models/PoseNet.py:31 -- pinned by the oracle's restatement).  A mask of ones changes nothing; a mask of
+    zeros on one direction removes that direction's loss and gradient."""
+    from oracle.compose import geonet_loss
+    from snde_b200.loss_functions import photometric_reconstruction_loss
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**CASES["small_smooth"])
+    d = inp.to(DEV)
+    rng = np.random.default_rng(17)
+    masks = []
+    for s in range(inp.num_scales):
+        _, _, h, w = inp.tgt_pyr[s].shape
+        masks.append((rng.random((inp.B * inp.S, h, w), np.float32), rng.random((inp.B * inp.S, h, w), np.float32)))
+    depth = [t.clone().requires_grad_(True) for t in d.depth_pyr]
+    poses = d.poses.clone().requires_grad_(True)
+    loss = photometric_reconstruction_loss(d.tgt_pyr, d.src_pyr, d.K_ms, depth, poses, explainability_mask=[(_t(a), _t(b)) for a, b in masks])
+    loss.backward()
+    o = geonet_loss(oracle32, **oracle_inputs(inp), w_smooth=0.0, masks=masks)
+    o64 = geonet_loss(oracle64, **oracle_inputs(inp), w_smooth=0.0, masks=masks)
+    assert abs(loss.item() - o["loss_total"]) < 1e-5 * abs(o["loss_total"])
+    check_depth_grads([t.grad.cpu().numpy() for t in depth], o["grad_depth"], o64["grad_depth"], tag="photometric + mask")
+    assert rel_l2(poses.grad.cpu().numpy(), o["grad_poses"]) < 1e-4
+    ones = [(torch.ones(inp.B * inp.S, *t.shape[2:], device=DEV),) * 2 for t in d.tgt_pyr]
+    with torch.no_grad():
+        plain = photometric_reconstruction_loss(d.tgt_pyr, d.src_pyr, d.K_ms, d.depth_pyr, d.poses)
+        with_ones = photometric_reconstruction_loss(d.tgt_pyr, d.src_pyr, d.K_ms, d.depth_pyr, d.poses, explainability_mask=ones)
+        fwd_only = photometric_reconstruction_loss(d.tgt_pyr, d.src_pyr, d.K_ms, d.depth_pyr, d.poses,
+                                                   explainability_mask=[(a, torch.zeros_like(b)) for a, b in ones])
+    assert abs(plain.item() - with_ones.item()) < 1e-6 * abs(plain.item())
+    ref = geonet_loss(oracle32, **oracle_inputs(inp), w_smooth=0.0, want_grad=False)
+    assert abs(fwd_only.item() - float(sum(ref["fwd_mean"]))) < 1e-5 * abs(fwd_only.item())       # weight * S/2 = 1 at S = 2
 
 
 def test_large_batch_indices_beyond_2_pow_24():
@@ -331,7 +396,7 @@ def test_lean_instance_equals_general_instance(name):
     assert rel_l2(a["grad_poses"], b["grad_poses"]) < 1e-5
 
 
-def test_lean_instance_config1_vs_golden(oracle32):
+def test_lean_instance_config1_vs_golden(oracle32, oracle64):
     from oracle.compose import geonet_loss
     from snde_b200.synthetic import make_inputs
     inp = make_inputs(**CASES["config1_smooth"])
@@ -342,25 +407,61 @@ def test_lean_instance_config1_vs_golden(oracle32):
     np.testing.assert_allclose(e["fwd_mean"], g["fwd_mean"], rtol=1e-5)
     np.testing.assert_allclose(e["bwd_mean"], g["bwd_mean"], rtol=1e-5)
     np.testing.assert_allclose(e["smooth"], g["smooth"], rtol=1e-5)
-    for s in range(4):
-        ok, rel, frac = close_except_flips(e["grad_depth"][s], o["grad_depth"][s])
-        assert ok, (s, rel, frac)
-    assert rel_l2(e["grad_poses"], g["grad_poses"]) < 1e-3
+    check_depth_grads(e["grad_depth"], o["grad_depth"], geonet_loss(oracle64, **oracle_inputs(inp))["grad_depth"], tag="lean config1_smooth")
+    r = rel_l2(e["grad_poses"], g["grad_poses"])
+    print(f"[pose-grad lean config1_smooth] vs reference golden {r:.2e}")
+    assert r < 1e-4
 
 
 @pytest.mark.parametrize("shape", [dict(B=1, S=2, H=480, W=640, num_scales=4, intrinsics="nyu"),      # BASELINE config 3 shape
                                    dict(B=1, S=4, H=376, W=1248, num_scales=4, intrinsics="kitti")])   # config 4 shape (S = 4)
-def test_lean_instance_other_baseline_shapes_vs_oracle(oracle32, shape):
+def test_lean_instance_other_baseline_shapes_vs_oracle(oracle32, oracle64, shape):
     from oracle.compose import geonet_loss
     from snde_b200.synthetic import make_inputs
     inp = make_inputs(seed=21, smooth=True, motion="small", **shape)
     e = _fused_lean(inp)
     o = geonet_loss(oracle32, **oracle_inputs(inp))
     assert abs(e["loss_total"] - o["loss_total"]) < 1e-5 * abs(o["loss_total"])
+    check_depth_grads(e["grad_depth"], o["grad_depth"], geonet_loss(oracle64, **oracle_inputs(inp))["grad_depth"], tag=str(shape["H"]))
+    r = rel_l2(e["grad_poses"], o["grad_poses"])
+    print(f"[pose-grad {shape['H']}x{shape['W']} B=1] vs oracle {r:.2e}")
+    assert r < 1e-4
+
+
+@pytest.mark.parametrize("name", sorted(FULL))
+def test_headline_sizes_vs_oracle_and_reference_golden(oracle32, oracle64, name):
+    """The BASELINE shapes at the sizes bench.py times them, exactly as bench.py runs them (lean <GRAD, FAST> instance, the
+    segment height the library picks at that size): config 2 (B=32: 64-row segments, 2,016 tasks), config 3 shape (NYU, B=8)
+    and config 4's per-GPU shard (376x1248, S=4, B=8), each against the fp32 oracle AND against the reference's own output
+    at that size (tests/golden/<name>.npz, generated by make_golden.py --round2)."""
+    from oracle.compose import geonet_loss
+    from snde_b200 import ops
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**FULL[name])
+    d = inp.to(DEV)
+    plan = ops.FusedLossPlan(d.tgt_pyr, d.src_pyr, d.depth_pyr, d.poses, d.K_ms, want_grad=True)
+    if name == "config2_smooth":
+        assert plan.num_tiles == 2016                  # 64-row segments: the decomposition bench.py's headline number runs
+    e = _fused_lean(inp)
+    o = geonet_loss(oracle32, **oracle_inputs(inp))
+    o64 = geonet_loss(oracle64, **oracle_inputs(inp))
+    g = load_golden(name)
+    assert abs(e["loss_total"] - o["loss_total"]) < 1e-5 * abs(o["loss_total"])
+    assert abs(e["loss_total"] - g["loss_total"]) < 1e-5 * abs(g["loss_total"])
+    np.testing.assert_allclose(e["fwd_mean"], g["fwd_mean"], rtol=1e-5)
+    np.testing.assert_allclose(e["bwd_mean"], g["bwd_mean"], rtol=1e-5)
+    np.testing.assert_allclose(e["smooth"], g["smooth"], rtol=1e-5)
+    check_depth_grads(e["grad_depth"], o["grad_depth"], o64["grad_depth"], rtol=1e-4, tag=name)
     for s in range(inp.num_scales):
-        ok, rel, frac = close_except_flips(e["grad_depth"][s], o["grad_depth"][s])
-        assert ok, (s, rel, frac)
-    assert rel_l2(e["grad_poses"], o["grad_poses"]) < 1e-3
+        gd = e["grad_depth"][s].astype(np.float64)
+        assert abs(np.sqrt((gd ** 2).sum()) - g[f"grad_depth_{s}_l2"]) < 1e-4 * g[f"grad_depth_{s}_l2"]
+    # pose gradients: 1e-4 against the reference-order oracle; against the reference's own numbers 1e-4 unless the
+    # reference's fp32 sums over these millions of pixels are themselves further than that from exact arithmetic
+    r_o, r_g = rel_l2(e["grad_poses"], o["grad_poses"]), rel_l2(e["grad_poses"], g["grad_poses"])
+    tol_g = pose_grad_tolerance(g["grad_poses"], o64["grad_poses"])
+    print(f"[pose-grad {name}] vs oracle {r_o:.2e} (<= 1e-4), vs reference golden {r_g:.2e} (<= {tol_g:.2e}: the reference's own distance from fp64)")
+    assert r_o < 1e-4
+    assert r_g < tol_g
 
 
 @pytest.mark.parametrize("cfg", [dict(B=32, S=2, H=128, W=416, num_scales=4),                          # config 2, full size
@@ -513,7 +614,7 @@ def test_disparity_input_matches_autograd_through_reciprocal(case):
     assert rel_l2(poses_b.grad.cpu().numpy(), poses_a.grad.cpu().numpy()) < 1e-6
 
 
-def test_odd_sizes_and_unaligned_views_on_hardware(oracle32):
+def test_odd_sizes_and_unaligned_views_on_hardware(oracle32, oracle64):
     """odd width / height and a depth slice with an odd storage offset: the generic instances (4-byte asynchronous row
     copies, scalar stores) on the GPU, against the oracle"""
     from oracle.compose import geonet_loss
@@ -528,19 +629,18 @@ def test_odd_sizes_and_unaligned_views_on_hardware(oracle32):
         big[3:] = t.reshape(-1)
         depth.append(big[3:].view(t.shape))
     o = geonet_loss(oracle32, **oracle_inputs(inp))
+    o64 = geonet_loss(oracle64, **oracle_inputs(inp))
     for want_K in (False, True):
         plan = ops.FusedLossPlan(d.tgt_pyr, d.src_pyr, depth, d.poses, d.K_ms, want_grad=True, want_grad_K=want_K)
         plan.run()
         torch.cuda.synchronize()
         assert abs(plan.loss_out[0].item() - o["loss_total"]) < 1e-5 * abs(o["loss_total"])
-        for s in range(inp.num_scales):
-            ok, rel, frac = close_except_flips(plan.grad_depth[s].cpu().numpy(), o["grad_depth"][s], max_flip_frac=2e-3)
-            assert ok, (s, rel, frac)
+        check_depth_grads([t.cpu().numpy() for t in plan.grad_depth], o["grad_depth"], o64["grad_depth"], tag="odd sizes")
         assert rel_l2(plan.grad_poses.cpu().numpy(), o["grad_poses"]) < 1e-4
 
 
 @pytest.mark.parametrize("seed", range(6))
-def test_random_shapes_on_hardware(oracle32, seed):
+def test_random_shapes_on_hardware(oracle32, oracle64, seed):
     """random small shapes (w below / just over a strip, h below a segment, S from 1 to 4, odd sizes) against the oracle"""
     from oracle.compose import geonet_loss
     from snde_b200 import ops
@@ -557,12 +657,15 @@ def test_random_shapes_on_hardware(oracle32, seed):
     torch.cuda.synchronize()
     o = geonet_loss(oracle32, **oracle_inputs(inp))
     assert abs(plan.loss_out[0].item() - o["loss_total"]) < 1e-5 * abs(o["loss_total"]), (B, S, H, W, ns)
-    for s in range(inp.num_scales):
-        g = plan.grad_depth[s].cpu().numpy()
-        assert not np.isnan(g).any()
-        ok, rel, frac = close_except_flips(g, o["grad_depth"][s], max_flip_frac=5e-3)
-        assert ok, (s, rel, frac, (B, S, H, W, ns))
-    assert rel_l2(plan.grad_poses.cpu().numpy(), o["grad_poses"]) < 2e-4
+    o64 = geonet_loss(oracle64, **oracle_inputs(inp))
+    got = [t.cpu().numpy() for t in plan.grad_depth]
+    assert not any(np.isnan(g).any() for g in got)
+    check_depth_grads(got, o["grad_depth"], o64["grad_depth"], tag=f"random {(B, S, H, W, ns)}")
+    # (large-motion cases leave few pixels in view: the pose gradient is a small sum with a high fp32 floor)
+    r = rel_l2(plan.grad_poses.cpu().numpy(), o["grad_poses"])
+    tol = pose_grad_tolerance(o["grad_poses"], o64["grad_poses"])
+    print(f"[pose-grad random {(B, S, H, W, ns)}] vs oracle {r:.2e} (<= {tol:.2e})")
+    assert r < tol
 
 
 def test_deterministic_image_gradient_mode():
