@@ -1,21 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- warped-pixel fwd+bwd per second of the fused rigid-warp + photometric + smoothness loss.
+"""bench.py -- warped-pixel fwd+bwd per second of the fused rigid-warp + photometric + smoothness loss, and the training step
+around it.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2|config1|nyu]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one fused fwd+bwd of the whole loss (all scales, both directions, smoothness) over one batch of
-synthetic KITTI-shaped frames (BASELINE.json configs[1]: 128x416, B=32 per GPU, S=2, 4 scales).
-  value  : warped pixels / s with inputs resident in HBM (CUDA-graph replay of the C-ABI call, 4 rotating
-           input sets = 540 MB > L2, CUDA events, max over ranks).
-  e2e    : same metric through the public autograd API (snde_b200.loss_functions.geonet_loss_from_frames + backward) with
-           HOST buffers as the reference's trainer has them: uint8 frames + intrinsics from the DataLoader, depth pyramid +
-           poses from the networks.  Pinned H2D copy of every input, on-device normalisation + pyramid (one kernel per
-           frame set), fused loss, D2H read of loss + all gradients, all inside the timed region (copies and compute of
-           consecutive steps overlap on three streams).
-  roofline : algorithmic bytes (60 B per warped pixel + 36 B per smoothness pixel) / step time.
-  cpu_baseline : oracle/torch_port.py (the reference's ATen op chain restated) on this box's host cores.
---impl reference times that CPU path alone (rank 0 only).
+Workloads (BASELINE.json configs):
+  config2 (default) / config1 / nyu / hires : a "step" is one fused fwd+bwd of the whole loss (all scales, both directions,
+      smoothness) over one batch of synthetic frames (config2 = configs[1]: 128x416, B=32 per GPU, S=2, 4 scales).
+        value    : warped pixels / s with inputs resident in HBM (CUDA-graph replay of the C-ABI call, 4 rotating input
+                   sets > L2, CUDA events, max over ranks).
+        e2e      : same metric through the public autograd API (geonet_loss_from_frames + backward) with HOST buffers as the
+                   reference's trainer has them: ONE pinned staging buffer each way (uint8 frames, intrinsics, depth pyramid
+                   and poses in; loss + every gradient out), one cudaMemcpyAsync per direction and step, copies and compute of
+                   consecutive steps overlapped on three streams, all inside the timed region.
+        roofline : algorithmic bytes (60 B per warped pixel + 36 B per smoothness pixel) / step time, plus
+                   the instruction-issue fraction of the strip kernel.
+        train    : (same line) the full training step of trainer.py on the same shape -- DispNetS + PoseNet (cuDNN), fused
+                   loss, backward, NCCL all-reduce of the 33.2 M network gradients under DDP when N > 1, Adam -- in samples/s.
+        cpu_baseline : oracle/torch_port.py (the reference's ATen op chain restated) on this box's host cores.
+  train_config2 / train_hires : the training step is the headline (metric train_samples_per_sec).  train_hires = config 4:
+      376x1248, S=4, global batch 64 sharded over the N ranks (strong scaling).
+  sweep5 : BASELINE config 5, the stand-alone inverse_warp + photometric_reconstruction_loss sweep through the public API.
+--impl reference times the reference's CPU path alone (rank 0 only).
 """
 import argparse
 import json
@@ -33,6 +40,10 @@ WORKLOADS = {
     "config1": dict(B=4, S=2, H=128, W=416, num_scales=4, intrinsics="kitti"),
     "nyu": dict(B=8, S=2, H=480, W=640, num_scales=4, intrinsics="nyu"),                 # BASELINE config 3 shape
     "hires": dict(B=8, S=4, H=376, W=1248, num_scales=4, intrinsics="kitti"),             # config 4: B=64 sharded over 8 GPUs
+}
+TRAIN_WORKLOADS = {
+    "train_config2": dict(B=32, S=2, H=128, W=416, num_scales=4, intrinsics="kitti", scaling="weak"),       # B per GPU
+    "train_hires": dict(B=64, S=4, H=376, W=1248, num_scales=4, intrinsics="kitti", scaling="strong"),      # global B
 }
 METRIC = "warped_pixel_fwd_bwd_per_sec"
 UNIT = "warped-px/s"
@@ -84,100 +95,173 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(cfg, iters=3, batch=None):
+# =====================================================================================================================
+# the reference's CPU path (oracle/torch_port.py: the one other place bench.py may execute oracle/)
+# =====================================================================================================================
+def cpu_baseline(cfg, iters=3, budget_s=25.0):
+    """bounded sample on all host cores: the full batch when 1 warm-up + `iters` steps fit ~budget_s, else a smaller one"""
     import torch
     from oracle import torch_port
     from snde_b200.synthetic import make_inputs
-    c = dict(cfg)
-    if batch:
-        c["B"] = batch
     torch.set_num_threads(os.cpu_count() or 1)
+    c = dict(cfg)
+    per_sample_s = 0.06 * (cfg["H"] * cfg["W"]) / (128 * 416) * cfg["S"] / 2 * 8 / max(1, min(os.cpu_count() or 1, 16))
+    c["B"] = int(max(1, min(cfg["B"], budget_s / ((iters + 1) * per_sample_s))))
     inp = make_inputs(seed=0, **c)
     sec, _ = torch_port.timed_fwd_bwd(inp, iters=iters, warmup=1)
-    return inp.warped_pixels() / sec, torch.get_num_threads(), f"B={c['B']} S={c['S']} {c['H']}x{c['W']} x{c['num_scales']} scales, 1 warm-up + {iters} timed fwd+bwd, median"
+    sample = f"B={c['B']} of {cfg['B']}, S={c['S']} {c['H']}x{c['W']} x{c['num_scales']} scales, 1 warm-up + {iters} timed fwd+bwd, median"
+    return inp.warped_pixels() / sec, torch.get_num_threads(), sample
 
 
 def run_reference(args, cfg, rank):
     """--impl reference: the reference's CPU implementation of the path (ATen op chain, oracle/torch_port.py) on the
-    host cores.  /root/reference is Python-only and does not travel to the GPU box, hence kind='port'."""
+    host cores.  /root/reference is Python-only and does not travel to the GPU box, hence kind='port' (the port was timed
+    against the imported reference in the authoring container: same time per step, identical loss -- DESIGN.md section 7)."""
     if rank != 0:
         return
     import torch
     from oracle import torch_port
     from snde_b200.synthetic import make_inputs
     torch.set_num_threads(os.cpu_count() or 1)
-    # bounded sample of the same workload per step, sized so that (steps + warmup) steps take ~2 minutes at most
-    per_sample_s = 0.07 * (cfg["H"] * cfg["W"]) / (128 * 416)
-    c = dict(cfg); c["B"] = int(max(1, min(cfg["B"], 8, 120.0 / ((args.steps + args.warmup) * per_sample_s))))
-    inp = make_inputs(seed=0, **c)
-    depth = [d.clone().requires_grad_(True) for d in inp.depth_pyr]
-    poses = inp.poses.clone().requires_grad_(True)
+    train = args.workload in TRAIN_WORKLOADS
+    # the full batch of the workload when (steps + warmup) steps fit ~150 s of CPU time, else a bounded sample of it
+    cores = max(1, min(os.cpu_count() or 1, 16))
+    per_sample_s = (0.35 if train else 0.085) * (cfg["H"] * cfg["W"]) / (128 * 416) * cfg["S"] / 2 * 8 / cores
+    budget_s = 150.0
+    c = dict(cfg)
+    c["B"] = int(max(1, min(cfg["B"], budget_s / ((args.steps + args.warmup) * per_sample_s))))
+    why = "full batch" if c["B"] == cfg["B"] else f"bounded sample: the full B={cfg['B']} would take ~{(args.steps + args.warmup) * per_sample_s * cfg['B']:.0f} s of CPU time for {args.steps}+{args.warmup} steps"
+    inp = make_inputs(seed=0, **{k: v for k, v in c.items() if k != "scaling"})
     to_u8 = lambda x: ((x + 1) * 127.5).round().clamp(0, 255).to(torch.uint8)
     tgt_u8, src_u8 = to_u8(inp.tgt_pyr[0]), to_u8(inp.src_pyr[0])          # what the DataLoader hands over
     ns = c["num_scales"]
-    def step():
-        for t in depth + [poses]:
-            t.grad = None
-        # iter_data_preparation (baseline.py:761-792) + loss path, as in one trainer iteration
-        tgt_pyr, src_pyr = torch_port.frames_to_pyramid(tgt_u8, ns), torch_port.frames_to_pyramid(src_u8, ns)
-        total, _, _ = torch_port.loss_path(tgt_pyr, src_pyr, depth, poses, inp.K_ms)
-        total.backward()
+    if train:
+        # the reference's training iteration: networks + op-chain loss + backward + Adam, on the host cores
+        from snde_b200.trainer import GeoNetTrainer, TrainConfig
+
+        def port_loss(tgt_pyr, src_pyr, disp_pyr, poses, K_ms, tc):
+            total, rigid, smooth = torch_port.loss_path(tgt_pyr, src_pyr, [1.0 / d for d in disp_pyr], poses, K_ms, tc.simi_alpha,
+                                                        tc.loss_weight_rigid_warp, tc.loss_weight_disparity_smooth)
+            return total, torch.stack([total.detach(), rigid.detach(), smooth.detach()])
+        tr = GeoNetTrainer(TrainConfig(num_source=c["S"], num_scales=ns), device=torch.device("cpu"), ddp=False, loss_fn=port_loss)
+        src_b = src_u8.view(c["S"], c["B"], 3, c["H"], c["W"]).transpose(0, 1).reshape(c["B"], 3 * c["S"], c["H"], c["W"]).contiguous()
+        step = lambda: tr.step(tgt_u8, src_b, inp.K)
+        units, metric, unit = c["B"], "train_samples_per_sec", "samples/s"
+    else:
+        depth = [d.clone().requires_grad_(True) for d in inp.depth_pyr]
+        poses = inp.poses.clone().requires_grad_(True)
+
+        def step():
+            for t in depth + [poses]:
+                t.grad = None
+            # iter_data_preparation (baseline.py:761-792) + loss path, as in one trainer iteration
+            tgt_pyr, src_pyr = torch_port.frames_to_pyramid(tgt_u8, ns), torch_port.frames_to_pyramid(src_u8, ns)
+            total, _, _ = torch_port.loss_path(tgt_pyr, src_pyr, depth, poses, inp.K_ms)
+            total.backward()
+        units, metric, unit = inp.warped_pixels(), METRIC, UNIT
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    value = inp.warped_pixels() * args.steps / dt
-    sample = f"B={c['B']} per step (bounded sample of B={cfg['B']}), S={c['S']} {c['H']}x{c['W']} x{c['num_scales']} scales"
+    value = units * args.steps / dt
+    sample = f"B={c['B']} per step ({why}), S={c['S']} {c['H']}x{c['W']} x{ns} scales"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": cfg.get("scaling", "weak"),
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: fused-loss fwd+bwd, " + sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": f"{args.workload}: " + ("training step, " if train else "fused-loss fwd+bwd, ") + sample},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=50)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the end-to-end leg (its keys are then null)")
-    args = ap.parse_args()
-    cfg = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, cfg, rank)
-        return
-    args.warmup = max(args.warmup, 3)
+# =====================================================================================================================
+# helpers shared by the GPU legs
+# =====================================================================================================================
+class Dist:
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    def init(self, dev):
+        import torch.distributed as dist
+        if self.world > 1 and not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=dev)
+
+    def barrier(self, dev):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(self, x, dev):
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def copy_probe(D, dev, mbytes=256, reps=4):
+    """plain pinned-memory copy bandwidth of THIS rank while every rank copies at once (GB/s each way): the ceiling the
+    end-to-end number runs into on a shared host"""
     import torch
-    import torch.distributed as dist
+    h = torch.empty(mbytes << 20, dtype=torch.uint8).pin_memory()
+    d = torch.empty(mbytes << 20, dtype=torch.uint8, device=dev)
+    out = {}
+    for name, (dst, src) in (("h2d_gbs", (d, h)), ("d2h_gbs", (h, d))):
+        dst.copy_(src, non_blocking=True)
+        D.barrier(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        D.barrier(dev)
+        out[name] = round(reps * (mbytes << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9, 2)
+    return out
+
+
+class Staging:
+    """ONE pinned host buffer and one device buffer per direction; typed sub-views on both sides (16-byte aligned)."""
+
+    def __init__(self, specs, dev, pinned_from=None):
+        import torch
+        self.offsets, off = [], 0
+        for shape, dtype in specs:
+            n = 1
+            for v in shape:
+                n *= v
+            nbytes = n * torch.empty((), dtype=dtype).element_size()
+            self.offsets.append((off, nbytes, shape, dtype))
+            off = (off + nbytes + 15) & ~15
+        self.nbytes = off
+        self.host = torch.empty(off, dtype=torch.uint8).pin_memory()
+        self.dev = torch.empty(off, dtype=torch.uint8, device=dev)
+        self.host_views = [self.host[o:o + n].view(dt).view(shape) for o, n, shape, dt in self.offsets]
+        self.dev_views = [self.dev[o:o + n].view(dt).view(shape) for o, n, shape, dt in self.offsets]
+        self.payload = sum(n for _, n, _, _ in self.offsets)
+
+
+# =====================================================================================================================
+# legs
+# =====================================================================================================================
+def loss_leg(args, cfg, D, dev):
+    """device-resident throughput of the fused loss: (ms_per_step, plans, graphs?, clocks)"""
+    import torch
     from snde_b200 import ops
-    from snde_b200.loss_functions import geonet_loss_from_frames
     from snde_b200.synthetic import make_inputs
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    # ---- device-resident: 4 rotating input sets (4 x 135 MB > 126 MB L2), one captured graph each ----
     NSETS = 4
     plans = []
     for i in range(NSETS):
-        d = make_inputs(seed=100 * rank + i, **cfg).to(dev)
+        d = make_inputs(seed=100 * D.rank + i, smooth=args.smooth_inputs, **cfg).to(dev)
         plans.append(ops.FusedLossPlan(d.tgt_pyr, d.src_pyr, d.depth_pyr, d.poses, d.K_ms, want_grad=True))
-    warped_px, algo_bytes = algorithmic_bytes(**cfg)
     stream = torch.cuda.Stream(dev)
     graphs = []
     with torch.cuda.stream(stream):
@@ -190,110 +274,94 @@ def main():
                 with torch.cuda.graph(g, stream=stream):
                     p.run()
                 graphs.append(g)
+
     def step(i):
         if graphs:
             graphs[i % NSETS].replay()
         else:
             plans[i % NSETS].run()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
     with torch.cuda.stream(stream):
-        clocks = ClockSampler(local_rank)
-        if rank == 0:
+        clocks = ClockSampler(D.local_rank)
+        if D.rank == 0:
             clocks.start()                        # samples from here to the end of the timed region (+ probe steps below)
         t_load = time.perf_counter()
         for i in range(args.warmup):
             step(i)
-        barrier()
+        D.barrier(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for i in range(args.steps):
             step(i)
         e1.record(stream)
-        barrier()
+        D.barrier(dev)
         ms = e0.elapsed_time(e1)
         # nvidia-smi samples every 100 ms: keep the same load running (untimed) until >= 1.5 s have been observed
-        while rank == 0 and time.perf_counter() - t_load < 1.5:
+        while D.rank == 0 and time.perf_counter() - t_load < 1.5:
             for i in range(200):
                 step(i)
             torch.cuda.synchronize(dev)
-        clk = clocks.stop() if rank == 0 else None
+        clk = clocks.stop() if D.rank == 0 else None
     loss_check = float(plans[0].loss_out[0].item())
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
-    value = world * warped_px / (ms_per_step * 1e-3)
+    ms = D.max_over_ranks(ms, dev)
+    return ms / args.steps, plans[0].num_tiles, bool(graphs), clk, loss_check, NSETS
 
-    # ---- end to end through the public API with host buffers ----
+
+def e2e_leg(args, cfg, D, dev):
+    """the public autograd API with host buffers: one pinned staging buffer each way"""
+    import torch
+    from snde_b200.loss_functions import geonet_loss_from_frames
+    from snde_b200.synthetic import make_inputs
+    host = make_inputs(seed=7 + D.rank, **cfg)
+    B_, S_, H, W, ns = cfg["B"], cfg["S"], cfg["H"], cfg["W"], cfg["num_scales"]
+    to_u8 = lambda x: ((x + 1) * 127.5).round().clamp(0, 255).to(torch.uint8)
     # host inputs as the reference's DataLoader delivers them (models/baseline.py:746-770): uint8 frames, tgt (B,3,H,W) and
     # src (B,3*S,H,W), intrinsics (B,3,3); plus the network outputs the loss consumes (depth pyramid, poses)
-    host = make_inputs(seed=7 + rank, **cfg)
-    pin = lambda t: t.contiguous().pin_memory()
-    B_, S_ = cfg["B"], cfg["S"]
-    to_u8 = lambda x: ((x + 1) * 127.5).round().clamp(0, 255).to(torch.uint8)
-    h_tgt = pin(to_u8(host.tgt_pyr[0]))
-    h_src = pin(to_u8(host.src_pyr[0]).view(S_, B_, 3, cfg["H"], cfg["W"]).transpose(0, 1).reshape(B_, 3 * S_, cfg["H"], cfg["W"]))
-    h_dep = [pin(t) for t in host.depth_pyr]
-    h_poses, h_K = pin(host.poses), pin(host.K)
-    h2d = sum(t.numel() * t.element_size() for t in [h_tgt, h_src] + h_dep + [h_poses, h_K])
-    out_host = [torch.empty_like(t).pin_memory() for t in h_dep] + [torch.empty_like(host.poses).pin_memory(), torch.empty(3 + 3 * cfg["num_scales"]).pin_memory()]
-    d2h = sum(t.numel() * 4 for t in out_host)
-
-    # Three device input sets and three streams: the H2D copy of step i+1, the fused loss of step i and the D2H read of
-    # step i-1 overlap (every byte still moves every step, inside the timed region).
+    items = [to_u8(host.tgt_pyr[0]), to_u8(host.src_pyr[0]).view(S_, B_, 3, H, W).transpose(0, 1).reshape(B_, 3 * S_, H, W).contiguous()]
+    items += list(host.depth_pyr) + [host.poses, host.K]
     NBUF = int(os.environ.get("SNDE_E2E_NBUF", "2"))
-    dev_in = [dict(tgt=torch.empty_like(h_tgt, device=dev), src=torch.empty_like(h_src, device=dev),
-                   dep=[torch.empty_like(t, device=dev) for t in h_dep], poses=torch.empty_like(h_poses, device=dev),
-                   K=torch.empty_like(h_K, device=dev)) for _ in range(NBUF)]
+    ins = [Staging([(tuple(t.shape), t.dtype) for t in items], dev) for _ in range(NBUF)]
+    for st in ins:
+        for v, t in zip(st.host_views, items):
+            v.copy_(t)
+    out_specs = [(tuple(t.shape), torch.float32) for t in host.depth_pyr] + [(tuple(host.poses.shape), torch.float32), ((3 + 3 * ns,), torch.float32)]
+    outs = [Staging(out_specs, dev) for _ in range(NBUF)]
+    h2d, d2h = ins[0].payload, outs[0].payload
     s_h2d, s_run, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     ev_in = [torch.cuda.Event() for _ in range(NBUF)]      # inputs of set j are on the device
     ev_free = [torch.cuda.Event() for _ in range(NBUF)]    # set j has been consumed
-    ev_res = [torch.cuda.Event() for _ in range(NBUF)]     # results of set j are in their staging buffers
+    ev_res = [torch.cuda.Event() for _ in range(NBUF)]     # results of set j are in their staging buffer
     ev_read = [torch.cuda.Event() for _ in range(NBUF)]    # ... and have been read back
-    # results leave through persistent device staging buffers: the autograd-allocated gradient tensors are released in
-    # stream order on the compute stream (no cross-stream allocator traffic), the D2H copy runs on its own stream
-    stage = [[torch.empty_like(t, device=dev) for t in out_host] for _ in range(NBUF)]
     step_no = [0]
 
     def e2e_step():
         j = step_no[0] % NBUF
         step_no[0] += 1
-        d = dev_in[j]
+        st, so = ins[j], outs[j]
         with torch.cuda.stream(s_h2d):
             s_h2d.wait_event(ev_free[j])
-            d["tgt"].copy_(h_tgt, non_blocking=True)
-            d["src"].copy_(h_src, non_blocking=True)
-            for a, b in zip(d["dep"], h_dep):
-                a.copy_(b, non_blocking=True)
-            d["poses"].copy_(h_poses, non_blocking=True)
-            d["K"].copy_(h_K, non_blocking=True)
+            st.dev.copy_(st.host, non_blocking=True)              # ONE cudaMemcpyAsync for every input of the step
             ev_in[j].record(s_h2d)
         with torch.cuda.stream(s_run):
             s_run.wait_event(ev_in[j])
-            dep = [t.detach().requires_grad_(True) for t in d["dep"]]
-            poses = d["poses"].detach().requires_grad_(True)
-            total, detail = geonet_loss_from_frames(d["tgt"], d["src"], dep, poses, d["K"])
+            v = st.dev_views
+            dep = [t.detach().requires_grad_(True) for t in v[2:2 + ns]]
+            poses = v[2 + ns].detach().requires_grad_(True)
+            total, detail = geonet_loss_from_frames(v[0], v[1], dep, poses, v[3 + ns], unit_upstream=True)
             total.backward()
-            s_run.wait_event(ev_read[j])                       # the staging set of two steps ago has been read back
-            torch._foreach_copy_(stage[j], [t.grad for t in dep] + [poses.grad, detail])
+            s_run.wait_event(ev_read[j])                          # the staging set of NBUF steps ago has been read back
+            torch._foreach_copy_(so.dev_views, [t.grad for t in dep] + [poses.grad, detail])
             ev_free[j].record(s_run)
             ev_res[j].record(s_run)
         with torch.cuda.stream(s_d2h):
             s_d2h.wait_event(ev_res[j])
-            for o, g in zip(out_host, stage[j]):
-                o.copy_(g, non_blocking=True)
+            so.host.copy_(so.dev, non_blocking=True)              # ONE cudaMemcpyAsync for the loss and every gradient
             ev_read[j].record(s_d2h)
 
-    e2e_steps = 0 if args.no_e2e else max(5, min(args.steps, 100))
-    for _ in range(3 if e2e_steps else 0):
+    e2e_steps = max(5, min(args.steps, 100))
+    for _ in range(3):
         e2e_step()
-    barrier()
+    D.barrier(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cur = torch.cuda.current_stream(dev)
     e0.record(cur)
@@ -304,52 +372,238 @@ def main():
     for s_ in (s_h2d, s_run, s_d2h):
         cur.wait_stream(s_)
     e1.record(cur)
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = world * warped_px * e2e_steps / (e2e_ms * 1e-3) if e2e_steps else None
-    e2e_loss = float(out_host[-1][0]) if e2e_steps else None
+    D.barrier(dev)
+    e2e_ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
+    warped_px, _ = algorithmic_bytes(**cfg)
+    last = outs[(step_no[0] - 1) % NBUF]
+    probe = copy_probe(D, dev)
+    return {"value": D.world * warped_px * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "loss_check": float(last.host_views[-1][0]),
+            "copies_per_step": {"h2d": 1, "d2h": 1},
+            "copy_probe": dict(probe, note="plain 256 MB pinned copies by this rank while every rank copies at once; "
+                                           f"floor of this step = {h2d / probe['h2d_gbs'] / 1e6:.3f} ms (H2D) / {d2h / probe['d2h_gbs'] / 1e6:.3f} ms (D2H, overlapped)")}
 
-    if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+def train_leg(args, tcfg, D, dev, steps, warmup):
+    """the full training step (trainer.py): uint8 frames from pinned host memory every step, networks, fused loss,
+    backward (+ NCCL all-reduce under DDP), Adam; a D2H read of the loss scalars every step"""
+    import torch
+    from snde_b200.trainer import GeoNetTrainer, TrainConfig
+    S, H, W, ns = tcfg["S"], tcfg["H"], tcfg["W"], tcfg["num_scales"]
+    if tcfg.get("scaling") == "strong":
+        if tcfg["B"] % D.world:
+            raise SystemExit(f"global batch {tcfg['B']} does not divide over {D.world} ranks")
+        B_local, B_global = tcfg["B"] // D.world, tcfg["B"]
+    else:
+        B_local, B_global = tcfg["B"], tcfg["B"] * D.world
+    g = torch.Generator().manual_seed(1234 + D.rank)
+    h_frames = torch.randint(0, 256, (B_local, 3 * (1 + S), H, W), generator=g, dtype=torch.uint8).pin_memory()
+    K1 = torch.tensor([[0.58 * W, 0, 0.5 * W], [0, 1.92 * H, 0.5 * H], [0, 0, 1]])
+    h_K = K1.repeat(B_local, 1, 1).pin_memory()
+    d_frames = [torch.empty_like(h_frames, device=dev) for _ in range(2)]
+    d_K = torch.empty_like(h_K, device=dev)
+    h_loss = torch.empty(3).pin_memory()
+    tr = GeoNetTrainer(TrainConfig(num_source=S, num_scales=ns), device=dev)
+    d_K.copy_(h_K)
+
+    def step(i):
+        fr = d_frames[i % 2]
+        fr.copy_(h_frames, non_blocking=True)                      # H2D of the step's frames (pinned)
+        out = tr.step(fr[:, :3], fr[:, 3:], d_K)
+        h_loss.copy_(torch.stack([out["loss_total"], out["loss_rigid_warp"], out["loss_disp_smooth"]]), non_blocking=True)
+
+    torch.cuda.reset_peak_memory_stats(dev)
+    for i in range(max(3, warmup)):
+        step(i)
+    D.barrier(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    D.barrier(dev)
+    ms = D.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    ddp = tr.model is not tr.nets
+    return {"samples_per_s": B_global / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "steps": steps, "global_batch": B_global,
+            "batch_per_gpu": B_local, "scaling": tcfg.get("scaling", "weak"), "shape": f"{H}x{W}, S={S}, {ns} scales",
+            "ddp": ddp, "backend": "nccl" if ddp else None, "allreduce_bytes_per_step": tr.gradient_bytes() if ddp else 0,
+            "parameters": tr.gradient_bytes() // 4, "h2d_bytes_per_step": h_frames.numel(), "d2h_bytes_per_step": 12,
+            "loss_check": float(h_loss[0]), "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2),
+            "conv_math": "fp32 storage, cuDNN default (TF32 allowed: torch.backends.cudnn.allow_tf32=%s, the reference's own default)" % torch.backends.cudnn.allow_tf32,
+            "optimizer": "Adam lr 2e-4 (stepped every iteration)"}
+
+
+def sweep5(args, D, dev):
+    """BASELINE config 5 through the north-star API: inverse_warp (one direction, warped image materialised) fwd+bwd and
+    photometric_reconstruction_loss (both directions, fused, smoothness off) fwd+bwd; single scale, S = 1."""
+    import torch
+    from snde_b200.loss_functions import inverse_warp, photometric_reconstruction_loss
+    from snde_b200.synthetic import make_inputs
+    rows = []
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) * 1e3 / n
+
+    for H, W in ((128, 416), (256, 832), (512, 1024), (1024, 2048)):
+        for B in (1, 8, 64):
+            inp = make_inputs(B=B, S=1, H=H, W=W, num_scales=1, seed=B, smooth=False).to(dev)
+            n = 20 if H * W * B < 5e7 else 4
+            img = inp.src_pyr[0].permute(0, 2, 3, 1)
+            gout = torch.randn(B, H, W, 3, device=dev)
+            for pad in ("zeros", "border"):
+                depth = inp.depth_pyr[0][:B].clone().requires_grad_(True)
+                pose = inp.poses[:, 0].clone().requires_grad_(True)
+
+                def warp_only():
+                    depth.grad = pose.grad = None
+                    warped, valid = inverse_warp(img, depth, pose, inp.K, False, pad)
+                    warped.backward(gout)
+                dep = [inp.depth_pyr[0].clone().requires_grad_(True)]
+                poses = inp.poses.clone().requires_grad_(True)
+
+                def photo():
+                    dep[0].grad = poses.grad = None
+                    photometric_reconstruction_loss(inp.tgt_pyr, inp.src_pyr, inp.K_ms, dep, poses, padding_mode=pad).backward()
+                us_w, us_p = timed(warp_only, n), timed(photo, n)
+                rows.append({"HxW": f"{H}x{W}", "B": B, "padding": pad, "inverse_warp_us": round(us_w, 1),
+                             "inverse_warp_gpx_s": round(B * H * W / us_w / 1e3, 2),
+                             "photometric_us": round(us_p, 1), "photometric_gpx_s": round(2 * B * H * W / us_p / 1e3, 2),
+                             "photometric_algorithmic_gbs": round(60 * 2 * B * H * W / us_p / 1e3, 0)})
+            del inp
+            torch.cuda.empty_cache()
+    return rows
+
+
+# =====================================================================================================================
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS) + ["sweep5"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the end-to-end leg (its keys are then null)")
+    ap.add_argument("--no-train", action="store_true", help="tuning runs only: skip the training-step leg of the default line")
+    ap.add_argument("--train-steps", type=int, default=0, help="steps of the training leg (default: min(steps, 20))")
+    ap.add_argument("--smooth-inputs", action="store_true", help="diagnostic only: band-limited frames and depth (coalesced gathers) instead of the SURVEY 8(d) white-noise generator")
+    args = ap.parse_args()
+    D = Dist()
+    train_only = args.workload in TRAIN_WORKLOADS
+    cfg = TRAIN_WORKLOADS[args.workload] if train_only else WORKLOADS.get(args.workload, WORKLOADS["config2"])
+    if args.impl == "reference":
+        run_reference(args, cfg, D.rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    torch.cuda.set_device(D.local_rank)
+    dev = torch.device("cuda", D.local_rank)
+    D.init(dev)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    if args.workload == "sweep5":
+        rows = sweep5(args, D, dev)
+        if D.rank == 0:
+            ref = [r for r in rows if r["HxW"] == "128x416" and r["B"] == 64 and r["padding"] == "zeros"][0]
+            print(json.dumps({"metric": METRIC, "value": ref["photometric_gpx_s"] * 1e9, "unit": UNIT, "n_gpus": 1, "steps": 20, "warmup": 3,
+                              "ms_per_step": ref["photometric_us"] * 1e-3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                              "dtype": "f32", "data": "synthetic",
+                              "config": {"workload": "sweep5: stand-alone inverse_warp and photometric_reconstruction_loss (public API, fwd+bwd, single scale, S=1), "
+                                                     "128x416..1024x2048, B=1/8/64, zeros vs border padding; value = 128x416 B=64 zeros photometric"},
+                              "sweep": rows}))
+        return
+
+    if train_only:
+        steps = args.train_steps or min(args.steps, 20)
+        clocks = ClockSampler(D.local_rank)
+        if D.rank == 0:
+            clocks.start()
+        tr = train_leg(args, cfg, D, dev, steps, min(args.warmup, 5))
+        clk = clocks.stop() if D.rank == 0 else None
+        if D.rank == 0:
+            # the loss kernel's share of the step, from its device-resident time at this shape
+            line = {"metric": "train_samples_per_sec", "value": tr["samples_per_s"], "unit": "samples/s", "n_gpus": D.world, "steps": steps,
+                    "warmup": max(3, min(args.warmup, 5)), "ms_per_step": tr["ms_per_step"], "higher_is_better": True, "scaling": tr["scaling"],
+                    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": f"{args.workload}: full training step (DispNetS + PoseNet in cuDNN, fused loss, backward, "
+                                           f"{'NCCL all-reduce of %d gradient bytes (DDP), ' % tr['allreduce_bytes_per_step'] if tr['ddp'] else ''}Adam), "
+                                           f"global batch {tr['global_batch']} ({tr['batch_per_gpu']} per GPU), {tr['shape']}",
+                               "parallelism": f"dp{D.world}"},
+                    "clocks": clk, "train": tr,
+                    "e2e": {"value": tr["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": tr["h2d_bytes_per_step"],
+                            "d2h_bytes_per_step": tr["d2h_bytes_per_step"], "note": "the training step IS end to end: frames come from pinned host memory every step, the loss scalars go back"},
+                    "gpu_launches": (1 + cfg["S"] + 3) * steps, "gpu_launches_note": "own kernels per step: 1 + S frames_to_pyramid, loss prep + strip + finalize; the networks are cuDNN/ATen"}
+            print(json.dumps(line))
+        if D.world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
+    # ---- the fused loss: device-resident, then end to end, then the training step around it ----
+    ms_per_step, num_tiles, graphed, clk, loss_check, NSETS = loss_leg(args, cfg, D, dev)
+    warped_px, algo_bytes = algorithmic_bytes(**cfg)
+    value = D.world * warped_px / (ms_per_step * 1e-3)
+    e2e = e2e_leg(args, cfg, D, dev) if not args.no_e2e else {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None}
+    train = None
+    if not args.no_train and args.workload == "config2":
+        torch.cuda.empty_cache()
+        train = train_leg(args, TRAIN_WORKLOADS["train_config2"], D, dev, args.train_steps or min(args.steps, 20), 3)
+
+    if D.rank == 0:
         achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of the strip kernel, one launch, from the committed ncu capture
-        traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        # per-launch counters of the strip kernel from the committed ncu capture of this workload
+        prof = {}
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if tj.get("workload") == args.workload:
-                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+            prof = tj.get(args.workload, {})
+        clk_mhz = (clk or {}).get("sm_mhz") or (clk or {}).get("sm_max_mhz") or 1965.0
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        issue_frac = prof["warp_instructions_per_launch"] / (sms * 4 * clk_mhz * 1e6 * ms_per_step * 1e-3) if prof.get("warp_instructions_per_launch") else None
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": D.world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: fused rigid-warp+SSIM/L1+smoothness loss fwd+bwd, B={cfg['B']} per GPU, S={cfg['S']}, "
                                    f"{cfg['H']}x{cfg['W']}, {cfg['num_scales']} scales", "warped_px_per_step_per_gpu": warped_px,
-                       "l2": f"{NSETS} rotating input sets ({NSETS} x {plans[0].num_tiles} tiles, > L2)", "cuda_graph": bool(graphs),
-                       "parallelism": f"dp{world} (batch sharded, no data-path collective)", "loss_check": loss_check},
+                       "l2": f"{NSETS} rotating input sets ({NSETS} x {num_tiles} tiles, > L2)", "cuda_graph": graphed,
+                       "parallelism": f"dp{D.world} (batch sharded; no collective in the loss path, NCCL all-reduce in the training leg)",
+                       "loss_check": loss_check},
             "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "ms_per_step": e2e_ms / e2e_steps if e2e_steps else None, "loss_check": e2e_loss},
+            "e2e": e2e,
             "gpu_launches": 3 * args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_step": algo_bytes, "traffic_source": traffic_src,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": prof.get("dram_bytes_per_launch"), "issue_frac": issue_frac,
+                         "issue_note": "issue_frac = warp-instructions of one strip-kernel launch (ncu, profiles/) / (SMs x 4 schedulers x SM clock x step time): "
+                                       "the share of all issue slots the kernel fills; the kernel is bound there and by dependent-issue latency, not by HBM",
+                         "peak_source": peak_src, "algorithmic_bytes_per_step": algo_bytes, "traffic_source": prof.get("source"),
                          "note": "duration = whole step (prep + strip kernel + finalize); the strip kernel is 98% of it "
                                  "(profiles/). Bytes per SURVEY 8(d): 60 B/warped px + 36 B/smooth px, as for separate fwd and bwd "
-                                 "passes; the single-pass kernel moves less and is bound by instruction issue and dependent-issue latency (DESIGN.md section 5)."},
+                                 "passes; the single-pass kernel moves less (traffic) -- DESIGN.md section 5."},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            v, cores, sample = cpu_baseline(cfg, iters=3, batch=min(cfg["B"], 8))
+        if train is not None:
+            line["train"] = train
+        if D.world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_baseline(cfg, iters=3)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))
-    if world > 1:
+    if D.world > 1:
+        import torch.distributed as dist
         dist.destroy_process_group()
 
 

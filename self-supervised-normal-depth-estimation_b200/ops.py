@@ -58,27 +58,35 @@ def map_nhw(t: torch.Tensor) -> _abi.SndeMap:
 # fused loss
 # ------------------------------------------------------------------------------------------------
 class FusedLossPlan:
-    """Pre-marshalled arguments + persistent output/workspace buffers of one fused-loss call shape.
+    """Pre-marshalled arguments + output/workspace buffers of one fused-loss call SHAPE.
 
-    Re-using a plan keeps every device pointer fixed, which is what CUDA-graph capture needs, and
-    takes the ctypes marshalling off the per-step path.  Inputs are read from the tensors given at
-    construction (update them in place); outputs live in ``loss_out``, ``grad_depth``, ``grad_poses``.
+    Two ways to use it:
+      * static (CUDA-graph style, bench.py, tests): construct once on fixed input tensors, ``run()`` any number of times;
+        outputs live in ``loss_out``, ``grad_depth``, ``grad_poses`` (rewritten by every run).  The plan keeps the input
+        tensors alive in this mode only.
+      * rebinding (the autograd path, a trainer whose depth / poses are fresh network outputs every step): ``rebind(...)``
+        patches the pointer fields of the cached ``SndeLossArgs`` for tensors of the SAME shapes and strides -- a few ctypes
+        stores, no allocation, no marshalling -- and ``fresh_outputs()`` points the call at newly allocated gradient /
+        loss tensors that the caller then owns.  Nothing of the caller's is retained.
     """
 
     def __init__(self, tgt_pyr: Sequence[torch.Tensor], src_pyr: Sequence[torch.Tensor], depth_pyr: Sequence[torch.Tensor],
                  poses: torch.Tensor, K_ms: torch.Tensor, alpha: float = 0.85, photo_weights: Optional[Sequence[float]] = None,
                  smooth_weights: Optional[Sequence[float]] = None, want_grad: bool = True, want_grad_K: bool = False,
                  padding_mode: str = "zeros", masks: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]] = None,
-                 want_maps: bool = False, no_photo: bool = False, no_smooth: bool = False, disparity: bool = False):
+                 want_maps: bool = False, no_photo: bool = False, no_smooth: bool = False, disparity: bool = False,
+                 keep_inputs: bool = True):
         ns = len(tgt_pyr)
         _require_cuda(poses, K_ms, *tgt_pyr, *src_pyr, *depth_pyr)
         B, S = poses.shape[0], poses.shape[1]
         dev = poses.device
         if poses.shape != (B, S, 6) or K_ms.shape != (B, ns, 3, 3):
             raise ValueError("poses must be (B,S,6) and K_ms (B,scales,3,3)")
-        self.B, self.S, self.ns = B, S, ns
-        self.poses = poses.contiguous()
-        self.K = [K_ms[:, s].contiguous() for s in range(ns)]
+        self.B, self.S, self.ns, self.device = B, S, ns, dev
+        self.want_grad, self.want_grad_K = want_grad, want_grad_K
+        # per-scale intrinsics as contiguous (B,3,3) blocks (what the C call points at): one scale-major buffer
+        self.K_buf = torch.empty(ns, B, 3, 3, device=dev)
+        self.K = [self.K_buf[s] for s in range(ns)]
         if photo_weights is None:
             photo_weights = [1.0 * S / 2] * ns            # models/baseline.py:1126-1129 with loss_weight_rigid_warp = 1
         if smooth_weights is None:
@@ -91,7 +99,7 @@ class FusedLossPlan:
         self.workspace = torch.empty(nbytes // 8 + 2, dtype=torch.float64, device=dev)
         wsp = (self.workspace.data_ptr() + 15) & ~15
         self.maps = []
-        self._keep = [tgt_pyr, src_pyr, depth_pyr, masks]
+        self._depth_shapes = [tuple(d.shape) for d in depth_pyr]
         scales = []
         for s in range(ns):
             tgt, src, depth = tgt_pyr[s], src_pyr[s], depth_pyr[s]
@@ -117,19 +125,66 @@ class FusedLossPlan:
             | (_abi.SNDE_LOSS_NO_PHOTO if no_photo else 0) | (_abi.SNDE_LOSS_NO_SMOOTH if no_smooth else 0) \
             | (_abi.SNDE_LOSS_DISPARITY if disparity else 0)
         pad = {"zeros": _abi.SNDE_PAD_ZEROS, "border": _abi.SNDE_PAD_BORDER}[padding_mode]
+        self.poses = poses.contiguous()
         self.args = _abi.make_loss_args(B, S, float(alpha), flags, pad, self.poses.data_ptr(), scales, self.loss_out.data_ptr(),
                                         self.grad_poses.data_ptr() if want_grad else None,
                                         self.grad_K.data_ptr() if want_grad_K else None, wsp, nbytes)
         self._fn = _abi.lib().snde_loss_fwdbwd
         self._ref = C.byref(self.args)
-        self.num_tiles = int(_abi.lib().snde_loss_num_tiles(self._ref))
-        self.kernel_launches = 3   # prep, strip, finalize (+ one memset node)
+        self._num_tiles = None
+        self.kernel_launches = 3   # prep (also zeroes the accumulators), strip, finalize
+        self._set_intrinsics(K_ms)
+        self._keep = [tgt_pyr, src_pyr, depth_pyr, masks] if keep_inputs else None
+        if not keep_inputs:
+            self.poses = None
+
+    @property
+    def num_tiles(self) -> int:
+        """strip tasks of one call (host-side preview of the library's segment-height rule)"""
+        if self._num_tiles is None:
+            self._num_tiles = int(_abi.lib().snde_loss_num_tiles(self._ref))
+        return self._num_tiles
+
+    def _set_intrinsics(self, K_ms: torch.Tensor) -> None:
+        if K_ms.data_ptr() == self.K_buf.data_ptr() and K_ms.stride() == (9, self.B * 9, 3, 1):
+            return                                        # the caller already filled this very buffer (a permuted view of it)
+        self.K_buf.copy_(K_ms.permute(1, 0, 2, 3))        # one small strided copy
 
     def refresh_intrinsics(self, K_ms: torch.Tensor) -> None:
-        """Re-copy the per-scale intrinsics (the plan keeps contiguous (B,3,3) copies of the strided K_ms[:, s])."""
+        """Re-copy the per-scale intrinsics (the plan keeps a contiguous scale-major copy of the strided K_ms[:, s])."""
+        self._set_intrinsics(K_ms)
+
+    def rebind(self, tgt_pyr, src_pyr, depth_pyr, poses: torch.Tensor, K_ms: torch.Tensor, masks=None) -> None:
+        """Point the cached arguments at other tensors of the same shapes AND strides (the caller checks that: the plan is
+        looked up by them).  poses must be contiguous."""
+        a = self.args
+        a.poses = poses.data_ptr()
         for s in range(self.ns):
-            if self.K[s].data_ptr() != K_ms[:, s].data_ptr():     # the plan already points at the caller's block
-                self.K[s].copy_(K_ms[:, s])
+            sc = a.scale[s]
+            sc.tgt.ptr, sc.src.ptr, sc.depth.ptr = tgt_pyr[s].data_ptr(), src_pyr[s].data_ptr(), depth_pyr[s].data_ptr()
+            if masks is not None:
+                sc.mask_fwd.ptr, sc.mask_bwd.ptr = masks[s][0].data_ptr(), masks[s][1].data_ptr()
+        self._set_intrinsics(K_ms)
+
+    def fresh_outputs(self):
+        """Newly allocated loss / gradient tensors for the next run (owned by the caller afterwards).
+        Returns (loss_out, grad_poses | None, grad_K | None, [grad_depth])."""
+        a, dev = self.args, self.device
+        loss_out = torch.empty(3 + 3 * self.ns, device=dev)
+        a.loss_out = loss_out.data_ptr()
+        gposes = gK = None
+        gdepth = []
+        if self.want_grad:
+            gposes = torch.empty(self.B, self.S, 6, device=dev)
+            a.grad_poses = gposes.data_ptr()
+            for s, shp in enumerate(self._depth_shapes):
+                g = torch.empty(shp, device=dev)
+                a.scale[s].grad_depth.ptr = g.data_ptr()
+                gdepth.append(g)
+        if self.want_grad_K:
+            gK = torch.empty(self.B, self.ns, 3, 3, device=dev)
+            a.grad_K = gK.data_ptr()
+        return loss_out, gposes, gK, gdepth
 
     def run(self) -> None:
         """Launch on the current stream (asynchronous)."""

@@ -121,19 +121,24 @@ def compute_rigid_flow(pose, depth, intrinsics, reverse_pose):
 
 
 class _Sampler(torch.autograd.Function):
+    """want_valid: also return the (N,h,w) validity mask from the same launch (non-differentiable)."""
+
     @staticmethod
-    def forward(ctx, imgs, coords, add_grid, padding_mode):
+    def forward(ctx, imgs, coords, add_grid, padding_mode, want_valid=False):
         imgs_d, coords_d = imgs.detach(), coords.detach()
-        out, _ = ops.sampler_fwd(imgs_d, coords_d, add_grid, padding_mode, False)
+        out, valid = ops.sampler_fwd(imgs_d, coords_d, add_grid, padding_mode, want_valid)
         ctx.save_for_backward(imgs_d, coords_d)
         ctx.cfg = (add_grid, padding_mode)
+        if want_valid:
+            ctx.mark_non_differentiable(valid)
+            return out, valid
         return out
 
     @staticmethod
-    def backward(ctx, gout):
+    def backward(ctx, gout, _gvalid=None):
         imgs, coords = ctx.saved_tensors
         gcoords, gimg = ops.sampler_bwd(imgs, coords, ctx.cfg[0], ctx.cfg[1], gout, ctx.needs_input_grad[0])
-        return gimg, (gcoords if ctx.needs_input_grad[1] else None), None, None
+        return gimg, (gcoords if ctx.needs_input_grad[1] else None), None, None, None
 
 
 def bilinear_sampler(imgs, coords, padding_mode="zeros"):

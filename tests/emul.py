@@ -8,7 +8,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "host_emul", "emul.cpp")
-OUT = os.path.join(ROOT, "tests", "_build", "libsnde_emul.so")
+DEFS = os.environ.get("SNDE_EMUL_DEFS", "").split()          # tuning experiments only (same switches as SNDE_NVCC_DEFS)
+OUT = os.path.join(ROOT, "tests", "_build", "libsnde_emul%s.so" % ("_" + "".join(c for c in "".join(DEFS) if c.isalnum()) if DEFS else ""))
 CSRC = os.path.join(ROOT, "self-supervised-normal-depth-estimation_b200", "csrc")
 
 
@@ -18,7 +19,7 @@ def build():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fvisibility=hidden",
-                    "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", OUT, SRC], check=True)
+                    "-I", os.path.join(ROOT, "include"), "-I", CSRC] + DEFS + ["-o", OUT, SRC], check=True)
     return OUT
 
 

@@ -189,6 +189,14 @@ def glue_kats(U, L):
     K4 = torch.zeros(b, 4, 4); K4[:, :3, :3] = Kc; K4[:, 3, 3] = 1.0
     proj = torch.matmul(K4, U.pose_vec2mat(vec))
     out.update(c2p_vec=vec.numpy(), c2p_proj=proj.numpy(), c2p_out=np.ascontiguousarray(U.cam2pixel(cam, proj).numpy()))
+    # flow_smooth_loss with its INTENDED semantics (the reference's body raises: it feeds (b,1,h,w) slices to a (b,h,w,1)
+    # function): every flow channel as a (b,h,w,1) map through the reference's own smooth_loss, averaged
+    g2 = torch.Generator().manual_seed(33)
+    flow = (torch.randn(2, 2, 10, 14, generator=g2) * 3).requires_grad_(True)
+    fimg = torch.rand(2, 10, 14, 3, generator=g2) * 2 - 1
+    fs = sum(L.smooth_loss(flow[:, i, :, :].unsqueeze(3), fimg) for i in range(2)) / 2
+    fs.backward()
+    out.update(fsl_flow=flow.detach().numpy(), fsl_img=fimg.numpy(), fsl_loss=np.float64(fs.item()), fsl_gflow=flow.grad.numpy())
     np.savez_compressed(os.path.join(HERE, "glue_kats.npz"), **out)
     print("glue_kats written:", len(out), "arrays")
 
@@ -202,10 +210,94 @@ def full_size_cases(U, L):
     run_case(U, L, "hires_b8_smooth", False, B=8, S=4, H=376, W=1248, num_scales=4, seed=14, smooth=True, motion="small")
 
 
+def network_kats(U, L):
+    """Round 2: the reference's DispNetS / PoseNet (models/DispNetS.py, models/PoseNet.py) with seeded xavier initialisation on
+    small seeded inputs -- pins the architecture, the head scaling and the initialisation order of snde_b200/networks.py."""
+    from models.DispNetS import DispNetS
+    from models.PoseNet import PoseNet
+    out = {}
+    torch.manual_seed(0); d = DispNetS(); d.init_weights(); d.train()
+    torch.manual_seed(1); p = PoseNet(2); p.init_weight(); p.train()
+    out["disp_params"] = np.int64(sum(t.numel() for t in d.parameters()))
+    out["pose_params"] = np.int64(sum(t.numel() for t in p.parameters()))
+    out["disp_keys"] = np.array(list(d.state_dict().keys()))
+    out["pose_keys"] = np.array(list(p.state_dict().keys()))
+    out["disp_abs_sums"] = np.array([float(t.double().abs().sum()) for t in d.state_dict().values()])
+    out["pose_abs_sums"] = np.array([float(t.double().abs().sum()) for t in p.state_dict().values()])
+    g = torch.Generator().manual_seed(5)
+    for tag, shape in (("a", (2, 3, 128, 160)), ("b", (1, 3, 72, 104))):          # b: not divisible by 128 (decoder crops)
+        x = torch.rand(shape, generator=g) * 2 - 1
+        out[f"disp_in_{tag}"] = x.numpy()
+        with torch.no_grad():
+            for i, t in enumerate(d(x)):
+                out[f"disp_out_{tag}_{i}"] = t.numpy()
+    xp = torch.rand(2, 9, 128, 160, generator=g) * 2 - 1
+    out["pose_in"] = xp.numpy()
+    with torch.no_grad():
+        out["pose_out"] = p(xp).numpy()
+    np.savez_compressed(os.path.join(HERE, "network_kats.npz"), **out)
+    print("network_kats written:", len(out), "arrays")
+
+
+def train_step_kats(U, L):
+    """Round 2: ONE iteration of the reference's trainer (GeoNetModel: iter_data_preparation, build_dispnet, build_posenet,
+    build_rigid_warp_flow, build_losses, backward, Adam step -- models/baseline.py:1170-1206) on seeded uint8 frames:
+    losses, network outputs and per-parameter gradient norms.  Pins snde_b200/trainer.py (step-level parity)."""
+    import argparse
+    import tempfile
+
+    class _SW:
+        def __init__(self, *a, **k): pass
+        def add_scalar(self, *a, **k): pass
+        def add_images(self, *a, **k): pass
+    for name, kw in (("tensorboardX", dict(SummaryWriter=_SW)), ("imageio", dict(imread=lambda *a, **k: None))):
+        m = types.ModuleType(name); m.__dict__.update(kw); sys.modules[name] = m
+    import models.baseline as MB
+    MB.n_iter = 1
+    B, S, H, W, ns, seed = 2, 2, 128, 160, 4, 8964
+    tmp = tempfile.mkdtemp()
+    args = argparse.Namespace(is_train=1, train_flow=False, batch_size=B, num_source=S, num_scales=ns, sequence_length=S + 1,
+                              img_height=H, img_width=W, simi_alpha=0.85, loss_weight_rigid_warp=1.0, loss_weight_disparity_smooth=0.5,
+                              graphs_dir=tmp, ckpt_dir=tmp, learning_rate=2e-4, momentum=0.9, beta=0.999, weight_decay=0.0)
+    torch.manual_seed(seed)
+    model = MB.GeoNetModel(args, torch.device("cpu"))
+    model.disp_net.train(); model.pose_net.train()
+    g = torch.Generator().manual_seed(77)
+    # band-limited frames (uint8), a KITTI-like intrinsics matrix
+    low = torch.rand(B, 3 * (1 + S), H // 8, W // 8, generator=g)
+    frames = (torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False).clamp(0, 1) * 255).round().to(torch.uint8)
+    tgt_u8, src_u8 = frames[:, :3].contiguous(), frames[:, 3:].contiguous()
+    K = torch.tensor([[0.58 * W, 0, 0.5 * W], [0, 1.92 * H, 0.5 * H], [0, 0, 1]]).repeat(B, 1, 1)
+    opt = torch.optim.Adam([{"params": v.parameters(), "lr": args.learning_rate} for v in model.nets.values()],
+                           betas=(args.momentum, args.beta), weight_decay=args.weight_decay)
+    model.iter_data_preparation((tgt_u8, src_u8, K))
+    model.build_dispnet(); model.build_posenet(); model.build_rigid_warp_flow(); model.build_losses()
+    opt.zero_grad(); model.loss_total.backward()
+    out = dict(B=np.int64(B), S=np.int64(S), H=np.int64(H), W=np.int64(W), seed=np.int64(seed), tgt_u8=tgt_u8.numpy(), src_u8=src_u8.numpy(), K=K.numpy(),
+               loss_total=np.float64(model.loss_total.item()), loss_rigid_warp=np.float64(model.loss_rigid_warp.item()),
+               loss_disp_smooth=np.float64(model.loss_disp_smooth.item()), poses=model.poses.detach().numpy(),
+               disp0_mean=np.float64(model.disparities[0].double().mean().item()),
+               disp_grad_l2=np.array([float(p.grad.double().norm()) for p in model.disp_net.parameters()]),
+               pose_grad_l2=np.array([float(p.grad.double().norm()) for p in model.pose_net.parameters()]))
+    opt.step()
+    out["disp_abs_sum_after_step"] = np.array([float(p.detach().double().abs().sum()) for p in model.disp_net.parameters()])
+    out["pose_abs_sum_after_step"] = np.array([float(p.detach().double().abs().sum()) for p in model.pose_net.parameters()])
+    np.savez_compressed(os.path.join(HERE, "train_step_kats.npz"), **out)
+    print("train_step_kats written: loss_total", out["loss_total"], "rigid", out["loss_rigid_warp"], "smooth", out["loss_disp_smooth"])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     U, L = import_reference()
+    if "--networks" in sys.argv:
+        network_kats(U, L)
+        sys.exit(0)
+    if "--train-step" in sys.argv:
+        train_step_kats(U, L)
+        sys.exit(0)
     if "--round2" in sys.argv:          # only the fixtures added in round 2 (the round-1 files stay byte-identical)
+        network_kats(U, L)
+        train_step_kats(U, L)
         glue_kats(U, L)
         full_size_cases(U, L)
         sys.exit(0)
@@ -219,3 +311,5 @@ if __name__ == "__main__":
     run_case(U, L, "config1_smooth", False, B=4, S=2, H=128, W=416, num_scales=4, seed=0, smooth=True, motion="small")
     glue_kats(U, L)
     full_size_cases(U, L)
+    network_kats(U, L)
+    train_step_kats(U, L)
