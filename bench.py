@@ -225,6 +225,24 @@ def copy_probe(D, dev, mbytes=256, reps=4):
         e1.record()
         D.barrier(dev)
         out[name] = round(reps * (mbytes << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9, 2)
+    # both directions at once (what the pipelined end-to-end step does), on two streams
+    h2 = torch.empty(mbytes << 20, dtype=torch.uint8).pin_memory()
+    d2 = torch.empty(mbytes << 20, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    D.barrier(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cur = torch.cuda.current_stream(dev)
+    e0.record(cur)
+    s1.wait_event(e0); s2.wait_event(e0)
+    for _ in range(reps):
+        with torch.cuda.stream(s1):
+            d.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h2.copy_(d2, non_blocking=True)
+    cur.wait_stream(s1); cur.wait_stream(s2)
+    e1.record(cur)
+    D.barrier(dev)
+    out["bidir_each_gbs"] = round(reps * (mbytes << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9, 2)
     return out
 
 
@@ -380,8 +398,9 @@ def e2e_leg(args, cfg, D, dev):
     return {"value": D.world * warped_px * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "loss_check": float(last.host_views[-1][0]),
             "copies_per_step": {"h2d": 1, "d2h": 1},
-            "copy_probe": dict(probe, note="plain 256 MB pinned copies by this rank while every rank copies at once; "
-                                           f"floor of this step = {h2d / probe['h2d_gbs'] / 1e6:.3f} ms (H2D) / {d2h / probe['d2h_gbs'] / 1e6:.3f} ms (D2H, overlapped)")}
+            "copy_probe": dict(probe, note="plain 256 MB pinned copies by this rank while every rank copies at once (each direction alone, then both "
+                                           f"together: GB/s per direction); floor of this step = {h2d / probe['bidir_each_gbs'] / 1e6:.3f} ms (H2D while the D2H of the "
+                                           f"previous step runs) / {h2d / probe['h2d_gbs'] / 1e6:.3f} ms (H2D alone)")}
 
 
 def train_leg(args, tcfg, D, dev, steps, warmup):
