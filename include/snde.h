@@ -200,6 +200,12 @@ SNDE_API int snde_smooth_loss_bwd(int M, int h, int w, SndeMap depth, SndeImage 
  * int(H/2^s) pyramid agrees with its networks); else SNDE_ERR_SHAPE. */
 SNDE_API int snde_frames_to_pyramid(int n, int H, int W, int num_scales, const uint8_t *frames, int64_t sn, int64_t sc,
                            int64_t sh, int64_t sw, float *const *levels, void *stream);
+/* Same, for a frame block whose channel axis holds groups * 3 channels -- the DataLoader's source block (B, 3*S, H, W),
+ * models/baseline.py:772-775: group g of frame b becomes image g * n + b of every level (the source-major order
+ * n = src * B + b of the loss path), so ONE launch prepares all S sources.  levels[s] is (groups*n, 3, H>>s, W>>s).
+ * num_scales <= SNDE_MAX_SCALES (6). */
+SNDE_API int snde_frames_to_pyramid_grouped(int n, int groups, int H, int W, int num_scales, const uint8_t *frames, int64_t sn,
+                                            int64_t sc, int64_t sh, int64_t sw, float *const *levels, void *stream);
 
 #ifdef __cplusplus
 }

@@ -85,6 +85,8 @@ SIGNATURES = {
     "snde_smooth_loss_bwd": (C.c_int, [C.c_int, C.c_int, C.c_int, SndeMap, SndeImage, C.c_void_p, SndeMap, C.c_void_p]),
     "snde_frames_to_pyramid": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                          C.POINTER(C.c_void_p), C.c_void_p]),
+    "snde_frames_to_pyramid_grouped": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                                 C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
 }
 
 _lib = None

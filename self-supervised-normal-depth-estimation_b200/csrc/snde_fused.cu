@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(64) loss_final_kernel(int B, int S, int ns, in
             for (int j = 0; j < 6; ++j) {
                 double a = 0.0;
                 for (int q = 0; q < ns && t + q < cnt; ++q) a += sv[t + q][j];
-                if (base == 0 || true) grad_poses[(b * S + kk) * 6 + j] = (float)a;
+                grad_poses[(b * S + kk) * 6 + j] = (float)a;
             }
         }
         if (wantK && t < ns && base == 0) {
@@ -148,15 +148,64 @@ extern "C" size_t snde_loss_workspace_bytes(int B, int S, int num_scales) {
     return loss_ws_layout(B, S, num_scales).end;
 }
 
-// host-only preview of the task count, with the segment-height rule of snde_loss_fwdbwd evaluated for a B200
-// (148 SMs x SNDE_STRIP_CTAS_PER_SM CTAs x PAIRS warp pairs)
+// ---- per-process caches, written once each under std::call_once / atomics (the entry points may be called from any
+//      number of host threads; nothing else in the library is shared between calls) ----
+#include <atomic>
+#include <mutex>
+namespace {
+// Tuning overrides of the task decomposition exist only in builds made with -DSNDE_TUNING (scripts/build_variants.sh);
+// the shipped library ignores the environment.
+struct SegOverrides { int seg_rows = 0, fine_rows = 0, fine_permille = 0; };
+static const SegOverrides &seg_overrides() {
+    static SegOverrides o;
+#ifdef SNDE_TUNING
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto env_int = [](const char *name) { const char *e = getenv(name); return e ? atoi(e) : 0; };
+        const int s = env_int("SNDE_SEG_ROWS");
+        o.seg_rows = (s == 16 || s == 32 || s == 64 || s == 128) ? s : 0;          // anything else is ignored
+        const int f = env_int("SNDE_FINE_ROWS");
+        o.fine_rows = (f == 8 || f == 16 || f == 32) ? f : 0;
+        const int pm = env_int("SNDE_FINE_PERMILLE");
+        o.fine_permille = pm > 0 && pm <= 1000 ? pm : 0;
+    });
+#endif
+    return o;
+}
+static std::atomic<int> g_sm_count[64];
+static int sm_count_of(int dev) {            // 0 on failure
+    int n = g_sm_count[dev].load(std::memory_order_relaxed);
+    if (n > 0) return n;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 0;
+    g_sm_count[dev].store(n, std::memory_order_relaxed);
+    return n;
+}
+static std::atomic<bool> g_attr_done[8][64];
+}  // namespace
+
+// Rows per strip segment, shared by snde_loss_fwdbwd and snde_loss_num_tiles.  Longer segments recompute fewer halo rows (a
+// segment of s rows costs s + 6 row steps) but give fewer tasks to balance over the resident warp pairs: 64 rows when that still
+// leaves two tasks per pair, else 32, else (fewer tasks than pairs: small batches such as the reference's default B = 4) 16.
+// Measured at config 2: 16 -> 344 us, 32 -> 318, 64 -> 308, 128 -> 416.
+static int build_dev_loss_for(const SndeLossArgs *a, DevLoss &d, const LossWorkspace *lay, int64_t *tiles, int sms) {
+    const SegOverrides &ov = seg_overrides();
+    int rc = build_dev_loss(a, d, lay, tiles, ov.seg_rows ? ov.seg_rows : 64, ov.fine_rows, ov.fine_permille);   // validates every argument
+    if (rc || ov.seg_rows) return rc;
+    const long long resident_pairs = (long long)sms * SNDE_STRIP_CTAS_PER_SM * StripCfg::PAIRS;
+    if (*tiles < 2 * resident_pairs) {
+        rc = build_dev_loss(a, d, lay, tiles, 32, ov.fine_rows, ov.fine_permille);
+        if (!rc && *tiles < resident_pairs) rc = build_dev_loss(a, d, lay, tiles, 16, ov.fine_rows, ov.fine_permille);
+    }
+    return rc;
+}
+
+// host-only preview of the task count of snde_loss_fwdbwd on the current device (148 SMs when no device is available)
 extern "C" int64_t snde_loss_num_tiles(const SndeLossArgs *args) {
     DevLoss d; int64_t n = 0;
     if (!args) return SNDE_ERR_NULL;
-    int rc = build_dev_loss(args, d, nullptr, &n, 64);
-    if (rc) return rc;
-    const long long pairs = 148LL * SNDE_STRIP_CTAS_PER_SM * StripCfg::PAIRS;
-    if (n < 2 * pairs) { rc = build_dev_loss(args, d, nullptr, &n, 32); if (!rc && n < pairs) rc = build_dev_loss(args, d, nullptr, &n, 16); }
+    int devi = 0, sms = 0;
+    if (cudaGetDevice(&devi) == cudaSuccess && devi >= 0 && devi < 64) sms = sm_count_of(devi);
+    const int rc = build_dev_loss_for(args, d, nullptr, &n, sms > 0 ? sms : 148);
     return rc ? rc : n;
 }
 
@@ -170,35 +219,14 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     const LossWorkspace lay = loss_ws_layout(a->B, a->S, a->num_scales);
     if (!a->workspace || a->workspace_bytes < lay.end || ((uintptr_t)a->workspace & 15)) return SNDE_ERR_WORKSPACE;
     DevLoss d; int64_t tiles = 0;
-    // Rows per strip segment.  Longer segments recompute fewer halo rows (a segment of s rows costs s + 6 row steps) but
-    // give fewer tasks to balance over the resident warp pairs: 64 rows when that still leaves two tasks per pair,
-    // else 32, else (fewer tasks than pairs) 16 (measured at config 2: 16 -> 344 us, 32 -> 318, 64 -> 308, 128 -> 416).  SNDE_SEG_ROWS overrides (tuning only).
-    static int seg_env = -1;
-    if (seg_env < 0) { const char *e = getenv("SNDE_SEG_ROWS"); seg_env = e ? atoi(e) : 0; if (seg_env < 0) seg_env = 0; }
-    // SNDE_FINE_ROWS / SNDE_FINE_PERMILLE: cut the last share of the owners into short tail-filling segments (tuning only;
-    // off by default: measured at config 2, 16 rows for 15 % .. 60 % of the owners gave 301 .. 323 us against 301 .. 306 us without)
-    static int fine_rows = -1, fine_pm = -1;
-    if (fine_rows < 0) { const char *e = getenv("SNDE_FINE_ROWS"); fine_rows = e ? atoi(e) : 0; }
-    if (fine_pm < 0) { const char *e = getenv("SNDE_FINE_PERMILLE"); fine_pm = e ? atoi(e) : 0; }
-    int rc = build_dev_loss(a, d, &lay, &tiles, seg_env ? seg_env : 64, fine_rows, fine_pm);       // validates every argument before any CUDA call
+    int rc = build_dev_loss(a, d, &lay, &tiles, 64);            // validates every argument before any CUDA call
     if (rc) return rc;
     int devi = 0;
     if (cudaGetDevice(&devi) != cudaSuccess || devi < 0 || devi >= 64) return SNDE_ERR_CUDA;
-    static int sm_count[64] = {};
-    if (!sm_count[devi]) {
-        int n = 0;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, devi) != cudaSuccess || n <= 0) return SNDE_ERR_CUDA;
-        sm_count[devi] = n;
-    }
-    const long long resident_pairs = (long long)sm_count[devi] * SNDE_STRIP_CTAS_PER_SM * StripCfg::PAIRS;
-    if (!seg_env && tiles < 2 * resident_pairs) {
-        rc = build_dev_loss(a, d, &lay, &tiles, 32, fine_rows, fine_pm);
-        if (rc) return rc;
-        if (tiles < resident_pairs) {             // small batches (the reference's default B = 4): latency, not throughput
-            rc = build_dev_loss(a, d, &lay, &tiles, 16, fine_rows, fine_pm);
-            if (rc) return rc;
-        }
-    }
+    const int sms = sm_count_of(devi);
+    if (sms <= 0) return SNDE_ERR_CUDA;
+    rc = build_dev_loss_for(a, d, &lay, &tiles, sms);           // the task table for this device
+    if (rc) return rc;
     cudaStream_t st = as_stream(stream_);
     const int B = a->B, S = a->S, ns = a->num_scales, N = B * S;
     unsigned char *ws = (unsigned char *)a->workspace;
@@ -211,16 +239,16 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     const size_t smem = sizeof(PairSmem) * StripCfg::PAIRS;
     const bool grad = a->flags & SNDE_LOSS_GRAD, gradk = a->flags & SNDE_LOSS_GRAD_K;
     // opt in to > 48 KB dynamic shared memory once per kernel variant and device (not a stream operation; kept out of
-    // the per-call path so the call can be captured into a CUDA graph after one eager warm-up)
-    static bool attr_done[8][64] = {};
+    // the per-call path so the call can be captured into a CUDA graph after one eager warm-up).  Setting it twice from two
+    // racing threads is harmless: same value.
     // persistent grid: as many CTAs as fit, but no more warp pairs than tasks
-    long long ctas = (long long)sm_count[devi] * SNDE_STRIP_CTAS_PER_SM;
+    long long ctas = (long long)sms * SNDE_STRIP_CTAS_PER_SM;
     const long long need = (tiles + StripCfg::PAIRS - 1) / StripCfg::PAIRS;
     if (ctas > need) ctas = need;
     auto launch = [&](auto kern, int variant) -> int {
-        if (!attr_done[variant][devi]) {
+        if (!g_attr_done[variant][devi].load(std::memory_order_acquire)) {
             if (snde_cuda_failed(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "shared-memory opt-in", __LINE__)) return SNDE_ERR_CUDA;
-            attr_done[variant][devi] = true;
+            g_attr_done[variant][devi].store(true, std::memory_order_release);
         }
         kern<<<(unsigned)ctas, StripCfg::NT, smem, st>>>(d);
         return SNDE_OK;

@@ -214,6 +214,32 @@ extern "C" int snde_bilinear_sampler_fwd(int N, int C, int hs, int ws, SndeImage
     return SNDE_OK;
 }
 
+// Lanes of the active mask that share `key`, as seen by each lane: the peers above it, whether it is the lowest of its
+// group, and the size of the largest group in the warp (the trip count of the reduction below; 1 = no collision at all).
+struct WarpTapGroups { unsigned active, above; int max_group; bool leader; };
+__device__ __forceinline__ WarpTapGroups warp_tap_groups(unsigned active, unsigned long long key) {
+    const int lane = (int)(threadIdx.x & 31);
+    const unsigned peers = __match_any_sync(active, key);
+    WarpTapGroups g;
+    g.active = active;
+    g.above = lane == 31 ? 0u : peers & ~((2u << lane) - 1u);
+    g.leader = (peers & ((1u << lane) - 1u)) == 0u;
+    g.max_group = (int)__reduce_max_sync(active, (unsigned)__popc(peers));
+    return g;
+}
+// sum of v over the lanes of this lane's group that lie above it, plus its own: the group's total in its leader
+__device__ __forceinline__ float warp_group_sum(const WarpTapGroups &g, float v) {
+    const int lane = (int)(threadIdx.x & 31);
+    float sum = v;
+    unsigned rest = g.above;
+    for (int it = 1; it < g.max_group; ++it) {
+        const int src = rest ? __ffs((int)rest) - 1 : lane;
+        const float o = __shfl_sync(g.active, v, src);
+        if (rest) { sum += o; rest &= rest - 1u; }
+    }
+    return sum;
+}
+
 __global__ void __launch_bounds__(256) sampler_bwd_kernel(long long total, int C, int hs, int ws, LImage img, int ht, int wt,
                                                           const float *__restrict__ coords, int add_grid,
                                                           const float *__restrict__ xtab, const float *__restrict__ ytab, int border,
@@ -229,16 +255,30 @@ __global__ void __launch_bounds__(256) sampler_bwd_kernel(long long total, int C
         const long long o10 = (long long)tp.y0 * img.sh + (long long)tp.x1 * img.sw, o11 = (long long)tp.y1 * img.sh + (long long)tp.x1 * img.sw;
         const float w00 = tp.wx0 * tp.wy0, w01 = tp.wx0 * tp.wy1, w10 = tp.wx1 * tp.wy0, w11 = tp.wx1 * tp.wy1;
         float g00 = 0.f, g01 = 0.f, g10 = 0.f, g11 = 0.f;
+        // image-gradient scatter (index_select backward, utils_edited.py:473-476), WARP-AGGREGATED: lanes of the warp whose tap
+        // lands on the same pixel are found with match.any on the pixel's address, the lowest of them adds the others'
+        // contributions (in lane order) and issues ONE atomic per distinct address and channel.
+        WarpTapGroups grp[4];
+        long long goff[4] = {0, 0, 0, 0};
+        if (gimg.p) {
+            const unsigned active = __activemask();
+            goff[0] = (long long)tp.y0 * gimg.sh + (long long)tp.x0 * gimg.sw; goff[1] = (long long)tp.y1 * gimg.sh + (long long)tp.x0 * gimg.sw;
+            goff[2] = (long long)tp.y0 * gimg.sh + (long long)tp.x1 * gimg.sw; goff[3] = (long long)tp.y1 * gimg.sh + (long long)tp.x1 * gimg.sw;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) grp[k] = warp_tap_groups(active, (unsigned long long)(n * gimg.sn + goff[k]));
+        }
         for (int c = 0; c < C; ++c) {
             const float *bc = base + c * img.sc;
             const float g = gout[i * C + c];
             g00 += g * __ldg(bc + o00); g01 += g * __ldg(bc + o01); g10 += g * __ldg(bc + o10); g11 += g * __ldg(bc + o11);
             if (gimg.p) {
                 float *gb = gimg.p + n * gimg.sn + c * gimg.sc;
-                atomicAdd(gb + (long long)tp.y0 * gimg.sh + (long long)tp.x0 * gimg.sw, w00 * g);
-                atomicAdd(gb + (long long)tp.y1 * gimg.sh + (long long)tp.x0 * gimg.sw, w01 * g);
-                atomicAdd(gb + (long long)tp.y0 * gimg.sh + (long long)tp.x1 * gimg.sw, w10 * g);
-                atomicAdd(gb + (long long)tp.y1 * gimg.sh + (long long)tp.x1 * gimg.sw, w11 * g);
+                const float wk[4] = {w00, w01, w10, w11};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float sum = warp_group_sum(grp[k], wk[k] * g);
+                    if (grp[k].leader) atomicAdd(gb + goff[k], sum);
+                }
             }
         }
         const float gwx0 = g00 * tp.wy0 + g01 * tp.wy1, gwx1 = g10 * tp.wy0 + g11 * tp.wy1;
@@ -382,28 +422,69 @@ extern "C" int snde_image_similarity_fwd(int N, int h, int w, float alpha, SndeI
     return SNDE_OK;
 }
 
-__global__ void __launch_bounds__(256) similarity_bwd_kernel(long long total, int h, int w, float alpha, float oma, LImage X, LImage Y,
-                                                             const float *__restrict__ gerr, float *__restrict__ gx, float *__restrict__ gy) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ix = (int)(i % w); const long long t = i / w; const int iy = (int)(t % h); const long long n = t / h;
+// Backward, tiled: a CTA owns a 32 x 8 tile of one image.  Per channel it stages the tile + a 2-pixel halo of x and y in
+// shared memory (zeros outside the image = the pools' padding), forms the four SSIM backward coefficients once per window
+// centre of the tile + 1-pixel halo (each centre is shared by the 9 pixels around it), then every pixel sums its 3 x 3
+// neighbourhood of coefficients.  Same operations in the same order as the per-pixel formulation it replaces (81 window taps
+// and 9 SSIM evaluations per pixel and channel, straight from global memory), so the results are bit-identical to it.
+constexpr int SIM_TX = 32, SIM_TY = 8;
+
+__global__ void __launch_bounds__(SIM_TX * SIM_TY) similarity_bwd_kernel(int h, int w, float alpha, float oma, LImage X, LImage Y,
+                                                                         const float *__restrict__ gerr, float *__restrict__ gx,
+                                                                         float *__restrict__ gy) {
+    __shared__ float sx_[SIM_TY + 4][SIM_TX + 4], sy_[SIM_TY + 4][SIM_TX + 4];
+    __shared__ float cf[4][SIM_TY + 2][SIM_TX + 2];
+    const long long n = blockIdx.z;
+    const int x0 = blockIdx.x * SIM_TX, y0 = blockIdx.y * SIM_TY;
+    const int tid = threadIdx.x, tx = tid % SIM_TX, ty = tid / SIM_TX;
+    const int ix = x0 + tx, iy = y0 + ty;
+    const bool inside = ix < w && iy < h;
+    const long long pix = (n * h + iy) * (long long)w + ix;
+    for (int c = 0; c < 3; ++c) {
+        __syncthreads();                                     // the previous channel's readers are done
+        for (int i = tid; i < (SIM_TY + 4) * (SIM_TX + 4); i += SIM_TX * SIM_TY) {
+            const int r = i / (SIM_TX + 4), q = i - r * (SIM_TX + 4);
+            const int gy_ = y0 + r - 2, gx_ = x0 + q - 2;
+            sx_[r][q] = img_or_zero(X, n, c, gy_, gx_, h, w);
+            sy_[r][q] = img_or_zero(Y, n, c, gy_, gx_, h, w);
+        }
+        __syncthreads();
+        for (int i = tid; i < (SIM_TY + 2) * (SIM_TX + 2); i += SIM_TX * SIM_TY) {
+            const int r = i / (SIM_TX + 2), q = i - r * (SIM_TX + 2);
+            const int qy = y0 + r - 1, qx = x0 + q - 1;
+            float cmx = 0.f, cmy = 0.f, ce = 0.f, cxy = 0.f;
+            if (qy >= 0 && qy < h && qx >= 0 && qx < w) {
+                float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+                for (int dr = 0; dr < 3; ++dr)
+#pragma unroll
+                    for (int dc = 0; dc < 3; ++dc) {
+                        const float xv = sx_[r + dr][q + dc], yv = sy_[r + dr][q + dc];
+                        sx = sx + xv; sy = sy + yv; sxx = sxx + xv * xv; syy = syy + yv * yv; sxy = sxy + xv * yv;
+                    }
+                Ssim ss; ssim_from_sums(sx, sy, sxx, syy, sxy, ss);
+                const float v = (1.f - ss.S) / 2.f;
+                const float g = gerr[((n * h + qy) * (long long)w + qx) * 3 + c];
+                const float gS = (v >= 0.f && v <= 1.f) ? -0.5f * alpha * g : 0.f;
+                ssim_bwd_coeffs(ss, gS, cmx, cmy, ce, cxy);
+            }
+            cf[0][r][q] = cmx; cf[1][r][q] = cmy; cf[2][r][q] = ce; cf[3][r][q] = cxy;
+        }
+        __syncthreads();
+        if (inside) {
             float bmx = 0.f, bmy = 0.f, be = 0.f, bxy = 0.f;
-            for (int dr = -1; dr <= 1; ++dr)
-                for (int dc = -1; dc <= 1; ++dc) {
-                    const int qy = iy + dr, qx = ix + dc;
+#pragma unroll
+            for (int dr = 0; dr < 3; ++dr)
+#pragma unroll
+                for (int dc = 0; dc < 3; ++dc) {
+                    const int qy = iy + dr - 1, qx = ix + dc - 1;
                     if (qy < 0 || qy >= h || qx < 0 || qx >= w) continue;
-                    Ssim ss; ssim_at(X, Y, n, c, qy, qx, h, w, ss);
-                    const float v = (1.f - ss.S) / 2.f;
-                    const float g = gerr[((n * h + qy) * (long long)w + qx) * 3 + c];
-                    const float gS = (v >= 0.f && v <= 1.f) ? -0.5f * alpha * g : 0.f;
-                    float cmx, cmy, ce, cxy; ssim_bwd_coeffs(ss, gS, cmx, cmy, ce, cxy);
-                    bmx += cmx; bmy += cmy; be += ce; bxy += cxy;
+                    bmx += cf[0][ty + dr][tx + dc]; bmy += cf[1][ty + dr][tx + dc]; be += cf[2][ty + dr][tx + dc]; bxy += cf[3][ty + dr][tx + dc];
                 }
-            const float xv = ld_img(X, n, c, iy, ix), yv = ld_img(Y, n, c, iy, ix);
-            const float l1 = oma * gerr[i * 3 + c] * signf(xv - yv);
-            if (gx) gx[i * 3 + c] = (bmx + 2.f * xv * be + yv * bxy) / 9.f + l1;
-            if (gy) gy[i * 3 + c] = (bmy + 2.f * yv * be + xv * bxy) / 9.f - l1;
+            const float xv = sx_[ty + 2][tx + 2], yv = sy_[ty + 2][tx + 2];
+            const float l1 = oma * gerr[pix * 3 + c] * signf(xv - yv);
+            if (gx) gx[pix * 3 + c] = (bmx + 2.f * xv * be + yv * bxy) / 9.f + l1;
+            if (gy) gy[pix * 3 + c] = (bmy + 2.f * yv * be + xv * bxy) / 9.f - l1;
         }
     }
 }
@@ -413,10 +494,10 @@ extern "C" int snde_image_similarity_bwd(int N, int h, int w, float alpha, SndeI
     if (!x.ptr || !y.ptr || !gerr) return SNDE_ERR_NULL;
     if (N <= 0 || h <= 0 || w <= 0) return SNDE_ERR_SHAPE;
     const long long total = (long long)N * h * w;
-    if (total * 3 >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
+    if (total * 3 >= (1LL << 31) || N > 65535 || (h + SIM_TY - 1) / SIM_TY > 65535) return SNDE_ERR_TOO_LARGE;
     if (!gx && !gy) return SNDE_OK;
-    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-    similarity_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(total, h, w, alpha, (float)(1.0 - (double)alpha), ldev(x), ldev(y), gerr, gx, gy);
+    const dim3 grid((w + SIM_TX - 1) / SIM_TX, (h + SIM_TY - 1) / SIM_TY, N);
+    similarity_bwd_kernel<<<grid, SIM_TX * SIM_TY, 0, as_stream(stream)>>>(h, w, alpha, (float)(1.0 - (double)alpha), ldev(x), ldev(y), gerr, gx, gy);
     SNDE_CHECK_LAUNCH();
     return SNDE_OK;
 }
@@ -481,83 +562,113 @@ extern "C" int snde_smooth_loss_bwd(int M, int h, int w, SndeMap depth, SndeImag
 
 // =============================================================================================
 // frames -> normalised fp32 pyramid (caller-side prep)
-// reference: models/baseline.py:761-767 (uint8 -> float, *= 1/255, * 2 - 1) and
+// reference: models/baseline.py:761-767 (uint8 -> float, *= 1/255, * 2 - 1), :772-775 (sources concatenated source-major) and
 // utils/utils_edited.py:89-112 (scale_pyramid: F.interpolate(mode='area')).
-// One thread owns one R x R block of one channel plane (R = 2^(num_scales-1)): it reads R rows of R bytes and writes
-// the block of every level; neighbouring threads own neighbouring blocks of a row, so every access is coalesced.
-// Sums run over each window in row-major order and are divided by the (power of two) count, like adaptive_avg_pool2d.
+// One CTA owns one tile of TR rows x 128 columns of one channel plane (TR = max(16, 2^(num_scales-1))).  The bytes come in
+// as 32-bit words along the row, become (u8 * 1/255) * 2 - 1 op by op, go to shared memory and straight out as level 0 with
+// 16-byte stores (a warp writes one 512-byte row segment); the coarser levels are then formed from the shared tile: every
+// output sums its 2^s x 2^s window in row-major order and multiplies by the (power of two) reciprocal count, like
+// adaptive_avg_pool2d, and consecutive threads write consecutive outputs of a row.
+// Traffic: 1 byte read + 4 * (1 + 1/4 + 1/16 + ...) bytes written per full-resolution pixel and channel.
+// `groups`: the channel axis holds groups * 3 channels (the DataLoader's (B, 3*S, H, W) source block); group g of frame b
+// lands in image g * n + b of the outputs -- the source-major order of the loss path -- so one launch does all S sources.
 // =============================================================================================
 struct PyrLevels { float *p[SNDE_MAX_SCALES]; };
 
 template <int NS>
-__global__ void __launch_bounds__(128) frames_to_pyramid_kernel(long long total, int H, int W, const uint8_t *__restrict__ frames,
+__global__ void __launch_bounds__(256) frames_to_pyramid_kernel(int n, int groups, int H, int W, const uint8_t *__restrict__ frames,
                                                                 long long sn, long long sc, long long sh, long long sw, PyrLevels lv) {
     constexpr int R = 1 << (NS - 1);
-    const int bw = W / R, bh = H / R;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int bx = (int)(i % bw);
-        long long r = i / bw;
-        const int by = (int)(r % bh);
-        r /= bh;
-        const int c = (int)(r % 3);
-        const long long n = r / 3;
-        const uint8_t *src = frames + n * sn + c * sc + (long long)(by * R) * sh + (long long)(bx * R) * sw;
-        float v[R][R];
+    constexpr int TR = R > 16 ? R : 16, TC = 128;
+    // one pad word per 32 columns: the strided reads of the coarser levels (stride 2^s words across a warp) then hit 32
+    // different banks
+    constexpr int TCP = TC + TC / 32;
+    __shared__ float tile[TR][TCP];
+    auto col = [](int x) { return x + (x >> 5); };
+    const int tiles_x = (W + TC - 1) / TC, tiles_y = (H + TR - 1) / TR;
+    long long t = blockIdx.x;
+    const int tx = (int)(t % tiles_x); t /= tiles_x;
+    const int ty = (int)(t % tiles_y); t /= tiles_y;
+    const int c = (int)(t % 3); t /= 3;
+    const int g = (int)(t % groups);
+    const long long b = t / groups;
+    const int x0 = tx * TC, y0 = ty * TR;
+    const int cols = min(TC, W - x0), rows = min(TR, H - y0);        // multiples of R (W % R == H % R == 0)
+    const uint8_t *src = frames + b * sn + (long long)(g * 3 + c) * sc + (long long)y0 * sh + (long long)x0 * sw;
+    const long long plane = ((long long)g * n + b) * 3 + c;
+    float *dst0 = lv.p[0] + (plane * H + y0) * (long long)W + x0;
+    const bool words = sw == 1 && ((sh | sc | sn) & 3) == 0 && (((uintptr_t)frames + (unsigned)(x0 & 3)) & 3) == 0 && (cols & 3) == 0 && (W & 3) == 0;
+    const bool vst = (W & 3) == 0 && (cols & 3) == 0 && ((uintptr_t)lv.p[0] & 15) == 0;
+    // ---- level 0: bytes -> normalised floats -> shared tile + global ----
+    for (int i = threadIdx.x; i < rows * (TC / 4); i += 256) {
+        const int y = i / (TC / 4), x4 = (i % (TC / 4)) * 4;
+        if (x4 >= cols) continue;
+        float v[4];
+        if (words) {
+            const unsigned w4 = __ldg(reinterpret_cast<const unsigned *>(src + (long long)y * sh + x4));
 #pragma unroll
-        for (int y = 0; y < R; ++y) {
-            if (sw == 1 && R == 8 && (((uintptr_t)(src + y * sh)) & 7) == 0) {
-                const uint2 w8 = __ldg(reinterpret_cast<const uint2 *>(src + y * sh));
+            for (int k = 0; k < 4; ++k) v[k] = (float)((w4 >> (8 * k)) & 0xffu);
+        } else {
 #pragma unroll
-                for (int x = 0; x < 8; ++x) v[y][x] = (float)(((x < 4 ? w8.x : w8.y) >> (8 * (x & 3))) & 0xffu);
-            } else {
-#pragma unroll
-                for (int x = 0; x < R; ++x) v[y][x] = (float)__ldg(src + y * sh + x * sw);
-            }
-#pragma unroll
-            for (int x = 0; x < R; ++x) v[y][x] = __fsub_rn(__fmul_rn(__fmul_rn(v[y][x], 1.f / 255.f), 2.f), 1.f);   // (u8 * 1/255) * 2 - 1, op by op
+            for (int k = 0; k < 4; ++k) v[k] = x4 + k < cols ? (float)__ldg(src + (long long)y * sh + (long long)(x4 + k) * sw) : 0.f;
         }
-        const long long plane = n * 3 + c;
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            constexpr int dummy = 0; (void)dummy;
-            const int k = 1 << s, hs = H >> s, ws = W >> s, m = R >> s;      // window size, level size, block size at this level
-            float *dst = lv.p[s] + (plane * hs + (long long)by * m) * ws + (long long)bx * m;
+        for (int k = 0; k < 4; ++k) v[k] = __fsub_rn(__fmul_rn(__fmul_rn(v[k], 1.f / 255.f), 2.f), 1.f);   // (u8 * 1/255) * 2 - 1, op by op
 #pragma unroll
-            for (int y = 0; y < m; ++y)
+        for (int k = 0; k < 4; ++k) tile[y][col(x4) + k] = v[k];              // (x4 .. x4+3 never straddle a pad word)
+        float *d = dst0 + (long long)y * W + x4;
+        if (vst) *reinterpret_cast<float4 *>(d) = make_float4(v[0], v[1], v[2], v[3]);        // W % 4 == 0 and x0 % 128 == 0: aligned
+        else {
 #pragma unroll
-                for (int x = 0; x < m; ++x) {
-                    float acc = 0.f;
+            for (int k = 0; k < 4; ++k) if (x4 + k < cols) d[k] = v[k];
+        }
+    }
+    __syncthreads();
+    // ---- levels 1 .. NS-1 from the shared tile ----
 #pragma unroll
-                    for (int dy = 0; dy < k; ++dy)
-#pragma unroll
-                        for (int dx = 0; dx < k; ++dx) acc = __fadd_rn(acc, v[y * k + dy][x * k + dx]);
-                    dst[(long long)y * ws + x] = s == 0 ? v[y][x] : __fmul_rn(acc, 1.f / (float)(k * k));
-                }
+    for (int s = 1; s < NS; ++s) {
+        const int k = 1 << s, hs = H >> s, ws = W >> s;
+        const int ocols = cols >> s, orows = rows >> s;
+        float *dst = lv.p[s] + (plane * hs + (y0 >> s)) * (long long)ws + (x0 >> s);
+        const float inv = 1.f / (float)(k * k);
+        for (int i = threadIdx.x; i < orows * ocols; i += 256) {
+            const int oy = i / ocols, ox = i - oy * ocols;
+            float acc = 0.f;
+            for (int dy = 0; dy < k; ++dy)
+#pragma unroll 4
+                for (int dx = 0; dx < k; ++dx) acc = __fadd_rn(acc, tile[oy * k + dy][col(ox * k + dx)]);
+            dst[(long long)oy * ws + ox] = __fmul_rn(acc, inv);
         }
     }
 }
 
-extern "C" int snde_frames_to_pyramid(int n, int H, int W, int num_scales, const uint8_t *frames, int64_t sn, int64_t sc, int64_t sh,
-                                      int64_t sw, float *const *levels, void *stream) {
+extern "C" int snde_frames_to_pyramid_grouped(int n, int groups, int H, int W, int num_scales, const uint8_t *frames, int64_t sn,
+                                              int64_t sc, int64_t sh, int64_t sw, float *const *levels, void *stream) {
     if (!frames || !levels) return SNDE_ERR_NULL;
-    if (n <= 0 || H <= 0 || W <= 0 || num_scales <= 0 || num_scales > 5) return SNDE_ERR_SHAPE;     // R x R floats live in registers: R <= 16
+    if (n <= 0 || groups <= 0 || H <= 0 || W <= 0 || num_scales <= 0 || num_scales > SNDE_MAX_SCALES) return SNDE_ERR_SHAPE;
     const int R = 1 << (num_scales - 1);
     if (H % R || W % R) return SNDE_ERR_SHAPE;
-    if ((long long)n * 3 * H * W >= (1LL << 40)) return SNDE_ERR_TOO_LARGE;
+    if ((long long)n * groups * 3 * H * W >= (1LL << 40)) return SNDE_ERR_TOO_LARGE;
     PyrLevels lv;
     for (int s = 0; s < SNDE_MAX_SCALES; ++s) lv.p[s] = nullptr;
     for (int s = 0; s < num_scales; ++s) { if (!levels[s]) return SNDE_ERR_NULL; lv.p[s] = levels[s]; }
-    const long long total = (long long)n * 3 * (H / R) * (W / R);
-    const long long want = (total + 127) / 128;
-    const int blocks = (int)(want < 148LL * 32 ? want : 148LL * 32);
+    const int TR = R > 16 ? R : 16;
+    const long long blocks = (long long)n * groups * 3 * ((H + TR - 1) / TR) * ((W + 127) / 128);
+    if (blocks >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
     cudaStream_t st = as_stream(stream);
     switch (num_scales) {
-        case 1: frames_to_pyramid_kernel<1><<<blocks, 128, 0, st>>>(total, H, W, frames, sn, sc, sh, sw, lv); break;
-        case 2: frames_to_pyramid_kernel<2><<<blocks, 128, 0, st>>>(total, H, W, frames, sn, sc, sh, sw, lv); break;
-        case 3: frames_to_pyramid_kernel<3><<<blocks, 128, 0, st>>>(total, H, W, frames, sn, sc, sh, sw, lv); break;
-        case 4: frames_to_pyramid_kernel<4><<<blocks, 128, 0, st>>>(total, H, W, frames, sn, sc, sh, sw, lv); break;
-        default: frames_to_pyramid_kernel<5><<<blocks, 128, 0, st>>>(total, H, W, frames, sn, sc, sh, sw, lv); break;
+        case 1: frames_to_pyramid_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(n, groups, H, W, frames, sn, sc, sh, sw, lv); break;
+        case 2: frames_to_pyramid_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(n, groups, H, W, frames, sn, sc, sh, sw, lv); break;
+        case 3: frames_to_pyramid_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(n, groups, H, W, frames, sn, sc, sh, sw, lv); break;
+        case 4: frames_to_pyramid_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(n, groups, H, W, frames, sn, sc, sh, sw, lv); break;
+        case 5: frames_to_pyramid_kernel<5><<<(unsigned)blocks, 256, 0, st>>>(n, groups, H, W, frames, sn, sc, sh, sw, lv); break;
+        default: frames_to_pyramid_kernel<6><<<(unsigned)blocks, 256, 0, st>>>(n, groups, H, W, frames, sn, sc, sh, sw, lv); break;
     }
     SNDE_CHECK_LAUNCH();
     return SNDE_OK;
+}
+
+extern "C" int snde_frames_to_pyramid(int n, int H, int W, int num_scales, const uint8_t *frames, int64_t sn, int64_t sc, int64_t sh,
+                                      int64_t sw, float *const *levels, void *stream) {
+    return snde_frames_to_pyramid_grouped(n, 1, H, W, num_scales, frames, sn, sc, sh, sw, levels, stream);
 }

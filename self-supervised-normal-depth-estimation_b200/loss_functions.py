@@ -198,9 +198,7 @@ def _frame_pyramids(tgt_u8, src_u8, ns: int):
         _PYR_CACHE[key] = bufs
     tgt_pyr, src_pyr = bufs
     ops.frames_to_pyramid(tgt_u8, ns, out=tgt_pyr)
-    # (B,3S,H,W) -> source-major (S*B,3,h,w) levels (baseline.py:772-775): one call per source on a strided view, no copy
-    for k in range(S):
-        ops.frames_to_pyramid(src_u8[:, 3 * k:3 * (k + 1)], ns, out=[t[k * B:(k + 1) * B] for t in src_pyr])
+    ops.frames_to_pyramid(src_u8, ns, out=src_pyr)      # (B,3S,H,W) -> source-major (S*B,3,h,w) levels (baseline.py:772-775), one launch
     return tgt_pyr, src_pyr
 
 

@@ -327,19 +327,26 @@ def smooth_bwd(depth_mhw, img_nhwc_, gscale):
 
 
 def frames_to_pyramid(frames_u8: torch.Tensor, num_scales: int, out: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
-    """uint8 frames (n,3,H,W), any strides -> list of planar fp32 levels (n,3,H>>s,W>>s) with values (u8/255)*2-1 averaged
-    over 2^s x 2^s blocks: the image part of iter_data_preparation fused with scale_pyramid (one kernel).
-    out: optional pre-allocated contiguous levels (e.g. slices of a source-major buffer)."""
+    """uint8 frames (n,3*G,H,W), any strides -> list of planar fp32 levels (G*n,3,H>>s,W>>s) with values (u8/255)*2-1 averaged
+    over 2^s x 2^s blocks: the image part of iter_data_preparation fused with scale_pyramid (ONE kernel launch).
+    G > 1 is the DataLoader's source block (B,3*S,H,W): group g of frame b lands in image g*n + b (source-major,
+    models/baseline.py:772-775).  out: optional pre-allocated contiguous levels."""
     if not frames_u8.is_cuda or frames_u8.dtype != torch.uint8:
         raise RuntimeError("frames_to_pyramid needs a CUDA uint8 tensor (there is no CPU fallback)")
     n, c, H, W = frames_u8.shape
-    if c != 3:
-        raise ValueError("frames must be (n,3,H,W)")
-    levels = list(out) if out is not None else [torch.empty(n, 3, H >> s, W >> s, device=frames_u8.device) for s in range(num_scales)]
+    if c % 3 or c == 0:
+        raise ValueError("frames must be (n,3*G,H,W)")
+    if not 1 <= num_scales <= _abi.SNDE_MAX_SCALES:
+        raise ValueError(f"num_scales must be 1..{_abi.SNDE_MAX_SCALES}")
+    R = 1 << (num_scales - 1)
+    if H % R or W % R:
+        raise RuntimeError(f"frames_to_pyramid: H and W must be multiples of 2^(num_scales-1) = {R} (got {H}x{W})")
+    G = c // 3
+    levels = list(out) if out is not None else [torch.empty(G * n, 3, H >> s, W >> s, device=frames_u8.device) for s in range(num_scales)]
     for s, t in enumerate(levels):
-        if t.shape != (n, 3, H >> s, W >> s) or not t.is_contiguous() or t.dtype != torch.float32:
-            raise ValueError("pyramid level buffers must be contiguous fp32 (n,3,H>>s,W>>s)")
+        if t.shape != (G * n, 3, H >> s, W >> s) or not t.is_contiguous() or t.dtype != torch.float32:
+            raise ValueError("pyramid level buffers must be contiguous fp32 (G*n,3,H>>s,W>>s)")
     ptrs = (C.c_void_p * num_scales)(*[t.data_ptr() for t in levels])
     st = frames_u8.stride()
-    _abi.check(_abi.lib().snde_frames_to_pyramid(n, H, W, num_scales, frames_u8.data_ptr(), st[0], st[1], st[2], st[3], ptrs, _stream()))
+    _abi.check(_abi.lib().snde_frames_to_pyramid_grouped(n, G, H, W, num_scales, frames_u8.data_ptr(), st[0], st[1], st[2], st[3], ptrs, _stream()))
     return levels
