@@ -10,8 +10,9 @@ __device__ __forceinline__ u64 fadd2(u64 a, u64 b) { u64 d; asm volatile("add.rn
 __device__ __forceinline__ u64 fmul2(u64 a, u64 b) { u64 d; asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 #define ILP 8
 template <int MODE> __global__ void k(float *out, int iters, float s) {
-    float a[ILP]; u64 p[ILP];
-    for (int i = 0; i < ILP; ++i) { a[i] = threadIdx.x * 1e-3f + i; p[i] = pack(a[i], a[i] + 1.f); }
+    float a[ILP]; u64 p[ILP]; unsigned q[ILP], q2[ILP];
+    for (int i = 0; i < ILP; ++i) { a[i] = threadIdx.x * 1e-3f + i; p[i] = pack(a[i], a[i] + 1.f); q[i] = threadIdx.x + i; q2[i] = q[i] * 3u; }
+    const unsigned qs = (unsigned)iters | 1u;
     const u64 ps = pack(s, s * 0.5f), pt = pack(1e-3f, 2e-3f);
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -23,10 +24,16 @@ template <int MODE> __global__ void k(float *out, int iters, float s) {
             if (MODE == 4) { a[i] = fmaf(a[i], s, 1e-3f); p[i] = ffma2(p[i], ps, pt); }   // mix 1:1
             if (MODE == 5) a[i] = __shfl_xor_sync(0xffffffffu, a[i], 1) + 1e-3f;        // SHFL + FADD
             if (MODE == 6) { float r; asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a[i])); a[i] = r; }
+            // does a packed op hold the ISSUE port for two cycles, or only the FMA pipe?  ALU-pipe companions (LOP3) tell:
+            if (MODE == 7) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(q[i]) : "r"(qs), "r"(q2[i]));                        // ALU only
+            if (MODE == 8) { p[i] = ffma2(p[i], ps, pt); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(q[i]) : "r"(qs), "r"(q2[i])); }   // FFMA2 + 1 ALU
+            if (MODE == 9) { p[i] = ffma2(p[i], ps, pt); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(q[i]) : "r"(qs), "r"(q2[i]));
+                             asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(q2[i]) : "r"(qs), "r"(q[i])); }                        // FFMA2 + 2 ALU
+            if (MODE == 10) { a[i] = fmaf(a[i], s, 1e-3f); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(q[i]) : "r"(qs), "r"(q2[i])); } // FFMA + 1 ALU
         }
     }
     float acc = 0.f;
-    for (int i = 0; i < ILP; ++i) { float x, y; unpack(p[i], x, y); acc += a[i] + x + y; }
+    for (int i = 0; i < ILP; ++i) { float x, y; unpack(p[i], x, y); acc += a[i] + x + y + (float)(q[i] ^ q2[i]); }
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 template <int MODE> void run(const char *name, int per_iter_inst) {
@@ -75,5 +82,6 @@ template <int MODE> void runlat(const char *name, int inst_per_iter) {
 int main() {
     runlat<0>("FFMA", 1); runlat<1>("FFMA2", 1); runlat<2>("FADD2", 1); runlat<3>("FFMA+FFMA2 alternating", 2); runlat<4>("SHFL", 1); runlat<5>("MUFU.RCP", 1);
     run<0>("FFMA", 1); run<1>("FFMA2", 1); run<2>("FADD2", 1); run<3>("FMUL2", 1); run<4>("FFMA+FFMA2", 2); run<5>("SHFL+FADD", 2); run<6>("MUFU.RCP", 1);
+    run<7>("LOP3 (ALU pipe)", 1); run<8>("FFMA2 + 1 LOP3", 2); run<9>("FFMA2 + 2 LOP3", 3); run<10>("FFMA + 1 LOP3", 2);
     return 0;
 }

@@ -575,69 +575,84 @@ extern "C" int snde_smooth_loss_bwd(int M, int h, int w, SndeMap depth, SndeImag
 // =============================================================================================
 struct PyrLevels { float *p[SNDE_MAX_SCALES]; };
 
+// grid: x = tile of the plane (tiles_x * tiles_y), y = channel + 3 * group, z = frame.  Everything inside a plane is 32-bit
+// index arithmetic with shifts (the kernel is instruction-bound, not bandwidth-bound: ncu, profiles/).
 template <int NS>
-__global__ void __launch_bounds__(256) frames_to_pyramid_kernel(int n, int groups, int H, int W, const uint8_t *__restrict__ frames,
+__global__ void __launch_bounds__(256) frames_to_pyramid_kernel(int n, int H, int W, int tiles_x, const uint8_t *__restrict__ frames,
                                                                 long long sn, long long sc, long long sh, long long sw, PyrLevels lv) {
     constexpr int R = 1 << (NS - 1);
     constexpr int TR = R > 16 ? R : 16, TC = 128;
-    // one pad word per 32 columns: the strided reads of the coarser levels (stride 2^s words across a warp) then hit 32
-    // different banks
-    constexpr int TCP = TC + TC / 32;
-    __shared__ float tile[TR][TCP];
-    auto col = [](int x) { return x + (x >> 5); };
-    const int tiles_x = (W + TC - 1) / TC, tiles_y = (H + TR - 1) / TR;
-    long long t = blockIdx.x;
-    const int tx = (int)(t % tiles_x); t /= tiles_x;
-    const int ty = (int)(t % tiles_y); t /= tiles_y;
-    const int c = (int)(t % 3); t /= 3;
-    const int g = (int)(t % groups);
-    const long long b = t / groups;
+    __shared__ __align__(16) float tile[TR][TC];
+    const int tx = (int)(blockIdx.x % (unsigned)tiles_x), ty = (int)(blockIdx.x / (unsigned)tiles_x);
+    const int cg = (int)blockIdx.y, g = cg / 3, c = cg - 3 * g;
+    const int b = (int)blockIdx.z;
     const int x0 = tx * TC, y0 = ty * TR;
     const int cols = min(TC, W - x0), rows = min(TR, H - y0);        // multiples of R (W % R == H % R == 0)
-    const uint8_t *src = frames + b * sn + (long long)(g * 3 + c) * sc + (long long)y0 * sh + (long long)x0 * sw;
+    const uint8_t *src = frames + b * sn + (long long)cg * sc + (long long)y0 * sh + (long long)x0 * sw;
     const long long plane = ((long long)g * n + b) * 3 + c;
     float *dst0 = lv.p[0] + (plane * H + y0) * (long long)W + x0;
-    const bool words = sw == 1 && ((sh | sc | sn) & 3) == 0 && (((uintptr_t)frames + (unsigned)(x0 & 3)) & 3) == 0 && (cols & 3) == 0 && (W & 3) == 0;
-    const bool vst = (W & 3) == 0 && (cols & 3) == 0 && ((uintptr_t)lv.p[0] & 15) == 0;
-    // ---- level 0: bytes -> normalised floats -> shared tile + global ----
-    for (int i = threadIdx.x; i < rows * (TC / 4); i += 256) {
-        const int y = i / (TC / 4), x4 = (i % (TC / 4)) * 4;
-        if (x4 >= cols) continue;
-        float v[4];
-        if (words) {
-            const unsigned w4 = __ldg(reinterpret_cast<const unsigned *>(src + (long long)y * sh + x4));
+    const int tid = (int)threadIdx.x;
+    // fast path: bytes contiguous along x and 4-byte aligned rows, level-0 rows 16-byte aligned
+    const bool words = sw == 1 && ((sh | sc | sn) & 3) == 0 && ((uintptr_t)frames & 3) == 0 && (W & 3) == 0;
+    const bool vst = words && ((uintptr_t)lv.p[0] & 15) == 0;
+    // ---- level 0: bytes -> normalised floats -> shared tile + global; thread = (row y, 4 columns x4), 8 rows per sweep ----
+    {
+        const int x4 = (tid & 31) * 4;
+        if (x4 < cols) {
+            const int sh32 = (int)sh;
+            for (int y = tid >> 5; y < rows; y += 8) {
+                float v[4];
+                if (words) {
+                    const unsigned w4 = __ldg(reinterpret_cast<const unsigned *>(src + y * sh32 + x4));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = (float)((w4 >> (8 * k)) & 0xffu);
-        } else {
+                    for (int k = 0; k < 4; ++k) v[k] = (float)__byte_perm(w4, 0u, 0x4440u + k);
+                } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = x4 + k < cols ? (float)__ldg(src + (long long)y * sh + (long long)(x4 + k) * sw) : 0.f;
-        }
+                    for (int k = 0; k < 4; ++k) v[k] = x4 + k < cols ? (float)__ldg(src + (long long)y * sh + (long long)(x4 + k) * sw) : 0.f;
+                }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = __fsub_rn(__fmul_rn(__fmul_rn(v[k], 1.f / 255.f), 2.f), 1.f);   // (u8 * 1/255) * 2 - 1, op by op
+                for (int k = 0; k < 4; ++k) v[k] = __fsub_rn(__fmul_rn(__fmul_rn(v[k], 1.f / 255.f), 2.f), 1.f);   // (u8 * 1/255) * 2 - 1, op by op
+                const float4 q = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(&tile[y][x4]) = q;
+                float *d = dst0 + y * W + x4;
+                if (vst) *reinterpret_cast<float4 *>(d) = q;                                    // a warp writes one 512-byte row segment
+                else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tile[y][col(x4) + k] = v[k];              // (x4 .. x4+3 never straddle a pad word)
-        float *d = dst0 + (long long)y * W + x4;
-        if (vst) *reinterpret_cast<float4 *>(d) = make_float4(v[0], v[1], v[2], v[3]);        // W % 4 == 0 and x0 % 128 == 0: aligned
-        else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (x4 + k < cols) d[k] = v[k];
+                    for (int k = 0; k < 4; ++k) if (x4 + k < cols) d[k] = v[k];
+                }
+            }
         }
     }
     __syncthreads();
-    // ---- levels 1 .. NS-1 from the shared tile ----
+    // ---- levels 1 .. NS-1 from the shared tile: every output sums its 2^s x 2^s window in row-major order; the window rows come
+    //      in as 8- / 16-byte shared loads, consecutive threads take consecutive outputs of a row ----
 #pragma unroll
     for (int s = 1; s < NS; ++s) {
-        const int k = 1 << s, hs = H >> s, ws = W >> s;
+        constexpr int dummy = 0; (void)dummy;
+        const int k = 1 << s, ws = W >> s;
         const int ocols = cols >> s, orows = rows >> s;
-        float *dst = lv.p[s] + (plane * hs + (y0 >> s)) * (long long)ws + (x0 >> s);
+        const int lcols = 7 - s;                                     // log2 of the outputs per full tile row (TC >> s)
+        float *dst = lv.p[s] + (plane * (H >> s) + (y0 >> s)) * (long long)ws + (x0 >> s);
         const float inv = 1.f / (float)(k * k);
-        for (int i = threadIdx.x; i < orows * ocols; i += 256) {
-            const int oy = i / ocols, ox = i - oy * ocols;
+        for (int i = tid; i < (orows << lcols); i += 256) {
+            const int oy = i >> lcols, ox = i & ((1 << lcols) - 1);
+            if (ox >= ocols) continue;
             float acc = 0.f;
-            for (int dy = 0; dy < k; ++dy)
-#pragma unroll 4
-                for (int dx = 0; dx < k; ++dx) acc = __fadd_rn(acc, tile[oy * k + dy][col(ox * k + dx)]);
-            dst[(long long)oy * ws + ox] = __fmul_rn(acc, inv);
+            const float *row = &tile[oy << s][ox << s];
+#pragma unroll
+            for (int dy = 0; dy < k; ++dy, row += TC) {
+                if (s == 1) {
+                    const float2 q = *reinterpret_cast<const float2 *>(row);
+                    acc = __fadd_rn(__fadd_rn(acc, q.x), q.y);
+                } else {
+#pragma unroll
+                    for (int dx = 0; dx < k; dx += 4) {
+                        const float4 q = *reinterpret_cast<const float4 *>(row + dx);
+                        acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, q.x), q.y), q.z), q.w);
+                    }
+                }
+            }
+            dst[oy * ws + ox] = __fmul_rn(acc, inv);
         }
     }
 }
@@ -653,16 +668,17 @@ extern "C" int snde_frames_to_pyramid_grouped(int n, int groups, int H, int W, i
     for (int s = 0; s < SNDE_MAX_SCALES; ++s) lv.p[s] = nullptr;
     for (int s = 0; s < num_scales; ++s) { if (!levels[s]) return SNDE_ERR_NULL; lv.p[s] = levels[s]; }
     const int TR = R > 16 ? R : 16;
-    const long long blocks = (long long)n * groups * 3 * ((H + TR - 1) / TR) * ((W + 127) / 128);
-    if (blocks >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
+    const int tiles_x = (W + 127) / 128, tiles_y = (H + TR - 1) / TR;
+    if (n > 65535 || groups * 3 > 65535 || (long long)sh * TR + W >= (1LL << 31)) return SNDE_ERR_TOO_LARGE;
+    const dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)(3 * groups), (unsigned)n);
     cudaStream_t st = as_stream(stream);
     switch (num_scales) {
-        case 1: frames_to_pyramid_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(n, groups, H, W, frames, sn, sc, sh, sw, lv); break;
-        case 2: frames_to_pyramid_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(n, groups, H, W, frames, sn, sc, sh, sw, lv); break;
-        case 3: frames_to_pyramid_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(n, groups, H, W, frames, sn, sc, sh, sw, lv); break;
-        case 4: frames_to_pyramid_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(n, groups, H, W, frames, sn, sc, sh, sw, lv); break;
-        case 5: frames_to_pyramid_kernel<5><<<(unsigned)blocks, 256, 0, st>>>(n, groups, H, W, frames, sn, sc, sh, sw, lv); break;
-        default: frames_to_pyramid_kernel<6><<<(unsigned)blocks, 256, 0, st>>>(n, groups, H, W, frames, sn, sc, sh, sw, lv); break;
+        case 1: frames_to_pyramid_kernel<1><<<grid, 256, 0, st>>>(n, H, W, tiles_x, frames, sn, sc, sh, sw, lv); break;
+        case 2: frames_to_pyramid_kernel<2><<<grid, 256, 0, st>>>(n, H, W, tiles_x, frames, sn, sc, sh, sw, lv); break;
+        case 3: frames_to_pyramid_kernel<3><<<grid, 256, 0, st>>>(n, H, W, tiles_x, frames, sn, sc, sh, sw, lv); break;
+        case 4: frames_to_pyramid_kernel<4><<<grid, 256, 0, st>>>(n, H, W, tiles_x, frames, sn, sc, sh, sw, lv); break;
+        case 5: frames_to_pyramid_kernel<5><<<grid, 256, 0, st>>>(n, H, W, tiles_x, frames, sn, sc, sh, sw, lv); break;
+        default: frames_to_pyramid_kernel<6><<<grid, 256, 0, st>>>(n, H, W, tiles_x, frames, sn, sc, sh, sw, lv); break;
     }
     SNDE_CHECK_LAUNCH();
     return SNDE_OK;
