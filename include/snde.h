@@ -35,7 +35,7 @@ extern "C" {
 #define SNDE_API
 #endif
 
-#define SNDE_VERSION 100      /* 0.1.0 */
+#define SNDE_VERSION 200      /* 0.2.0: grouped pyramid prep, image-gradient outputs of the fused loss */
 #define SNDE_MAX_SCALES 6
 #define SNDE_MAX_SOURCES 8     /* source views per target in the fused loss */
 
@@ -94,6 +94,14 @@ typedef struct SndeLossScale {
     SndeMap mask_fwd, mask_bwd;         /* optional (ptr may be NULL): explainability weight per pixel, (S*B,h,w); extension */
     SndeImageOut warped_fwd, warped_bwd;/* optional outputs (S*B,3,h,w): flow_warp results (logged by the reference every 10k it) */
     SndeImageOut err_fwd, err_bwd;      /* optional outputs (S*B,3,h,w): image_similarity maps */
+    /* optional (SNDE_LOSS_GRAD; extension, section 8(f3)): d loss_rigid_warp / d image, ACCUMULATED into buffers the caller has
+     * zero-filled -- (B,3,h,w) and (S*B,3,h,w), any strides.  Two parts land in the same buffer: the dense part (the image as
+     * the x argument of image_similarity) and the scatter part (the image as sampled by bilinear_sampler: index_select
+     * backward, utils_edited.py:473-476), the latter with warp-aggregated atomics (lanes hitting the same pixel are found with
+     * match.any; one atomic per distinct address).  The smoothness term gives the images no gradient (as in the reference,
+     * where they are data).  Summation order varies from run to run in the last bits; the deterministic alternative is the
+     * stand-alone snde_bilinear_sampler_bwd_deterministic. */
+    SndeImageOut grad_tgt_img, grad_src_img;
 } SndeLossScale;
 
 enum {

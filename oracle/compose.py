@@ -35,7 +35,7 @@ def multi_scale_intrinsics(orc: Oracle, K, num_scales):
 
 
 def geonet_loss(orc: Oracle, tgt_pyr, src_pyr, depth_pyr, poses, K_ms, alpha=0.85, w_rigid=1.0,
-                w_smooth=0.5, want_grad=True, keep_maps=False, masks=None):
+                w_smooth=0.5, want_grad=True, keep_maps=False, masks=None, want_grad_images=False):
     """tgt_pyr[s] (B,h,w,3); src_pyr[s] (S*B,h,w,3) source-major; depth_pyr[s] (B(1+S),h,w);
     poses (B,S,6); K_ms (B,scales,3,3).  Returns a dict of losses (+ grads, + maps)."""
     num_scales = len(tgt_pyr)
@@ -85,10 +85,17 @@ def geonet_loss(orc: Oracle, tgt_pyr, src_pyr, depth_pyr, poses, K_ms, alpha=0.8
         if want_grad:
             g = orc.dt(w_rigid * S / 2 / fwd_err.size)
             gerr = np.full(fwd_err.shape, g, orc.dt)
-            _, gy_f = orc.image_similarity_bwd(alpha, tgt_tile, fwd_warp, gerr * mf if mf is not None else gerr)
-            _, gy_b = orc.image_similarity_bwd(alpha, src, bwd_warp, gerr * mb if mb is not None else gerr)
-            gc_f, _ = orc.bilinear_sampler_bwd(src, fwd_coords, gy_f)
-            gc_b, _ = orc.bilinear_sampler_bwd(tgt_tile, bwd_coords, gy_b)
+            gx_f, gy_f = orc.image_similarity_bwd(alpha, tgt_tile, fwd_warp, gerr * mf if mf is not None else gerr)
+            gx_b, gy_b = orc.image_similarity_bwd(alpha, src, bwd_warp, gerr * mb if mb is not None else gerr)
+            gc_f, gi_f = orc.bilinear_sampler_bwd(src, fwd_coords, gy_f, want_gimg=want_grad_images)
+            gc_b, gi_b = orc.bilinear_sampler_bwd(tgt_tile, bwd_coords, gy_b, want_gimg=want_grad_images)
+            if want_grad_images:
+                # what autograd gives images that require grad (extension; the reference's images are data): the dense part through
+                # image_similarity's x argument + the scatter part through index_select (utils_edited.py:473-476); target
+                # copies (tgt_tile = tgt.repeat(S)) sum over the S sources.  smooth_loss gives the images nothing.
+                out.setdefault("grad_tgt_img", []).append(
+                    (gx_f.astype(np.float64) + gi_b.astype(np.float64)).reshape(S, B, h, w, C).sum(0).astype(orc.dt))
+                out.setdefault("grad_src_img", []).append((gi_f.astype(np.float64) + gx_b.astype(np.float64)).astype(orc.dt))
             gd_f, gPf, gKi_f = orc.rigid_flow_bwd(d_fwd, Kinv_n, Pf, gc_f)
             gd_b, gPb, gKi_b = orc.rigid_flow_bwd(d_bwd, Kinv_n, Pb, gc_b)
             gdepth = np.zeros(depth.shape, np.float64)

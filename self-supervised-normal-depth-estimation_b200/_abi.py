@@ -40,6 +40,7 @@ class SndeLossScale(C.Structure):
         ("mask_fwd", SndeMap), ("mask_bwd", SndeMap),
         ("warped_fwd", SndeImage), ("warped_bwd", SndeImage),
         ("err_fwd", SndeImage), ("err_bwd", SndeImage),
+        ("grad_tgt_img", SndeImage), ("grad_src_img", SndeImage),
     ]
 
 
@@ -154,7 +155,7 @@ def make_loss_args(B, S, alpha, flags, padding_mode, poses_ptr, scales, loss_out
         d.tgt, d.src, d.depth = sc["tgt"], sc["src"], sc["depth"]
         d.K, d.xtab, d.ytab = sc["K"], sc["xtab"], sc["ytab"]
         d.photo_weight, d.smooth_weight = sc["photo_weight"], sc["smooth_weight"]
-        for key in ("grad_depth", "mask_fwd", "mask_bwd", "warped_fwd", "warped_bwd", "err_fwd", "err_bwd"):
+        for key in ("grad_depth", "mask_fwd", "mask_bwd", "warped_fwd", "warped_bwd", "err_fwd", "err_bwd", "grad_tgt_img", "grad_src_img"):
             if sc.get(key) is not None:
                 setattr(d, key, sc[key])
     a.loss_out, a.grad_poses, a.grad_K = loss_out_ptr, grad_poses_ptr, grad_K_ptr

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(64) loss_final_kernel(int B, int S, int ns, in
 // nothing, so there is no CTA-wide barrier in the kernel; the two warps of a pair meet at a 64-thread named barrier.
 // Warps w and w + PAIRS form a pair; which of the two is the geometry warp alternates with the CTA index, so every
 // scheduler (warp index mod 4) hosts both kinds of warp.
-template <bool GRAD, bool GRADK, bool EXTRA, bool FAST, bool DISP = false>
+template <bool GRAD, bool GRADK, bool EXTRA, bool FAST, bool DISP = false, bool GIMG = false>
 // (register budget: each of the four schedulers of an SM has its own 16 K registers, so 3 warps per scheduler may use 168
 // registers and 4 warps 128 -- nothing in between: 14 warps of 144 registers do not launch)
 __global__ void __launch_bounds__(StripCfg::NT, SNDE_STRIP_CTAS_PER_SM) loss_strip_kernel(const __grid_constant__ DevLoss p) {
@@ -133,10 +133,10 @@ __global__ void __launch_bounds__(StripCfg::NT, SNDE_STRIP_CTAS_PER_SM) loss_str
         const int task = __shfl_sync(0xffffffffu, sm.task, 0);
         if (task >= p.total_tasks) break;
 #if defined(SNDE_ONLY_ROLE)            // register-budget probe of one role (never shipped)
-        if (role == SNDE_ONLY_ROLE) { if (SNDE_ONLY_ROLE == 0) geo_role<GRAD, GRADK, EXTRA, FAST, DISP>(p, task, lane, sm, bar); else ssim_role<GRAD, EXTRA, FAST, DISP>(p, task, lane, sm, bar); }
+        if (role == SNDE_ONLY_ROLE) { if (SNDE_ONLY_ROLE == 0) geo_role<GRAD, GRADK, EXTRA, FAST, DISP, GIMG>(p, task, lane, sm, bar); else ssim_role<GRAD, EXTRA, FAST, DISP, GIMG>(p, task, lane, sm, bar); }
 #else
-        if (role == 0) geo_role<GRAD, GRADK, EXTRA, FAST, DISP>(p, task, lane, sm, bar);
-        else ssim_role<GRAD, EXTRA, FAST, DISP>(p, task, lane, sm, bar);
+        if (role == 0) geo_role<GRAD, GRADK, EXTRA, FAST, DISP, GIMG>(p, task, lane, sm, bar);
+        else ssim_role<GRAD, EXTRA, FAST, DISP, GIMG>(p, task, lane, sm, bar);
 #endif
     }
 }
@@ -180,7 +180,7 @@ static int sm_count_of(int dev) {            // 0 on failure
     g_sm_count[dev].store(n, std::memory_order_relaxed);
     return n;
 }
-static std::atomic<bool> g_attr_done[8][64];
+static std::atomic<bool> g_attr_done[12][64];
 }  // namespace
 
 // Rows per strip segment, shared by snde_loss_fwdbwd and snde_loss_num_tiles.  Longer segments recompute fewer halo rows (a
@@ -256,19 +256,22 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     // EXTRA variants honour masks / warped+error outputs / border padding / intrinsics gradients; FAST ones need planar,
     // aligned tensors at every scale (the optional mask / output tensors keep their own strides).  The lean fast one is
     // the hot path.
-    bool extra = gradk || a->padding_mode != SNDE_PAD_ZEROS, fast = true;
+    bool extra = gradk || a->padding_mode != SNDE_PAD_ZEROS, fast = true, gimg = false;
     const bool disp = (a->flags & SNDE_LOSS_DISPARITY) != 0;
     for (int s = 0; s < ns; ++s) {
         const SndeLossScale &in = a->scale[s];
         extra = extra || in.mask_fwd.ptr || in.mask_bwd.ptr || in.warped_fwd.ptr || in.warped_bwd.ptr || in.err_fwd.ptr || in.err_bwd.ptr;
+        gimg = gimg || in.grad_tgt_img.ptr || in.grad_src_img.ptr;
         fast = fast && d.sc[s].fast;
     }
+    if (gimg) extra = true;                      // image gradients ride on the general instance
     // disparity input: one more lean instance (<GRAD, FAST, DISP>); every other combination goes through the general one
     if (disp && !(grad && fast && !extra)) extra = true;
     if (!grad) {
         if (extra) rc = launch(loss_strip_kernel<false, false, true, false>, 0);
         else rc = fast ? launch(loss_strip_kernel<false, false, false, true>, 1) : launch(loss_strip_kernel<false, false, false, false>, 2);
-    } else if (extra) rc = fast ? launch(loss_strip_kernel<true, true, true, true>, 7) : launch(loss_strip_kernel<true, true, true, false>, 3);
+    } else if (gimg) rc = fast ? launch(loss_strip_kernel<true, true, true, true, false, true>, 8) : launch(loss_strip_kernel<true, true, true, false, false, true>, 9);
+    else if (extra) rc = fast ? launch(loss_strip_kernel<true, true, true, true>, 7) : launch(loss_strip_kernel<true, true, true, false>, 3);
     else if (disp) rc = launch(loss_strip_kernel<true, false, false, true, true>, 6);
     else rc = fast ? launch(loss_strip_kernel<true, false, false, true>, 4) : launch(loss_strip_kernel<true, false, false, false>, 5);
     if (rc) return rc;

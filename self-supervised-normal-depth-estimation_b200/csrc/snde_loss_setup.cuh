@@ -142,8 +142,11 @@ static inline int build_dev_loss(const SndeLossArgs *a, DevLoss &d, const LossWo
             !fits32(0, in.depth.sh, in.depth.sw, in.h, in.w) || !fits32(0, in.grad_depth.sh, in.grad_depth.sw, in.h, in.w) ||
             !fits32(0, in.mask_fwd.sh, in.mask_fwd.sw, in.h, in.w) || !fits32(0, in.mask_bwd.sh, in.mask_bwd.sw, in.h, in.w) ||
             !fits32(in.warped_fwd.sc, in.warped_fwd.sh, in.warped_fwd.sw, in.h, in.w) || !fits32(in.warped_bwd.sc, in.warped_bwd.sh, in.warped_bwd.sw, in.h, in.w) ||
-            !fits32(in.err_fwd.sc, in.err_fwd.sh, in.err_fwd.sw, in.h, in.w) || !fits32(in.err_bwd.sc, in.err_bwd.sh, in.err_bwd.sw, in.h, in.w))
+            !fits32(in.err_fwd.sc, in.err_fwd.sh, in.err_fwd.sw, in.h, in.w) || !fits32(in.err_bwd.sc, in.err_bwd.sh, in.err_bwd.sw, in.h, in.w) ||
+            !fits32(in.grad_tgt_img.sc, in.grad_tgt_img.sh, in.grad_tgt_img.sw, in.h, in.w) ||
+            !fits32(in.grad_src_img.sc, in.grad_src_img.sh, in.grad_src_img.sw, in.h, in.w))
             return SNDE_ERR_TOO_LARGE;
+        if ((in.grad_tgt_img.ptr || in.grad_src_img.ptr) && !(a->flags & SNDE_LOSS_GRAD)) return SNDE_ERR_ARG;
         o.h = in.h; o.w = in.w;
         o.tiles_x = (in.w + StripCfg::TW - 1) / StripCfg::TW;
         // fast path: planar tensors, unit x-stride, even row / plane / batch strides and 8-byte aligned bases, even width:
@@ -173,6 +176,7 @@ static inline int build_dev_loss(const SndeLossArgs *a, DevLoss &d, const LossWo
         o.mask_fwd = dev(in.mask_fwd); o.mask_bwd = dev(in.mask_bwd);
         o.warped_fwd = dev(in.warped_fwd); o.warped_bwd = dev(in.warped_bwd);
         o.err_fwd = dev(in.err_fwd); o.err_bwd = dev(in.err_bwd);
+        o.gimg_tgt = dev(in.grad_tgt_img); o.gimg_src = dev(in.grad_src_img);
     }
     if (lay) d.counter = (int *)(ws + lay->counter);
     // Task table.  Most owners are cut into long segments (seg_rows rows: few halo rows recomputed); the last fine_permille

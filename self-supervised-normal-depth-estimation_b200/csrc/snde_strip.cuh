@@ -93,6 +93,7 @@ struct DevScale {
     int pad_;
     DevMap mask_fwd, mask_bwd;
     DevImageOut warped_fwd, warped_bwd, err_fwd, err_bwd;
+    DevImageOut gimg_tgt, gimg_src;  // optional: d loss_rigid_warp / d image, accumulated (section 8(f3))
 };
 
 // one block of the task table: `count` tasks starting at number `begin`; owners first_owner.. of class cls (0 = F, 1 = R)
@@ -193,6 +194,31 @@ SNDE_STRIP_FN void atomic_add_double(double *dst, double v) { atomicAdd(dst, v);
 SNDE_STRIP_FN void add_pair_noreturn(float *dst, F2 v) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(v.x), "f"(v.y) : "memory");
 }
+SNDE_STRIP_FN void atomic_add_float(float *dst, float v) { atomicAdd(dst, v); }
+SNDE_STRIP_FN void add_pair_atomic(float *dst, F2 v) { asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(v.x), "f"(v.y) : "memory"); }
+// Warp-aggregated scatter: all 32 lanes call this together.  Lanes with the same `key` (a pixel of the image being
+// scattered into) form a group; the lowest lane of a group gathers the others' values in lane order and alone issues the
+// atomic.  `above` = the group's lanes above this one, `max_group` = the size of the largest group of the warp (the trip
+// count of the gathering loop; 1 when no two lanes collide).
+struct TapGroup { unsigned above; int max_group; bool leader; };
+SNDE_STRIP_FN TapGroup tap_group(int lane, long long key) {
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    TapGroup g;
+    g.above = lane == 31 ? 0u : peers & ~((2u << lane) - 1u);
+    g.leader = (peers & ((1u << lane) - 1u)) == 0u;
+    g.max_group = (int)__reduce_max_sync(0xffffffffu, (unsigned)__popc(peers));
+    return g;
+}
+SNDE_STRIP_FN float group_sum(int lane, const TapGroup &g, float v) {
+    float sum = v;
+    unsigned rest = g.above;
+    for (int it = 1; it < g.max_group; ++it) {
+        const int src = rest ? __ffs((int)rest) - 1 : lane;
+        const float o = __shfl_sync(0xffffffffu, v, src);
+        if (rest) { sum += o; rest &= rest - 1u; }
+    }
+    return sum;
+}
 SNDE_STRIP_FN void warp_fence(int) { __syncwarp(); }
 // rendezvous of the two warps of a pair (named barrier `bar`, 64 threads); orders their shared-memory traffic
 SNDE_STRIP_FN void pair_barrier(int, int bar) { asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory"); }
@@ -270,6 +296,11 @@ SNDE_STRIP_FN float warp_sum_scatter(int who, const float (&in)[N]) {
 }
 SNDE_STRIP_FN void atomic_add_double(double *dst, double v) { *dst += v; }
 SNDE_STRIP_FN void add_pair_noreturn(float *dst, F2 v) { dst[0] += v.x; dst[1] += v.y; }
+SNDE_STRIP_FN void atomic_add_float(float *dst, float v) { *dst += v; }
+SNDE_STRIP_FN void add_pair_atomic(float *dst, F2 v) { dst[0] += v.x; dst[1] += v.y; }
+struct TapGroup { unsigned above; int max_group; bool leader; };
+SNDE_STRIP_FN TapGroup tap_group(int, long long) { return TapGroup{0u, 1, true}; }        // emulation: every fiber adds its own value
+SNDE_STRIP_FN float group_sum(int, const TapGroup &, float v) { return v; }
 SNDE_STRIP_FN void warp_fence(int who) { host_warp_sync(who); }
 SNDE_STRIP_FN void pair_barrier(int who, int) { host_pair_sync(who); }
 template <int BYTES>
@@ -291,6 +322,7 @@ SNDE_STRIP_FN F2 ldcg2(const float *p) { return F2{p[0], p[1]}; }
 // (xx + yy is carried as ONE sum q: SSIM and its backward use the two second moments only through their sum)
 struct HS { P2 x, y, q, xy; };
 struct CS { P2 a, b, c; };
+struct CSX { P2 d; };           // box sums of the x-side coefficient (image gradients only)
 
 SNDE_STRIP_FN void hsum_row(const F2 xv, const F2 yv, float xm, float xp, float ym, float yp, HS &o) {
     const float tx = xv.x + xv.y, ty = yv.x + yv.y;
@@ -416,7 +448,7 @@ struct OwnerRows {
 // ===============================================================================================================
 // SSIM warp
 // ===============================================================================================================
-template <bool GRAD, bool EXTRA, bool FAST, bool DISP>
+template <bool GRAD, bool EXTRA, bool FAST, bool DISP, bool GIMG = false>
 SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, int bar) {
     const int lane = who & 31;
     StripTask T;
@@ -441,11 +473,19 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
             eout_base = eout.p ? eout.p + n * eout.sn : nullptr; eout_sc = eout.sc; eout_sh = eout.sh; eout_sw = eout.sw;
         }
         const bool has_mask = EXTRA && mask_base != nullptr;
+        // image gradients (GIMG): the dense part -- d loss / d(owner image) through the x argument of image_similarity -- is
+        // formed here next to d loss / d(warped) and added to the owner's gradient image
+        float *gown_base = nullptr; int gown_sc = 0, gown_sh = 0, gown_sw = 0;
+        if (GIMG) {
+            const DevImageOut &go = T.clsF ? sc.gimg_tgt : sc.gimg_src;
+            gown_base = go.p ? go.p + (long long)T.m * go.sn : nullptr; gown_sc = go.sc; gown_sh = go.sh; gown_sw = go.sw;
+        }
         // rolling sums: the two carried rows start as zero rows
         HS s1[3], s2[3];          // H(t-2) + H(t-1), H(t-1)
         CS c1[3], c2[3];          // Hc(t-3) + Hc(t-2), Hc(t-2)
+        CSX xa1[3], xa2[3];       // the same for the x-side coefficient (GIMG)
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) { hs_zero(s1[ch]); hs_zero(s2[ch]); cs_zero(c1[ch]); cs_zero(c2[ch]); }
+        for (int ch = 0; ch < 3; ++ch) { hs_zero(s1[ch]); hs_zero(s2[ch]); cs_zero(c1[ch]); cs_zero(c2[ch]); xa1[ch].d = xa2[ch].d = p2s(0.f); }
         float err_acc = 0.f;
 
         // prologue: owner rows t_begin .. t_begin+2 on their way into the ring, the first two landed and published
@@ -484,6 +524,7 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                 // (SNDE_SSIM_STRAIGHT: a row that is not a phase-B row runs the same arithmetic on finite sums and contributes
                 // exact zeros (ngq = 0) and nothing to the error sum)
                 CS co; cs_zero(co);
+                P2 cod = p2s(0.f);
                 if (SNDE_SSIM_STRAIGHT || rowB) {
                     HS tot; hs_add(s1[ch], H, tot);
                     const F2 xc = sm.X[rb & 7][ch][lane], yc = sm.Y[rb & 3][ch][lane];
@@ -503,6 +544,7 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                         ngq[q] = (rowB && vq[q] == vcq[q]) ? (EXTRA ? ngSm[q] * mk[q] : ngSm[q]) : 0.f;       // the clamp passes gradient inside [0,1] only
                     }
                     if (GRAD) ssim_sums_bwd_p(ss, tot.x, tot.y, p2(ngq[0], ngq[1]), co.a, co.b, co.c);
+                    if (GRAD && GIMG) cod = ssim_sums_bwd_x_p(ss, tot.x, tot.y, p2(ngq[0], ngq[1]));
                 }
                 hs_add(s2[ch], H, s1[ch]);        // s1 <- H(t-1) + H(t)
                 s2[ch] = H;
@@ -519,6 +561,14 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                         Hc.b = p2add(p2(from_left[1], from_right[1]), p2s(tb));
                         Hc.c = p2add(p2(from_left[2], from_right[2]), p2s(tc));
                     }
+                    P2 Hd = p2s(0.f);
+                    if (GIMG) {
+                        const float dl = p2lo(cod), dh = p2hi(cod);
+                        const float to_right[1] = {dh}, to_left[1] = {dl};
+                        float from_left[1], from_right[1];
+                        neighbor_exchange<1>(who, to_right, to_left, from_left, from_right);
+                        Hd = p2add(p2(from_left[0], from_right[0]), p2s(dl + dh));
+                    }
                     // ---------------- phase C (row t-2): dL/d(warped) ----------------
                     // (computed every step, stored when the row exists: see phase B)
                     if (SNDE_SSIM_STRAIGHT || doC) {
@@ -529,9 +579,17 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                         const float l0 = d0 > 0.f ? gl[0] : (d0 < 0.f ? -gl[0] : 0.f), l1 = d1 > 0.f ? gl[1] : (d1 < 0.f ? -gl[1] : 0.f);
                         const P2 po = p2sub(p2fma(p2add(yv, yv), bs.b, p2fma(xv, bs.c, bs.a)), p2(l0, l1));
                         if (doC) sm.PO[rc & 1][ch][lane] = f2p(po);
+                        if (GIMG && gown_base && doC) {
+                            // d loss / dx(p) = box(c_sx) + 2 x box(c_sxx) + y box(c_sxy) + (1 - alpha) g sign(x - y)
+                            const F2 pox = f2p(p2add(p2fma(p2add(xv, xv), bs.b, p2fma(yv, bs.c, p2add(xa1[ch].d, Hd))), p2(l0, l1)));
+                            float *dst = gown_base + (ch * gown_sc + rc * gown_sh + T.ix0 * gown_sw);
+                            if (T.colI[0]) atomic_add_float(dst, pox.x);
+                            if (T.colI[1]) atomic_add_float(dst + gown_sw, pox.y);
+                        }
                     }
                     cs_add(c2[ch], Hc, c1[ch]);   // c1 <- Hc(t-2) + Hc(t-1)
                     c2[ch] = Hc;
+                    if (GIMG) { xa1[ch].d = p2add(xa2[ch].d, Hd); xa2[ch].d = Hd; }
                 }
             }
             }
@@ -555,7 +613,7 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
 // ===============================================================================================================
 // geometry warp
 // ===============================================================================================================
-template <bool GRAD, bool GRADK, bool EXTRA, bool FAST, bool DISP>
+template <bool GRAD, bool GRADK, bool EXTRA, bool FAST, bool DISP, bool GIMG = false>
 struct GeoLane {
     const DevLoss &p;
     const DevScale &sc;
@@ -570,6 +628,7 @@ struct GeoLane {
     // current other image
     const float *oth_base; int oth_sc, oth_sh, oth_sw;
     float *wout_base; int wout_sc, wout_sh, wout_sw;
+    float *gim_base; int gim_sc, gim_sh, gim_sw;      // gradient image of the OTHER image (GIMG: the scatter part)
     float P[12], Ki[9];       // projection and inverse intrinsics of the current pass
     // accumulators
     float dP[12], dK[9], sx_acc, sy_acc;
@@ -723,6 +782,32 @@ struct GeoLane {
             P2 gu[3], gcam[3];
             const P2 gdp = reproject_bwd_fast_p(P, rp, gx, gy, gu, gcam, on[0], on[1]);
             const float gdq[2] = {p2lo(gdp), p2hi(gdp)};
+            if (GIMG && gim_base) {
+                // ---- image-gradient scatter of row r (index_select backward, utils_edited.py:473-476): the sample position
+                //      again (with the division), its four taps and weights, dL/d(warped) times the weight to every tap.  Lanes
+                //      whose taps land on the same pixel are grouped (match.any): one atomic per distinct pixel and channel. ----
+                ReprojP rq; reproject_fast_p(Ki, P, xtp, yt2, d2, rq);
+                P2 xsp, ysp; flow_coords_p(rq, xtp, yt2, xsp, ysp);
+                const float xs[2] = {p2lo(xsp), p2hi(xsp)}, ys[2] = {p2lo(ysp), p2hi(ysp)};
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    Taps tp; make_taps(xs[q], ys[q], T.h, T.w, (EXTRA && p.padding) ? 1 : 0, tp);
+                    const bool live = on[q] && ((EXTRA && p.padding) || tap_valid(xs[q], ys[q], T.h, T.w, 0) != 0.f);
+                    const float wk[4] = {tp.wx0 * tp.wy0, tp.wx0 * tp.wy1, tp.wx1 * tp.wy0, tp.wx1 * tp.wy1};
+                    const int ok[4] = {tp.y0 * gim_sh + tp.x0 * gim_sw, tp.y1 * gim_sh + tp.x0 * gim_sw,
+                                       tp.y0 * gim_sh + tp.x1 * gim_sw, tp.y1 * gim_sh + tp.x1 * gim_sw};
+                    const float pq[3] = {q ? p2hi(po[0]) : p2lo(po[0]), q ? p2hi(po[1]) : p2lo(po[1]), q ? p2hi(po[2]) : p2lo(po[2])};
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const TapGroup grp = tap_group(lane, live ? (long long)ok[k4] : -(long long)(1 + lane * 8 + q * 4 + k4));
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            const float sum = group_sum(lane, grp, live ? wk[k4] * pq[ch] : 0.f);
+                            if (grp.leader && live) atomic_add_float(gim_base + (ch * gim_sc + ok[k4]), sum);
+                        }
+                    }
+                }
+            }
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 gd[q] = gdq[q];               // (exact zero for an idle pixel)
@@ -840,14 +925,14 @@ struct GeoLane {
 // warped / error-map outputs and border padding.  FAST: planar tensors with unit x-stride and 8-byte aligned rows
 // (64-bit loads / stores of the lane's pixel pair).  DISP: the depth maps hold disparities (lean instance; the EXTRA
 // instance handles the flag at run time).
-template <bool GRAD, bool GRADK, bool EXTRA, bool FAST, bool DISP>
+template <bool GRAD, bool GRADK, bool EXTRA, bool FAST, bool DISP, bool GIMG = false>
 SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, int bar) {
     const int lane = who & 31;
     StripTask T;
     decode_task(p, task, lane, T);
     const DevScale &sc = p.sc[T.scale];
     const int B = p.B;
-    GeoLane<GRAD, GRADK, EXTRA, FAST, DISP> L(p, sc, sm, T, lane);
+    GeoLane<GRAD, GRADK, EXTRA, FAST, DISP, GIMG> L(p, sc, sm, T, lane);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         L.xt[q] = T.in[q] ? ldg(sc.xtab + (T.ix0 + q)) : 0.f;
@@ -871,6 +956,11 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
         const DevImage &oth = clsF ? sc.src : sc.tgt;
         L.oth_base = oth.p + (clsF ? n : (long long)b) * oth.sn; L.oth_sc = oth.sc; L.oth_sh = oth.sh; L.oth_sw = oth.sw;
         L.wout_base = nullptr; L.wout_sc = L.wout_sh = L.wout_sw = 0;
+        L.gim_base = nullptr; L.gim_sc = L.gim_sh = L.gim_sw = 0;
+        if (GIMG) {
+            const DevImageOut &go = clsF ? sc.gimg_src : sc.gimg_tgt;
+            L.gim_base = go.p ? go.p + (clsF ? n : (long long)b) * go.sn : nullptr; L.gim_sc = go.sc; L.gim_sh = go.sh; L.gim_sw = go.sw;
+        }
         if (EXTRA) {
             const DevImageOut &wout = clsF ? sc.warped_fwd : sc.warped_bwd;
             L.wout_base = wout.p ? wout.p + n * wout.sn : nullptr; L.wout_sc = wout.sc; L.wout_sh = wout.sh; L.wout_sw = wout.sw;

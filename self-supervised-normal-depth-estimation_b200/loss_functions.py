@@ -86,7 +86,7 @@ _PYR_CACHE: "dict[tuple, tuple]" = {}
 _PLAN_CACHE_MAX = 16
 
 
-def _cached_plan(cfg, poses, K_ms, depth_pyr, tgt_pyr, src_pyr, need, want_K):
+def _cached_plan(cfg, poses, K_ms, depth_pyr, tgt_pyr, src_pyr, need, want_K, want_img=False):
     """FusedLossPlan for this call SHAPE: shapes, strides, device, stream and options -- never buffer addresses, so a trainer
     whose depth / poses are fresh network outputs every step hits the cache.  The cached plan holds no caller tensor; its
     pointer fields are patched per call (ops.FusedLossPlan.rebind)."""
@@ -95,7 +95,7 @@ def _cached_plan(cfg, poses, K_ms, depth_pyr, tgt_pyr, src_pyr, need, want_K):
     masks = cfg["masks"]
     key = (str(poses.device), torch.cuda.current_stream().cuda_stream, sig(poses), tuple(sig(t) for t in depth_pyr),
            tuple(sig(t) for t in tgt_pyr), tuple(sig(t) for t in src_pyr),
-           cfg["alpha"], tuple(cfg["photo_weights"]), tuple(cfg["smooth_weights"]), need, want_K, cfg["padding_mode"],
+           cfg["alpha"], tuple(cfg["photo_weights"]), tuple(cfg["smooth_weights"]), need, want_K, want_img, cfg["padding_mode"],
            None if masks is None else tuple((sig(a), sig(b)) for a, b in masks), cfg["no_photo"], cfg["no_smooth"], cfg["disparity"])
     plan = _PLAN_CACHE.get(key)
     if plan is None:
@@ -103,7 +103,8 @@ def _cached_plan(cfg, poses, K_ms, depth_pyr, tgt_pyr, src_pyr, need, want_K):
             _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
         plan = ops.FusedLossPlan(tgt_pyr, src_pyr, depth_pyr, poses, K_ms, cfg["alpha"], cfg["photo_weights"], cfg["smooth_weights"],
                                  want_grad=need, want_grad_K=want_K, padding_mode=cfg["padding_mode"], masks=masks,
-                                 no_photo=cfg["no_photo"], no_smooth=cfg["no_smooth"], disparity=cfg["disparity"], keep_inputs=False)
+                                 no_photo=cfg["no_photo"], no_smooth=cfg["no_smooth"], disparity=cfg["disparity"], keep_inputs=False,
+                                 want_image_grads=want_img)
         _PLAN_CACHE[key] = plan
     plan.rebind(tgt_pyr, src_pyr, depth_pyr, poses, K_ms, masks)
     return plan
@@ -122,15 +123,18 @@ class _FusedLoss(torch.autograd.Function):
         tgt_pyr, src_pyr = rest[ns:2 * ns], rest[2 * ns:3 * ns]
         need = any(ctx.needs_input_grad)
         want_K = ctx.needs_input_grad[2]
+        want_img = any(ctx.needs_input_grad[3 + ns:])          # images that require grad (never in the reference's trainer)
+        tgt_pyr, src_pyr = [t.detach() for t in tgt_pyr], [t.detach() for t in src_pyr]
         poses_c = poses.detach()
         if not poses_c.is_contiguous():
             poses_c = poses_c.contiguous()
-        plan = _cached_plan(cfg, poses_c, K_ms.detach(), depth_pyr, tgt_pyr, src_pyr, need, want_K)
+        plan = _cached_plan(cfg, poses_c, K_ms.detach(), depth_pyr, tgt_pyr, src_pyr, need, want_K, want_img)
         out, gposes, gK, gdepth = plan.fresh_outputs()
+        gimg = (plan.grad_tgt_img + plan.grad_src_img) if want_img else []
         plan.run()
         if need:
-            ctx.ns, ctx.has_K, ctx.unit = ns, gK is not None, bool(cfg["unit_upstream"])
-            ctx.save_for_backward(gposes, *([gK] if gK is not None else []), *gdepth)
+            ctx.ns, ctx.has_K, ctx.unit, ctx.has_img = ns, gK is not None, bool(cfg["unit_upstream"]), want_img
+            ctx.save_for_backward(gposes, *([gK] if gK is not None else []), *gdepth, *gimg)
         ctx.mark_non_differentiable(out)
         return out[0], out
 
@@ -140,11 +144,13 @@ class _FusedLoss(torch.autograd.Function):
         ns = ctx.ns
         gposes = saved[0]
         gK = saved[1] if ctx.has_K else None
-        gdepth = list(saved[1 + (1 if ctx.has_K else 0):])
+        o = 1 + (1 if ctx.has_K else 0)
+        gdepth = list(saved[o:o + ns])
+        gimg = list(saved[o + ns:]) if ctx.has_img else [None] * (2 * ns)
         if not ctx.unit:
             # one multi-tensor launch over tensors only this graph node refers to (in place: no copies)
-            torch._foreach_mul_(gdepth + [gposes] + ([gK] if gK is not None else []), g)
-        return (None, gposes if ctx.needs_input_grad[1] else None, gK, *gdepth, *([None] * (2 * ns)))
+            torch._foreach_mul_(gdepth + [gposes] + ([gK] if gK is not None else []) + (gimg if ctx.has_img else []), g)
+        return (None, gposes if ctx.needs_input_grad[1] else None, gK, *gdepth, *gimg)
 
 
 def geonet_loss(tgt_pyr: Sequence[torch.Tensor], src_pyr: Sequence[torch.Tensor], depth_pyr: Sequence[torch.Tensor],

@@ -75,7 +75,7 @@ class FusedLossPlan:
                  smooth_weights: Optional[Sequence[float]] = None, want_grad: bool = True, want_grad_K: bool = False,
                  padding_mode: str = "zeros", masks: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]] = None,
                  want_maps: bool = False, no_photo: bool = False, no_smooth: bool = False, disparity: bool = False,
-                 keep_inputs: bool = True):
+                 keep_inputs: bool = True, want_image_grads: bool = False):
         ns = len(tgt_pyr)
         _require_cuda(poses, K_ms, *tgt_pyr, *src_pyr, *depth_pyr)
         B, S = poses.shape[0], poses.shape[1]
@@ -84,6 +84,13 @@ class FusedLossPlan:
             raise ValueError("poses must be (B,S,6) and K_ms (B,scales,3,3)")
         self.B, self.S, self.ns, self.device = B, S, ns, dev
         self.want_grad, self.want_grad_K = want_grad, want_grad_K
+        self.want_image_grads = bool(want_image_grads)
+        if want_image_grads and not want_grad:
+            raise ValueError("want_image_grads needs want_grad")
+        # d loss_rigid_warp / d image (section 8(f3)): ACCUMULATED by the kernel (atomics), so they are zero-filled before every run
+        self.grad_tgt_img = [torch.zeros(t.shape, device=dev) for t in tgt_pyr] if want_image_grads else []
+        self.grad_src_img = [torch.zeros(t.shape, device=dev) for t in src_pyr] if want_image_grads else []
+        self._img_shapes = [(tuple(t.shape), tuple(u.shape)) for t, u in zip(tgt_pyr, src_pyr)]
         # per-scale intrinsics as contiguous (B,3,3) blocks (what the C call points at): one scale-major buffer
         self.K_buf = torch.empty(ns, B, 3, 3, device=dev)
         self.K = [self.K_buf[s] for s in range(ns)]
@@ -115,6 +122,8 @@ class FusedLossPlan:
                 mf, mb = masks[s]
                 _require_cuda(mf, mb)
                 sc["mask_fwd"], sc["mask_bwd"] = map_nhw(mf), map_nhw(mb)
+            if want_image_grads:
+                sc["grad_tgt_img"], sc["grad_src_img"] = img_nchw(self.grad_tgt_img[s]), img_nchw(self.grad_src_img[s])
             if want_maps:
                 m = {k: torch.empty(B * S, 3, h, w, device=dev) for k in ("warped_fwd", "warped_bwd", "err_fwd", "err_bwd")}
                 for k, v in m.items():
@@ -184,10 +193,21 @@ class FusedLossPlan:
         if self.want_grad_K:
             gK = torch.empty(self.B, self.ns, 3, 3, device=dev)
             a.grad_K = gK.data_ptr()
+        if self.want_image_grads:
+            self.grad_tgt_img = [torch.zeros(t, device=dev) for t, _ in self._img_shapes]
+            self.grad_src_img = [torch.zeros(u, device=dev) for _, u in self._img_shapes]
+            for s in range(self.ns):
+                a.scale[s].grad_tgt_img.ptr, a.scale[s].grad_src_img.ptr = self.grad_tgt_img[s].data_ptr(), self.grad_src_img[s].data_ptr()
+            self._fresh_img = True
         return loss_out, gposes, gK, gdepth
 
     def run(self) -> None:
         """Launch on the current stream (asynchronous)."""
+        if self.want_image_grads:
+            if getattr(self, "_fresh_img", False):
+                self._fresh_img = False                   # fresh_outputs() just handed out zero-filled buffers
+            else:
+                torch._foreach_zero_(self.grad_tgt_img + self.grad_src_img)
         rc = self._fn(self._ref, _stream())
         if rc:
             _abi.check(rc)

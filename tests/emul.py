@@ -33,7 +33,8 @@ def _map(a):   # numpy (n,h,w)
     return _abi.map_view(a.ctypes.data, [s // 4 for s in a.strides])
 
 
-def run_loss(inp, alpha=0.85, w_rigid=1.0, w_smooth=0.5, flags=1, padding=0, masks=None, want_maps=False, seg_rows=0, fine_rows=0, fine_permille=0):
+def run_loss(inp, alpha=0.85, w_rigid=1.0, w_smooth=0.5, flags=1, padding=0, masks=None, want_maps=False, seg_rows=0, fine_rows=0, fine_permille=0,
+             want_image_grads=False):
     """inp: snde_b200.synthetic.LossInputs (CPU torch). Returns dict like oracle.compose.geonet_loss."""
     from snde_b200 import _abi
     lib = C.CDLL(build())
@@ -65,6 +66,9 @@ def run_loss(inp, alpha=0.85, w_rigid=1.0, w_smooth=0.5, flags=1, padding=0, mas
             for key in ("warped_fwd", "warped_bwd", "err_fwd", "err_bwd"):
                 o[key] = np.full((B * S, 3, h, w), np.nan, np.float32)
                 sc[key] = _img(o[key])
+        if want_image_grads:
+            o["grad_tgt_img"] = np.zeros(tgt.shape, np.float32); o["grad_src_img"] = np.zeros(src.shape, np.float32)
+            sc["grad_tgt_img"], sc["grad_src_img"] = _img(o["grad_tgt_img"]), _img(o["grad_src_img"])
         keep += [tgt, src, depth, K]
         scales.append(sc); outs.append(o)
     loss_out = np.zeros(3 + 3 * ns, np.float32)
@@ -83,5 +87,8 @@ def run_loss(inp, alpha=0.85, w_rigid=1.0, w_smooth=0.5, flags=1, padding=0, mas
                grad_depth=[o["grad_depth"] for o in outs], grad_poses=gposes, grad_K_ms=gK)
     if want_maps:
         for key in ("warped_fwd", "warped_bwd", "err_fwd", "err_bwd"):
+            res[key] = [o[key] for o in outs]
+    if want_image_grads:
+        for key in ("grad_tgt_img", "grad_src_img"):
             res[key] = [o[key] for o in outs]
     return res

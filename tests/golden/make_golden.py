@@ -286,11 +286,34 @@ def train_step_kats(U, L):
     print("train_step_kats written: loss_total", out["loss_total"], "rigid", out["loss_rigid_warp"], "smooth", out["loss_disp_smooth"])
 
 
+def image_grad_kats(U, L):
+    """Round 2 (section 8(f3)): what the reference's autograd gives IMAGES that require grad -- d loss_rigid_warp / d tgt_pyr[s],
+    d src_pyr[s] through image_similarity (dense) and bilinear_sampler's index_select (scatter) -- on the small cases."""
+    from snde_b200.synthetic import make_inputs
+    out = {}
+    for name, gen in (("small_smooth", dict(B=2, S=2, H=32, W=64, num_scales=3, seed=1, smooth=True, motion="small")),
+                      ("small_s1_nyu", dict(B=1, S=1, H=30, W=44, num_scales=2, seed=3, smooth=True, motion="large", intrinsics="nyu"))):
+        inp = make_inputs(**gen)
+        for t in inp.tgt_pyr + inp.src_pyr:
+            t.requires_grad_(True)
+        lr, ls, _ = reference_loss_path(U, L, inp)
+        lr.backward()
+        out[f"{name}_loss_rigid_warp"] = np.float64(lr.item())
+        for s in range(inp.num_scales):
+            out[f"{name}_grad_tgt_{s}"] = inp.tgt_pyr[s].grad.numpy().copy()       # planar (B,3,h,w)
+            out[f"{name}_grad_src_{s}"] = inp.src_pyr[s].grad.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "image_grad_kats.npz"), **out)
+    print("image_grad_kats written:", len(out), "arrays")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     U, L = import_reference()
     if "--networks" in sys.argv:
         network_kats(U, L)
+        sys.exit(0)
+    if "--image-grads" in sys.argv:
+        image_grad_kats(U, L)
         sys.exit(0)
     if "--train-step" in sys.argv:
         train_step_kats(U, L)
@@ -298,6 +321,7 @@ if __name__ == "__main__":
     if "--round2" in sys.argv:          # only the fixtures added in round 2 (the round-1 files stay byte-identical)
         network_kats(U, L)
         train_step_kats(U, L)
+        image_grad_kats(U, L)
         glue_kats(U, L)
         full_size_cases(U, L)
         sys.exit(0)
@@ -313,3 +337,4 @@ if __name__ == "__main__":
     full_size_cases(U, L)
     network_kats(U, L)
     train_step_kats(U, L)
+    image_grad_kats(U, L)

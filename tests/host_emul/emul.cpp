@@ -39,11 +39,11 @@ void sync_on(SyncObj &s, int n) {
     while (s.gen == g) yield_to_scheduler();
 }
 
-template <bool GRAD, bool GRADK, bool EXTRA, bool FAST, bool DISP = false>
+template <bool GRAD, bool GRADK, bool EXTRA, bool FAST, bool DISP = false, bool GIMG = false>
 void run_role(int who) {
     HostPair &w = g_pair;
-    if (who < 32) geo_role<GRAD, GRADK, EXTRA, FAST, DISP>(*w.p, w.task, who, *w.sm, 1);
-    else ssim_role<GRAD, EXTRA, FAST, DISP>(*w.p, w.task, who, *w.sm, 1);
+    if (who < 32) geo_role<GRAD, GRADK, EXTRA, FAST, DISP, GIMG>(*w.p, w.task, who, *w.sm, 1);
+    else ssim_role<GRAD, EXTRA, FAST, DISP, GIMG>(*w.p, w.task, who, *w.sm, 1);
 }
 
 void fiber_main(int who) {
@@ -56,6 +56,8 @@ void fiber_main(int who) {
         case 4: run_role<true, false, false, true>(who); break;
         case 6: run_role<true, false, false, true, true>(who); break;
         case 7: run_role<true, true, true, true>(who); break;
+        case 8: run_role<true, true, true, true, false, true>(who); break;
+        case 9: run_role<true, true, true, false, false, true>(who); break;
         default: run_role<true, false, false, false>(who); break;
     }
     w.done[who] = true;
@@ -115,15 +117,17 @@ extern "C" __attribute__((visibility("default"))) int emul_loss_fwdbwd(const Snd
     build_prep_final(a, kp, fp);
     for (int i = 0; i < ns * N; ++i) loss_prep_thread(i, B, S, ns, a->poses, kp, (float *)(ws + lay.P), (float *)(ws + lay.Kinv));
     const bool grad = a->flags & SNDE_LOSS_GRAD, gradk = a->flags & SNDE_LOSS_GRAD_K;
-    bool extra = gradk || a->padding_mode != SNDE_PAD_ZEROS, fast = true;      // same variant selection as snde_loss_fwdbwd
+    bool extra = gradk || a->padding_mode != SNDE_PAD_ZEROS, fast = true, gimg = false;      // same variant selection as snde_loss_fwdbwd
     for (int s = 0; s < ns; ++s) {
         const SndeLossScale &in = a->scale[s];
         extra = extra || in.mask_fwd.ptr || in.mask_bwd.ptr || in.warped_fwd.ptr || in.warped_bwd.ptr || in.err_fwd.ptr || in.err_bwd.ptr;
+        gimg = gimg || in.grad_tgt_img.ptr || in.grad_src_img.ptr;
         fast = fast && d.sc[s].fast;
     }
+    if (gimg) extra = true;
     const bool disp = (a->flags & SNDE_LOSS_DISPARITY) != 0;
     if (disp && !(grad && fast && !extra)) extra = true;
-    const int variant = !grad ? (extra ? 0 : (fast ? 1 : 2)) : (extra ? (fast ? 7 : 3) : (disp ? 6 : (fast ? 4 : 5)));
+    const int variant = !grad ? (extra ? 0 : (fast ? 1 : 2)) : (gimg ? (fast ? 8 : 9) : (extra ? (fast ? 7 : 3) : (disp ? 6 : (fast ? 4 : 5))));
     PairSmem *sm = new PairSmem;
     for (int64_t t = 0; t < tasks; ++t) {
         memset(sm, 0xff, sizeof(PairSmem));    // NaN-fill: catches reads of unwritten shared memory

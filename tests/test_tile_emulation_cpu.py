@@ -229,3 +229,24 @@ def test_emulated_random_shapes(oracle32, seed):
         ok, rel, frac = close_except_flips(e["grad_depth"][s], o["grad_depth"][s], max_flip_frac=5e-3)
         assert ok, (s, rel, frac, (B, S, H, W, ns, seg))
     assert rel_l2(e["grad_poses"], o["grad_poses"]) < 2e-4
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_emulated_image_gradients_match_oracle(oracle32, name):
+    """section 8(f3): the strip program's optional image-gradient outputs (dense part formed by the SSIM warp, scatter part by
+    the geometry warp) against the oracle; the other outputs must not change when they are switched on"""
+    from oracle.compose import geonet_loss
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**CASES[name])
+    e = emul.run_loss(inp, flags=1, want_image_grads=True)
+    plain = emul.run_loss(inp, flags=1)
+    o = geonet_loss(oracle32, **oracle_inputs(inp), want_grad_images=True)
+    assert e["variant"] in (8, 9)
+    assert abs(e["loss_total"] - plain["loss_total"]) < 1e-7 * abs(plain["loss_total"])
+    for s in range(inp.num_scales):
+        assert np.array_equal(e["grad_depth"][s], plain["grad_depth"][s])
+        for key in ("grad_tgt_img", "grad_src_img"):
+            got = e[key][s].transpose(0, 2, 3, 1)
+            assert not np.isnan(got).any()
+            ok, rel, frac = close_except_flips(got, o[key][s], rtol=1e-4, max_flip_frac=2e-3)
+            assert ok, (key, s, rel, frac)
