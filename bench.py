@@ -22,6 +22,7 @@ Workloads (BASELINE.json configs):
   train_config2 / train_hires : the training step is the headline (metric train_samples_per_sec).  train_hires = config 4:
       376x1248, S=4, global batch 64 sharded over the N ranks (strong scaling).
   sweep5 : BASELINE config 5, the stand-alone inverse_warp + photometric_reconstruction_loss sweep through the public API.
+  nyu_dn : BASELINE config 3's depth <-> normal consistency term (section 8(f4)) at 480x640, B = 8.
 --impl reference times the reference's CPU path alone (rank 0 only).
 """
 import argparse
@@ -452,6 +453,65 @@ def train_leg(args, tcfg, D, dev, steps, warmup):
             "optimizer": "Adam lr 2e-4 (stepped every iteration)"}
 
 
+def dn_workload(args, D, dev, peak, peak_src):
+    """BASELINE config 3's own term: the depth <-> normal consistency loss (section 8(f4)) at 480x640, B = 8 per GPU, fwd + bwd
+    through the public autograd API on device-resident maps (4 rotating input sets), with the oracle timed beside it."""
+    import torch
+    from snde_b200.normal_depth import depth_normal_consistency_loss
+    B, h, w = 8, 480, 640
+    g = torch.Generator().manual_seed(5 + D.rank)
+    sets = []
+    for i in range(4):
+        depth = (torch.rand(B, h, w, generator=g) * 3 + 0.5).to(dev)
+        nrm = torch.randn(B, 3, h, w, generator=g)
+        nrm[:, 2] = nrm[:, 2].abs() + 2.0
+        sets.append((depth, (nrm / nrm.norm(dim=1, keepdim=True)).to(dev)))
+
+    def step(i):
+        d, n = sets[i % 4]
+        dd = d.detach().requires_grad_(True)
+        loss, _ = depth_normal_consistency_loss(dd, n)
+        loss.backward()
+        return loss
+    for i in range(max(3, args.warmup)):
+        step(i)
+    steps = min(args.steps, 200)
+    D.barrier(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        last = step(i)
+    e1.record()
+    D.barrier(dev)
+    ms = D.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    px = B * h * w
+    algo = 48 * px                    # fwd: depth 4 + normal 12 in, 8 out (backward scratch); bwd: normal 12 + scratch 8 in, gradient 4 out
+    if D.rank != 0:
+        return
+    line = {"metric": "depth_normal_consistency_pixel_fwd_bwd_per_sec", "value": D.world * px / (ms * 1e-3), "unit": "px/s", "n_gpus": D.world,
+            "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"nyu_dn: depth<->normal consistency loss (D2N + N2D over a 9x9 window, dilation 4) fwd+bwd, B={B} per GPU, {h}x{w}",
+                       "l2": "4 rotating input sets", "loss_check": float(last)},
+            "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": algo / (ms * 1e-3) / 1e9 / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": algo,
+                         "note": "81 taps x ~35 flops per pixel out of shared memory: compute/LDS-bound, not HBM-bound"},
+            "gpu_launches": 3 * steps}
+    if D.world == 1 and not args.no_cpu_baseline:
+        from oracle import normal_depth as ND
+        torch.set_num_threads(os.cpu_count() or 1)
+        dc, nc = sets[0][0][:2].cpu(), sets[0][1][:2].cpu()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            dd = dc.clone().requires_grad_(True)
+            ND.consistency_loss(dd, nc)[0].backward()
+            ts.append(time.perf_counter() - t0)
+        line["cpu_baseline"] = {"value": 2 * h * w / sorted(ts)[1], "unit": "px/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"B=2 of {B}, {h}x{w}, oracle/normal_depth.py (torch, F.unfold) fwd+bwd, median of 3"}
+    print(json.dumps(line))
+
+
 def sweep5(args, D, dev):
     """BASELINE config 5 through the north-star API: inverse_warp (one direction, warped image materialised) fwd+bwd and
     photometric_reconstruction_loss (both directions, fused, smoothness off) fwd+bwd; single scale, S = 1."""
@@ -509,7 +569,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS) + ["sweep5"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS) + ["sweep5", "nyu_dn"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the end-to-end leg (its keys are then null)")
@@ -535,6 +595,9 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
 
+    if args.workload == "nyu_dn":
+        dn_workload(args, D, dev, peak, peak_src)
+        return
     if args.workload == "sweep5":
         rows = sweep5(args, D, dev)
         if D.rank == 0:

@@ -215,6 +215,38 @@ SNDE_API int snde_frames_to_pyramid(int n, int H, int W, int num_scales, const u
 SNDE_API int snde_frames_to_pyramid_grouped(int n, int groups, int H, int W, int num_scales, const uint8_t *frames, int64_t sn,
                                             int64_t sc, int64_t sh, int64_t sw, float *const *levels, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Depth <-> normal consistency (BASELINE config 3).  The reference holds the inference-only GeoNet
+ * (Qi et al. 2018) refinement inside NNET.forward -- depth-to-normal, models/baseline.py:350-446, and normal-to-depth,
+ * :495-547, over a k x k window (k = 9) with dilation `rate` (4) -- with a scrambled patch extraction (F.unfold on NHWC
+ * tensors), a hard-coded batch of 4, no loss and no backward.  These entry points implement the INTENDED computation
+ * (spatial windows, zero padding) and define a consistency loss on it; parity is pinned by oracle/normal_depth.py.
+ *   grid     g_i = (xgrid[x_i], ygrid[y_i], 1)   (the reference: linspace(-0.6, 0.6, w), linspace(-0.4, 0.4, h), :308-317)
+ *   D2N      n'_i = normalize((det M > 1e-5 ? M : I)^-1 b),  M = sum_j P_j P_j^T, b = sum_j P_j over the window's j with
+ *            n_j . n_i > thresh,  P_j = d_j g_j
+ *   N2D      d'_i = clamp( sum_j [n_j.g_i > 1e-5] (n_j.g_j)/(n_j.g_i) d_j (n_j.n_i) / (sum_j [..] (n_j.n_i) + 1e-5), 0, clamp_max)
+ *   loss     w_depth * mean_i |d_i - d'_i| + w_normal * mean_i (1 - n_i . n'_i)
+ * snde_dn_consistency_fwd writes loss_out = {total, depth term, normal term} and, when given, n', d' and the per-pixel
+ * scratch `sq` (2 floats per pixel) that snde_dn_consistency_bwd needs; the backward writes d loss / d depth * (*gscale_dev)
+ * (through d_i and through the d_j inside d'_i; normals are data and n' is a constant: the normal term has no gradient).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct SndeDnArgs {
+    int32_t B, h, w;
+    int32_t k, rate;                    /* window: k x k taps (odd, <= 15), `rate` pixels apart (<= 16) */
+    float thresh, clamp_max;            /* reference: 0.95, 10.0 */
+    float w_depth, w_normal;
+    SndeMap depth;                      /* (B,h,w) linear depth */
+    SndeImage normal;                   /* (B,3,h,w) unit normals, n . ray > 0 */
+    const float *xgrid, *ygrid;         /* device arrays (w), (h) */
+    SndeImageOut normal_from_depth;     /* optional output (B,3,h,w) */
+    SndeMapOut depth_from_normal;       /* optional output (B,h,w) */
+    float *loss_out;                    /* device, 3 floats */
+    float *sq;                          /* optional device scratch, 2*B*h*w floats (required by the backward) */
+    double *sums;                       /* device scratch, 2 doubles (zeroed by the call) */
+} SndeDnArgs;
+SNDE_API int snde_dn_consistency_fwd(const SndeDnArgs *args, void *stream);
+SNDE_API int snde_dn_consistency_bwd(const SndeDnArgs *args, const float *gscale_dev, SndeMapOut grad_depth, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

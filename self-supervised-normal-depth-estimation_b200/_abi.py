@@ -55,6 +55,16 @@ class SndeLossArgs(C.Structure):
     ]
 
 
+class SndeDnArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("k", C.c_int32), ("rate", C.c_int32),
+        ("thresh", C.c_float), ("clamp_max", C.c_float), ("w_depth", C.c_float), ("w_normal", C.c_float),
+        ("depth", SndeMap), ("normal", SndeImage), ("xgrid", C.c_void_p), ("ygrid", C.c_void_p),
+        ("normal_from_depth", SndeImage), ("depth_from_normal", SndeMap),
+        ("loss_out", C.c_void_p), ("sq", C.c_void_p), ("sums", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/snde.h declares
 SIGNATURES = {
     "snde_version": (C.c_int, []),
@@ -86,6 +96,8 @@ SIGNATURES = {
     "snde_smooth_loss_bwd": (C.c_int, [C.c_int, C.c_int, C.c_int, SndeMap, SndeImage, C.c_void_p, SndeMap, C.c_void_p]),
     "snde_frames_to_pyramid": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                          C.POINTER(C.c_void_p), C.c_void_p]),
+    "snde_dn_consistency_fwd": (C.c_int, [C.POINTER(SndeDnArgs), C.c_void_p]),
+    "snde_dn_consistency_bwd": (C.c_int, [C.POINTER(SndeDnArgs), C.c_void_p, SndeMap, C.c_void_p]),
     "snde_frames_to_pyramid_grouped": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                                  C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
 }

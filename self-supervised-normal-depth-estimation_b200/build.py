@@ -19,7 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.environ.get("SNDE_LIB", os.path.join(HERE, "libsnde.so"))   # SNDE_LIB / SNDE_NVCC_DEFS: tuning experiments only
 # (source, fp-contraction flag): the fused kernel spells out its exact-order arithmetic, the reference-signature
 # kernels follow the reference op by op
-SOURCES = [("snde_fused.cu", "-fmad=true"), ("snde_ops.cu", "-fmad=false")]
+SOURCES = [("snde_fused.cu", "-fmad=true"), ("snde_ops.cu", "-fmad=false"), ("snde_dn.cu", "-fmad=true")]
 HEADERS = ["snde_math.cuh", "snde_strip.cuh", "snde_loss_setup.cuh"]
 
 
