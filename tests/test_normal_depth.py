@@ -82,10 +82,16 @@ def test_kernels_match_oracle(shape):
     assert abs(detail[1].item() - old.item()) < 1e-5 * abs(old.item())
     assert abs(detail[2].item() - oln.item()) < 1e-4 * abs(oln.item()) + 1e-7
     assert abs(loss.item() - ol.item()) < 1e-5 * abs(ol.item())
+    # a non-default window (k = 5, dilation 3) takes the generic kernel instance
+    n5, d5 = depth_normal_maps(d, n, k=5, rate=3)
+    assert rel_l2(d5.cpu().numpy(), ND.normal_to_depth(depth, normal, k=5, rate=3).numpy()) < 1e-5
+    assert (n5.cpu().double() - ND.depth_to_normal(depth.double(), normal.double(), k=5, rate=3)).norm(dim=1).max().item() < 5e-3
     g, og = dd.grad.cpu().numpy(), od_.grad.numpy()
-    flips = np.abs(g - og) > 1e-3 * np.abs(og).max()          # sign(d - d') flips where the two agree to the last bits
+    # sign(d_i - d'_i) flips where the two agree to the last bits; ONE such pixel moves the gradient of the k*k pixels whose
+    # window holds it, so up to three flipped signs are tolerated
+    flips = np.abs(g - og) > 1e-3 * np.abs(og).max()
     print(f"[dn grad {shape}] rel {rel_l2(g[~flips], og[~flips]):.2e}, flipped {flips.mean():.2e}")
-    assert rel_l2(g[~flips], og[~flips]) < 1e-4 and flips.mean() < 2e-3
+    assert rel_l2(g[~flips], og[~flips]) < 1e-4 and flips.sum() <= 3 * 81
 
 
 @pytest.mark.gpu
