@@ -567,6 +567,26 @@ def test_frames_to_pyramid_matches_reference_prep(shape):
         ops.frames_to_pyramid(frames[:, :, :H - 1], ns)          # H not a multiple of 2^(ns-1)
 
 
+def test_frames_to_pyramid_six_scales_and_grouped_sources():
+    """num_scales up to SNDE_MAX_SCALES = 6 (32x32 blocks); a (B,3S,H,W) source block in ONE launch lands source-major
+    (image g*B + b, models/baseline.py:772-775), identical to S separate calls on channel slices"""
+    from snde_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    frames = torch.randint(0, 256, (2, 3, 96, 160), generator=g, dtype=torch.uint8).to(DEV)
+    for a, b in zip(ops.frames_to_pyramid(frames, 6), _reference_prep(frames, 6)):
+        assert a.shape == b.shape and (a - b).abs().max().item() <= 2e-7
+    with pytest.raises(ValueError):
+        ops.frames_to_pyramid(frames, 7)
+    B, S, H, W, ns = 3, 4, 64, 96, 3
+    src = torch.randint(0, 256, (B, 3 * S, H, W), generator=g, dtype=torch.uint8).to(DEV)
+    grouped = ops.frames_to_pyramid(src, ns)
+    for s in range(ns):
+        assert grouped[s].shape == (S * B, 3, H >> s, W >> s)
+        for k in range(S):
+            single = ops.frames_to_pyramid(src[:, 3 * k:3 * (k + 1)], ns)
+            assert torch.equal(grouped[s][k * B:(k + 1) * B], single[s])
+
+
 def test_geonet_loss_from_frames_equals_reference_prep_then_loss():
     from snde_b200.loss_functions import geonet_loss, geonet_loss_from_frames
     from snde_b200.synthetic import make_inputs
