@@ -131,7 +131,8 @@ typedef struct SndeLossArgs {
 /* sizeof(SndeLossArgs) as compiled: lets an FFI binding verify its struct layout */
 SNDE_API size_t snde_sizeof_loss_args(void);
 SNDE_API size_t snde_loss_workspace_bytes(int B, int S, int num_scales);
-/* launches: 3 kernels (matrix prep + zeroing of the accumulators, persistent fused strip kernel over every scale/direction/strip, finalize) */
+/* launches: 3 kernels (matrix prep + zeroing of the accumulators, persistent fused strip kernel over every scale/direction/strip, finalize),
+ * chained by programmatic dependent launch: each waits for its predecessor on the stream with griddepcontrol.wait */
 SNDE_API int snde_loss_fwdbwd(const SndeLossArgs *args, void *stream);
 /* number of strip tasks (owner x 60-column strip x row segment) the fused kernel works through for these shapes on a
  * B200 (host only; used by tests/bench) */

@@ -62,12 +62,31 @@ extern "C" int snde_fill_grid_table(int n, float *out) {
 }
 
 
+// Programmatic dependent launch (sm_90+): the three kernels of a call are launched with the programmatic-stream-serialization
+// attribute, so the next one is scheduled while its predecessor drains and its launch latency disappears from the step; each
+// waits for the predecessor's memory with griddepcontrol.wait before touching anything the predecessor writes.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // (also zeroes the accumulators and the task counter of the call, [zero, zero + zero_words) in 16-byte words: one graph node
 // less than a separate memset)
 __global__ void __launch_bounds__(128) loss_prep_kernel(int B, int S, int ns, const float *__restrict__ poses, PrepParams kp,
                                                         float *__restrict__ P, float *__restrict__ Kinv, uint4 *__restrict__ zero,
                                                         int zero_words) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();                  // the strip kernel may be scheduled (it waits for this grid's memory itself)
+    pdl_wait();                               // whatever ran before on the stream may still be reading the workspace
     for (int j = i; j < zero_words; j += gridDim.x * blockDim.x) zero[j] = make_uint4(0u, 0u, 0u, 0u);
     loss_prep_thread(i, B, S, ns, poses, kp, P, Kinv);
 }
@@ -82,6 +101,7 @@ __global__ void __launch_bounds__(64) loss_final_kernel(int B, int S, int ns, in
     __shared__ double sv[64][6];
     __shared__ double sk[64][9];
     const int b = blockIdx.x, t = threadIdx.x;
+    pdl_wait();                               // the strip kernel's sums
     if (b == B) { if (t == 0) loss_final_scalars(ns, fp, loss, loss_out); return; }
     if (!(flags & FLAG_GRAD)) return;
     const bool wantK = (flags & FLAG_GRAD_K) != 0;
@@ -125,6 +145,8 @@ __global__ void __launch_bounds__(StripCfg::NT, SNDE_STRIP_CTAS_PER_SM) loss_str
     const int role = ((warp / StripCfg::PAIRS) + (int)blockIdx.x) & 1;      // 0 = geometry warp, 1 = SSIM warp
     PairSmem &sm = reinterpret_cast<PairSmem *>(smem_raw)[pair];
     const int bar = 1 + pair;                                               // barrier 0 is __syncthreads'
+    pdl_launch_dependents();                  // the finalize kernel may be scheduled as CTAs of this grid retire
+    pdl_wait();                               // the prep kernel's matrices, zeroed accumulators and task counter
     for (;;) {
         if (role == 0 && lane == 0) sm.task = atomicAdd(p.counter, 1);
         pair_barrier(lane, bar);
@@ -233,9 +255,9 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     PrepParams kp; FinalParams fp;
     build_prep_final(a, kp, fp);
     // [gP, end) is a whole number of 16-byte words (every offset of the layout is rounded up to 16)
-    loss_prep_kernel<<<(ns * N + 127) / 128, 128, 0, st>>>(B, S, ns, a->poses, kp, (float *)(ws + lay.P), (float *)(ws + lay.Kinv),
-                                                       (uint4 *)(ws + lay.gP), (int)((lay.end - lay.gP) / 16));
-    SNDE_CHECK_LAUNCH();
+    if (snde_cuda_failed(launch_pdl(loss_prep_kernel, dim3((ns * N + 127) / 128), dim3(128), 0, st, B, S, ns, a->poses, kp, (float *)(ws + lay.P),
+                                    (float *)(ws + lay.Kinv), (uint4 *)(ws + lay.gP), (int)((lay.end - lay.gP) / 16)), "prep launch", __LINE__))
+        return SNDE_ERR_CUDA;
     const size_t smem = sizeof(PairSmem) * StripCfg::PAIRS;
     const bool grad = a->flags & SNDE_LOSS_GRAD, gradk = a->flags & SNDE_LOSS_GRAD_K;
     // opt in to > 48 KB dynamic shared memory once per kernel variant and device (not a stream operation; kept out of
@@ -250,7 +272,7 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
             if (snde_cuda_failed(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "shared-memory opt-in", __LINE__)) return SNDE_ERR_CUDA;
             g_attr_done[variant][devi].store(true, std::memory_order_release);
         }
-        kern<<<(unsigned)ctas, StripCfg::NT, smem, st>>>(d);
+        if (snde_cuda_failed(launch_pdl(kern, dim3((unsigned)ctas), dim3(StripCfg::NT), smem, st, d), "strip launch", __LINE__)) return SNDE_ERR_CUDA;
         return SNDE_OK;
     };
     // EXTRA variants honour masks / warped+error outputs / border padding / intrinsics gradients; FAST ones need planar,
@@ -276,10 +298,10 @@ extern "C" int snde_loss_fwdbwd(const SndeLossArgs *a, void *stream_) {
     else rc = fast ? launch(loss_strip_kernel<true, false, false, true>, 4) : launch(loss_strip_kernel<true, false, false, false>, 5);
     if (rc) return rc;
     SNDE_CHECK_LAUNCH();
-    loss_final_kernel<<<B + 1, 64, 0, st>>>(B, S, ns, a->flags, a->poses, fp, (const double *)(ws + lay.gP),
-                                                           (const double *)(ws + lay.gKinv), (const double *)(ws + lay.loss),
-                                                           a->loss_out, a->grad_poses, a->grad_K);
-    SNDE_CHECK_LAUNCH();
+    if (snde_cuda_failed(launch_pdl(loss_final_kernel, dim3(B + 1), dim3(64), 0, st, B, S, ns, (int)a->flags, a->poses, fp, (const double *)(ws + lay.gP),
+                                    (const double *)(ws + lay.gKinv), (const double *)(ws + lay.loss), a->loss_out, a->grad_poses, a->grad_K),
+                         "finalize launch", __LINE__))
+        return SNDE_ERR_CUDA;
     return SNDE_OK;
 }
 
