@@ -98,14 +98,16 @@ struct DevScale {
 
 // one block of the task table: `count` tasks starting at number `begin`; owners first_owner.. of class cls (0 = F, 1 = R)
 // at `scale`, cut into tiles_y segments of seg_h rows
-struct DevEntry { int begin, count, scale, cls, first_owner, seg_h, tiles_y, pad_; };
+// (y_base: first row of the block's segments; a scale whose height is not a multiple of seg_h gets a second block for the
+//  short last segment, so that the table can be ordered by task cost)
+struct DevEntry { int begin, count, scale, cls, first_owner, seg_h, tiles_y, y_base; };
 
 struct DevLoss {
     int B, S, num_scales, flags, padding, num_entries;
     float alpha, oma;
     int total_tasks, pad_;
     int *counter;                    // workspace: next task to hand out (zeroed per call)
-    DevEntry entry[4 * SNDE_MAX_SCALES];
+    DevEntry entry[8 * SNDE_MAX_SCALES];
     DevScale sc[SNDE_MAX_SCALES];
 };
 
@@ -366,7 +368,7 @@ SNDE_STRIP_FN void decode_task(const DevLoss &p, int task, int lane, StripTask &
     const int tt = local - mo * per_owner;
     const int sy = tt / sc.tiles_x, sx = tt - sy * sc.tiles_x;
     T.h = sc.h; T.w = sc.w;
-    T.y0 = sy * ent.seg_h; T.y1 = T.y0 + ent.seg_h < sc.h ? T.y0 + ent.seg_h : sc.h;
+    T.y0 = ent.y_base + sy * ent.seg_h; T.y1 = T.y0 + ent.seg_h < sc.h ? T.y0 + ent.seg_h : sc.h;
     T.ix0 = sx * C::TW - 2 + 2 * lane;
     T.clsF = ent.cls == 0;
     T.b = T.clsF ? T.m : (T.m % p.B);                // batch element (selects K)
