@@ -69,25 +69,31 @@ __global__ void __launch_bounds__(SPLIT_WARPS * 32, SPLIT_MIN_CTAS) ssim_channel
 #pragma unroll
     for (int q = 0; q < 2; ++q) ngSm[q] = colB[q] ? 0.5f * p.alpha * sc.gphoto : 0.f;
 
-    auto load_row = [&](int iy, F2 &xr, F2 &yr) {
+    // rows go global -> shared by cp.async (zero-filled outside the image), three rows ahead, into a ring of 8 rows per warp:
+    // no register ever holds a value that has not arrived.  (Versions 1-3 of this experiment loaded into registers: the select
+    // behind the load, then the register rotation, then ptxas' own copy of the loaded pair each waited for the load -- 50-60 % of
+    // all stall samples on one instruction, 149-178 us.)
+    __shared__ F2 ring_all[SPLIT_WARPS][8][2][32];
+    F2 (*ring)[2][32] = ring_all[threadIdx.x >> 5];
+    auto prefetch = [&](int iy) {
         const bool take = in0 && iy >= 0 && iy < h;
         const int off = take ? iy * w + ix0 : 0;
-        const F2 a = ldg2(xbase + off), b = ldg2(ybase + off);
-        xr = take ? a : F2{0.f, 0.f};
-        yr = take ? b : F2{0.f, 0.f};
+        row_copy_async<8>(&ring[iy & 7][0][lane], xbase + off, take);
+        row_copy_async<8>(&ring[iy & 7][1][lane], ybase + off, take);
+        row_copy_commit();
     };
 
     HS s1, s2; CS c1, c2;
     hs_zero(s1); hs_zero(s2); cs_zero(c1); cs_zero(c2);
     float err_acc = 0.f;
-    F2 x1 = F2{0.f, 0.f}, yy1 = x1, x2 = x1, yy2 = x1;            // rows t-1, t-2
-    F2 xa, ya, xb, yb;                                            // rows t, t+1 (in flight)
-    load_row(t_begin, xa, ya);
-    load_row(t_begin + 1, xb, yb);
+    prefetch(t_begin - 2); prefetch(t_begin - 1);                 // (rows t-1, t-2 of the first steps: zero rows or the rows above the segment)
+    prefetch(t_begin); prefetch(t_begin + 1); prefetch(t_begin + 2);
     for (int t = t_begin; t <= t_end; ++t) {
-        const F2 xr = xa, yr = ya;
-        xa = xb; ya = yb;
-        load_row(t + 2, xb, yb);
+        row_copy_wait<2>();
+        const F2 xr = ring[t & 7][0][lane], yr = ring[t & 7][1][lane];
+        const F2 x1 = ring[(t - 1) & 7][0][lane], yy1 = ring[(t - 1) & 7][1][lane];
+        const F2 x2 = ring[(t - 2) & 7][0][lane], yy2 = ring[(t - 2) & 7][1][lane];
+        prefetch(t + 3);
         const int rb = t - 1, rc = t - 2;
         const bool doB = t >= y0, doC = t >= y0 + 2;
         const bool rowB = doB && rb >= 0 && rb < h;
@@ -139,8 +145,8 @@ __global__ void __launch_bounds__(SPLIT_WARPS * 32, SPLIT_MIN_CTAS) ssim_channel
         }
         cs_add(c2, Hc, c1);
         c2 = Hc;
-        x2 = x1; yy2 = yy1; x1 = xr; yy1 = yr;
     }
+    row_copy_wait<0>();
     {
         float v[1] = {err_acc};
         warp_sum<1>(who, v);
