@@ -13,6 +13,16 @@ CASES = {
     "config1_smooth": dict(B=4, S=2, H=128, W=416, num_scales=4, seed=0, smooth=True, motion="small"),
 }
 SMALL = ["small_smooth", "small_noise_large_motion", "small_s1_nyu"]
+
+# extreme shapes: the smallest image smooth_loss is defined on, widths below one pixel pair per lane, the most sources the
+# library takes (SNDE_MAX_SOURCES), a width one pixel past two strips, a height a few rows past a 64-row segment
+EDGE = [dict(B=1, S=1, H=2, W=2, num_scales=1, seed=1, smooth=True, motion="small"),
+        dict(B=1, S=1, H=2, W=3, num_scales=1, seed=2, smooth=True, motion="small"),
+        dict(B=2, S=1, H=3, W=5, num_scales=1, seed=3, smooth=True, motion="small"),
+        dict(B=1, S=2, H=4, W=4, num_scales=2, seed=4, smooth=True, motion="small"),
+        dict(B=1, S=8, H=16, W=24, num_scales=2, seed=5, smooth=True, motion="small"),
+        dict(B=1, S=1, H=8, W=122, num_scales=1, seed=6, smooth=True, motion="small"),
+        dict(B=1, S=1, H=70, W=61, num_scales=1, seed=7, smooth=True, motion="small")]
 # round 2: the BASELINE shapes at their full bench sizes, run through the reference itself (scalars, pose gradients, checksums)
 FULL = {
     "config2_smooth": dict(B=32, S=2, H=128, W=416, num_scales=4, seed=12, smooth=True, motion="small"),

@@ -67,6 +67,9 @@ def test_argument_validation_without_launch(abi):
     args.B, args.S, args.num_scales = 1, 1, 7
     assert lib.snde_loss_fwdbwd(C.byref(args), None) == -2          # too many scales
     args.num_scales = 1
+    args.S = 9
+    assert lib.snde_loss_fwdbwd(C.byref(args), None) in (-2, -4)    # more than SNDE_MAX_SOURCES views (or the workspace check first)
+    args.S = 1
     assert lib.snde_loss_fwdbwd(C.byref(args), None) == -4          # workspace missing
     ws = np.zeros(4096, np.float64)
     args.workspace = (ws.ctypes.data + 15) & ~15; args.workspace_bytes = 16

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from cases import CASES, FULL, SMALL, check_depth_grads, close_except_flips, load_golden, oracle_inputs, pose_grad_tolerance, rel_l2
+from cases import CASES, EDGE, FULL, SMALL, check_depth_grads, close_except_flips, load_golden, oracle_inputs, pose_grad_tolerance, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -657,6 +657,30 @@ def test_odd_sizes_and_unaligned_views_on_hardware(oracle32, oracle64):
         assert abs(plan.loss_out[0].item() - o["loss_total"]) < 1e-5 * abs(o["loss_total"])
         check_depth_grads([t.cpu().numpy() for t in plan.grad_depth], o["grad_depth"], o64["grad_depth"], tag="odd sizes")
         assert rel_l2(plan.grad_poses.cpu().numpy(), o["grad_poses"]) < 1e-4
+
+
+@pytest.mark.parametrize("case", EDGE, ids=lambda c: f"B{c['B']}S{c['S']}_{c['H']}x{c['W']}x{c['num_scales']}")
+def test_extreme_shapes_on_hardware(oracle32, case):
+    """the shapes of cases.EDGE (2x2 images, 8 sources, one column past two strips, ...) on the GPU against the oracle; too many
+    sources and a one-row image are refused with the documented codes"""
+    from oracle.compose import geonet_loss
+    from snde_b200 import ops
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**case)
+    d = inp.to(DEV)
+    o = geonet_loss(oracle32, **oracle_inputs(inp))
+    for want_K in (False, True):
+        plan = ops.FusedLossPlan(d.tgt_pyr, d.src_pyr, d.depth_pyr, d.poses, d.K_ms, want_grad=True, want_grad_K=want_K)
+        plan.run()
+        torch.cuda.synchronize()
+        assert abs(plan.loss_out[0].item() - o["loss_total"]) < 1e-5 * abs(o["loss_total"])
+        for s in range(inp.num_scales):
+            g = plan.grad_depth[s].cpu().numpy()
+            assert not np.isnan(g).any()
+            assert rel_l2(g, o["grad_depth"][s]) < 1e-4
+        assert rel_l2(plan.grad_poses.cpu().numpy(), o["grad_poses"]) < 1e-4
+        if want_K:
+            assert rel_l2(plan.grad_K.cpu().numpy(), o["grad_K_ms"]) < 1e-4
 
 
 @pytest.mark.parametrize("seed", range(6))

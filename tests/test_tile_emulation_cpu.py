@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import emul
-from cases import CASES, SMALL, close_except_flips, load_golden, oracle_inputs, rel_l2
+from cases import CASES, EDGE, SMALL, close_except_flips, load_golden, oracle_inputs, rel_l2
 
 
 def _nhwc(a):
@@ -250,3 +250,21 @@ def test_emulated_image_gradients_match_oracle(oracle32, name):
             assert not np.isnan(got).any()
             ok, rel, frac = close_except_flips(got, o[key][s], rtol=1e-4, max_flip_frac=2e-3)
             assert ok, (key, s, rel, frac)
+
+
+@pytest.mark.parametrize("case", EDGE, ids=lambda c: f"B{c['B']}S{c['S']}_{c['H']}x{c['W']}x{c['num_scales']}")
+def test_emulated_extreme_shapes_match_oracle(oracle32, case):
+    """2x2 images, odd widths below one strip, 8 sources, one column past two strips, a few rows past a segment"""
+    from oracle.compose import geonet_loss
+    from snde_b200.synthetic import make_inputs
+    inp = make_inputs(**case)
+    o = geonet_loss(oracle32, **oracle_inputs(inp))
+    for flags in (1, 3):
+        e = emul.run_loss(inp, flags=flags)
+        assert abs(e["loss_total"] - o["loss_total"]) < 1e-6 * abs(o["loss_total"])
+        for s in range(inp.num_scales):
+            assert not np.isnan(e["grad_depth"][s]).any()
+            assert rel_l2(e["grad_depth"][s], o["grad_depth"][s]) < 1e-4
+        assert rel_l2(e["grad_poses"], o["grad_poses"]) < 1e-4
+        if flags & 2:
+            assert rel_l2(e["grad_K_ms"], o["grad_K_ms"]) < 1e-4
