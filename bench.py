@@ -673,6 +673,8 @@ def main():
             "gpu_launches": 3 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": prof.get("dram_bytes_per_launch"), "issue_frac": issue_frac,
+                         "l1_data_pipe_frac": (prof["l1_data_pipe_wavefronts_per_launch"] / (sms * clk_mhz * 1e6 * ms_per_step * 1e-3)
+                                               if prof.get("l1_data_pipe_wavefronts_per_launch") else None),
                          "issue_note": "issue_frac = warp-instructions of one strip-kernel launch (ncu, profiles/) / (SMs x 4 schedulers x SM clock x step time): "
                                        "the share of all issue slots the kernel fills; the kernel is bound there and by dependent-issue latency, not by HBM",
                          "peak_source": peak_src, "algorithmic_bytes_per_step": algo_bytes, "traffic_source": prof.get("source"),
