@@ -59,6 +59,27 @@
 #ifndef SNDE_SSIM_STRAIGHT
 #define SNDE_SSIM_STRAIGHT 1
 #endif
+// 1: the lean instances (zero padding, no optional outputs) blend the four taps as two nested linear interpolations, which
+// yields the warped value and both tap derivatives from the same differences (27 packed operations per row instead of 46);
+// an invalid pixel is switched off by one 0/1 factor on the warped value and by a validity bit on the way back (the bit
+// travels in a per-lane shift register: row t-3's bits are 4 pushes old when the row is taken back through the projection)
+#ifndef SNDE_LERP_BLEND
+#define SNDE_LERP_BLEND 1
+#endif
+// 1: the lean instances add the L1 part of the error sum when a row arrives (phase H) instead of one row later (phase B
+// re-read x and y of row t-1 for nothing else: 6 shared-memory loads per row less), and form the three backward
+// coefficients from one shared factor ngS * rB (12 packed operations instead of 16)
+#ifndef SNDE_SSIM_LEAN
+#define SNDE_SSIM_LEAN 1
+#endif
+// 1: the SSIM warp's row step runs phase-major over the three colour channels (see the row step)
+#ifndef SNDE_SSIM_PHASED
+#define SNDE_SSIM_PHASED 1
+#endif
+// 1: the geometry warp runs the smoothness term on every pass (masked to zero after the first) instead of branching around it
+#ifndef SNDE_SMOOTH_ALWAYS
+#define SNDE_SMOOTH_ALWAYS 0
+#endif
 
 namespace snde {
 
@@ -319,6 +340,16 @@ SNDE_STRIP_FN F2 ldcg2(const float *p) { return F2{p[0], p[1]}; }
 #define SNDE_PIN_F32(x) ((void)0)
 #endif
 
+// g * sign(d) (0 for d == 0) without a branch: the sign bit of d is xor-ed into g
+SNDE_STRIP_FN float times_sign(float g, float d) {
+#if defined(__CUDA_ARCH__)
+    const float s = __int_as_float(__float_as_int(g) ^ (__float_as_int(d) & (int)0x80000000u));
+    return d != 0.f ? s : 0.f;
+#else
+    return d > 0.f ? g : (d < 0.f ? -g : 0.f);
+#endif
+}
+
 // horizontal 3-sums of one row for the lane's two columns (left column = left neighbour + (a + b), right column =
 // (a + b) + right neighbour: the association the golden-vector tolerances were measured with)
 // (xx + yy is carried as ONE sum q: SSIM and its backward use the two second moments only through their sum)
@@ -461,8 +492,10 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
     float alpha = p.alpha, oma = p.oma, g1 = p.oma * sc.gphoto;
     SNDE_PIN_F32(alpha); SNDE_PIN_F32(oma); SNDE_PIN_F32(g1);
     float ngSm[2];            // -dL/dS = 0.5*alpha*gphoto where the column takes part in phase B, else 0
+    constexpr bool LEAN = SNDE_SSIM_LEAN && !EXTRA;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) ngSm[q] = T.colB[q] ? -(-0.5f * p.alpha * sc.gphoto) : 0.f;
+    for (int q = 0; q < 2; ++q) ngSm[q] = T.colB[q] ? -(-0.5f * p.alpha * sc.gphoto) * (LEAN ? 2.f : 1.f) : 0.f;      // (LEAN carries 2 ngS)
+    float alI[2] = {alpha * T.mI[0], alpha * T.mI[1]}, omI[2] = {oma * T.mI[0], oma * T.mI[1]};      // LEAN: the inner-column gate folded in
     const int y0 = T.y0, y1 = T.y1, h = T.h;
     for (int k = 0; k < T.n_pass; ++k) {
         const long long n = T.clsF ? (long long)k * p.B + T.b : T.m;      // index into the N-sized tensors
@@ -496,7 +529,7 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
         if (disp_in) { rows.disparity_to_depth(sm, T, lane, T.t_begin); rows.disparity_to_depth(sm, T, lane, T.t_begin + 1); }
         pair_barrier(who, bar);
 
-        for (int t = T.t_begin; t <= T.t_end + 1; ++t) {
+        auto row_step = [&](const int t) {
             pair_barrier(who, bar);              // row t of the warped image is in shared memory
             if (t <= T.t_end && T.do_photo) {
             const int rb = t - 1, rc = t - 2;
@@ -511,25 +544,38 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                     if (GRAD && doC && T.colI[q]) gl[q] = g1 * ldg(mask_base + rc * mask_sh + (T.ix0 + q) * mask_sw);
                 }
             }
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
+            // The row step as four phases per colour channel.  Warp shuffles keep their program order, so the ORDER OF THE PHASES
+            // IN THE SOURCE decides what can overlap: channel-major (phases A..C2 of channel 0, then channel 1, ...) runs the
+            // three channels strictly one after the other; phase-major (SNDE_SSIM_PHASED: phase A of all channels, then B of
+            // all, ...) lets the loads, shuffles and reciprocals of the three channels overlap, at the price of holding the
+            // three channels' intermediate rows at once.
+            F2 xr3[3], yr3[3]; HS H3[3]; CS co3[3]; P2 cod3[3]; CS Hc3[3]; P2 Hd3[3]; F2 po3[3];
+            auto phase_load = [&](const int ch) { xr3[ch] = sm.X[t & 7][ch][lane]; yr3[ch] = sm.Y[t & 3][ch][lane]; };
+            auto phase_a = [&](const int ch) {
                 // ---------------- horizontal sums of row t ----------------
-                const F2 xr = sm.X[t & 7][ch][lane], yr = sm.Y[t & 3][ch][lane];
-                HS H;
+                const F2 xr = xr3[ch], yr = yr3[ch];
                 {
                     const float to_right[2] = {xr.y, yr.y}, to_left[2] = {xr.x, yr.x};
                     float from_left[2], from_right[2];
                     neighbor_exchange<2>(who, to_right, to_left, from_left, from_right);
-                    hsum_row(xr, yr, from_left[0], from_right[0], from_left[1], from_right[1], H);
+                    hsum_row(xr, yr, from_left[0], from_right[0], from_left[1], from_right[1], H3[ch]);
                 }
+                if (LEAN && t >= y0 && t < y1) {      // L1 part of the error of row t (an inner row)
+                    err_acc = fmaf(fabsf(xr.x - yr.x), omI[0], err_acc);
+                    err_acc = fmaf(fabsf(xr.y - yr.y), omI[1], err_acc);
+                }
+            };
+            auto phase_b = [&](const int ch) {
                 // ---------------- phase B (row t-1) ----------------
                 // (SNDE_SSIM_STRAIGHT: a row that is not a phase-B row runs the same arithmetic on finite sums and contributes
                 // exact zeros (ngq = 0) and nothing to the error sum)
+                const HS H = H3[ch];
                 CS co; cs_zero(co);
                 P2 cod = p2s(0.f);
                 if (SNDE_SSIM_STRAIGHT || rowB) {
                     HS tot; hs_add(s1[ch], H, tot);
-                    const F2 xc = sm.X[rb & 7][ch][lane], yc = sm.Y[rb & 3][ch][lane];
+                    F2 xc = F2{0.f, 0.f}, yc = F2{0.f, 0.f};
+                    if (!LEAN) { xc = sm.X[rb & 7][ch][lane]; yc = sm.Y[rb & 3][ch][lane]; }
                     SsimP ss; ssim_sums_p(tot.x, tot.y, tot.q, tot.xy, ss);
                     const P2 v = p2fma(p2s(-0.5f), ss.S, p2s(0.5f));
                     const float vq[2] = {p2lo(v), p2hi(v)};
@@ -538,69 +584,109 @@ SNDE_STRIP_FN void ssim_role(const DevLoss &p, int task, int who, PairSmem &sm, 
                     float ngq[2];
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
+                        if (LEAN) {
+                            if (rowB && row_inner) err_acc = fmaf(vcq[q], alI[q], err_acc);        // the SSIM part; the L1 part was added at phase H
+                            ngq[q] = (rowB & (vq[q] == vcq[q])) ? ngSm[q] : 0.f;
+                            continue;
+                        }
                         const float err = fmaf(alpha, vcq[q], oma * fabsf(dq[q]));
                         if (rowB && row_inner) {
                             err_acc = fmaf(EXTRA ? err * mk[q] : err, T.mI[q], err_acc);
                             if (EXTRA && eout_base && T.colI[q]) eout_base[ch * eout_sc + rb * eout_sh + (T.ix0 + q) * eout_sw] = err;
                         }
-                        ngq[q] = (rowB && vq[q] == vcq[q]) ? (EXTRA ? ngSm[q] * mk[q] : ngSm[q]) : 0.f;       // the clamp passes gradient inside [0,1] only
+                        ngq[q] = (rowB & (vq[q] == vcq[q])) ? (EXTRA ? ngSm[q] * mk[q] : ngSm[q]) : 0.f;      // the clamp passes gradient inside [0,1] only
                     }
-                    if (GRAD) ssim_sums_bwd_p(ss, tot.x, tot.y, p2(ngq[0], ngq[1]), co.a, co.b, co.c);
+                    if (GRAD && LEAN) ssim_sums_bwd_lean_p(ss, tot.x, tot.y, p2(ngq[0], ngq[1]), co.a, co.b, co.c);
+                    else if (GRAD) ssim_sums_bwd_p(ss, tot.x, tot.y, p2(ngq[0], ngq[1]), co.a, co.b, co.c);
                     if (GRAD && GIMG) cod = ssim_sums_bwd_x_p(ss, tot.x, tot.y, p2(ngq[0], ngq[1]));
                 }
                 hs_add(s2[ch], H, s1[ch]);        // s1 <- H(t-1) + H(t)
                 s2[ch] = H;
-                if (GRAD) {
-                    // ---------------- horizontal sums of the coefficient row t-1 ----------------
-                    CS Hc;
-                    {
-                        const float al = p2lo(co.a), ah = p2hi(co.a), bl = p2lo(co.b), bh = p2hi(co.b), cl = p2lo(co.c), chh = p2hi(co.c);
-                        const float to_right[3] = {ah, bh, chh}, to_left[3] = {al, bl, cl};
-                        float from_left[3], from_right[3];
-                        neighbor_exchange<3>(who, to_right, to_left, from_left, from_right);
-                        const float ta = al + ah, tb = bl + bh, tc = cl + chh;
-                        Hc.a = p2add(p2(from_left[0], from_right[0]), p2s(ta));
-                        Hc.b = p2add(p2(from_left[1], from_right[1]), p2s(tb));
-                        Hc.c = p2add(p2(from_left[2], from_right[2]), p2s(tc));
+                co3[ch] = co; cod3[ch] = cod;
+            };
+            auto phase_c1 = [&](const int ch) {
+                // ---------------- horizontal sums of the coefficient row t-1 ----------------
+                const CS co = co3[ch];
+                CS Hc;
+                {
+                    const float al = p2lo(co.a), ah = p2hi(co.a), bl = p2lo(co.b), bh = p2hi(co.b), cl = p2lo(co.c), chh = p2hi(co.c);
+                    const float to_right[3] = {ah, bh, chh}, to_left[3] = {al, bl, cl};
+                    float from_left[3], from_right[3];
+                    neighbor_exchange<3>(who, to_right, to_left, from_left, from_right);
+                    const float ta = al + ah, tb = bl + bh, tc = cl + chh;
+                    Hc.a = p2add(p2(from_left[0], from_right[0]), p2s(ta));
+                    Hc.b = p2add(p2(from_left[1], from_right[1]), p2s(tb));
+                    Hc.c = p2add(p2(from_left[2], from_right[2]), p2s(tc));
+                }
+                P2 Hd = p2s(0.f);
+                if (GIMG) {
+                    const float dl = p2lo(cod3[ch]), dh = p2hi(cod3[ch]);
+                    const float to_right[1] = {dh}, to_left[1] = {dl};
+                    float from_left[1], from_right[1];
+                    neighbor_exchange<1>(who, to_right, to_left, from_left, from_right);
+                    Hd = p2add(p2(from_left[0], from_right[0]), p2s(dl + dh));
+                }
+                Hc3[ch] = Hc; Hd3[ch] = Hd;
+            };
+            auto phase_c2 = [&](const int ch) {
+                // ---------------- phase C (row t-2): dL/d(warped) ----------------
+                // (computed every step, stored when the row exists: see phase B)
+                const CS Hc = Hc3[ch]; const P2 Hd = Hd3[ch];
+                if (SNDE_SSIM_STRAIGHT || doC) {
+                    CS bs; cs_add(c1[ch], Hc, bs);
+                    const F2 xf = sm.X[rc & 7][ch][lane], yf = sm.Y[rc & 3][ch][lane];
+                    const P2 xv = p2f(xf), yv = p2f(yf);
+                    const float d0 = xf.x - yf.x, d1 = xf.y - yf.y;
+                    const float l0 = times_sign(gl[0], d0), l1 = times_sign(gl[1], d1);      // g * sign(x - y), as two selects (no branch)
+                    const P2 po = p2sub(p2fma(p2add(yv, yv), bs.b, p2fma(xv, bs.c, bs.a)), p2(l0, l1));
+                    // (phase-major: stored after the last channel's loads -- a shared-memory store in between would pin the order
+                    // of the next channel's loads behind this channel's whole dependency chain)
+                    if (SNDE_SSIM_PHASED) po3[ch] = f2p(po);
+                    else if (doC) sm.PO[rc & 1][ch][lane] = f2p(po);
+                    if (GIMG && gown_base && doC) {
+                        // d loss / dx(p) = box(c_sx) + 2 x box(c_sxx) + y box(c_sxy) + (1 - alpha) g sign(x - y)
+                        const F2 pox = f2p(p2add(p2fma(p2add(xv, xv), bs.b, p2fma(yv, bs.c, p2add(xa1[ch].d, Hd))), p2(l0, l1)));
+                        float *dst = gown_base + (ch * gown_sc + rc * gown_sh + T.ix0 * gown_sw);
+                        if (T.colI[0]) atomic_add_float(dst, pox.x);
+                        if (T.colI[1]) atomic_add_float(dst + gown_sw, pox.y);
                     }
-                    P2 Hd = p2s(0.f);
-                    if (GIMG) {
-                        const float dl = p2lo(cod), dh = p2hi(cod);
-                        const float to_right[1] = {dh}, to_left[1] = {dl};
-                        float from_left[1], from_right[1];
-                        neighbor_exchange<1>(who, to_right, to_left, from_left, from_right);
-                        Hd = p2add(p2(from_left[0], from_right[0]), p2s(dl + dh));
-                    }
-                    // ---------------- phase C (row t-2): dL/d(warped) ----------------
-                    // (computed every step, stored when the row exists: see phase B)
-                    if (SNDE_SSIM_STRAIGHT || doC) {
-                        CS bs; cs_add(c1[ch], Hc, bs);
-                        const F2 xf = sm.X[rc & 7][ch][lane], yf = sm.Y[rc & 3][ch][lane];
-                        const P2 xv = p2f(xf), yv = p2f(yf);
-                        const float d0 = xf.x - yf.x, d1 = xf.y - yf.y;
-                        const float l0 = d0 > 0.f ? gl[0] : (d0 < 0.f ? -gl[0] : 0.f), l1 = d1 > 0.f ? gl[1] : (d1 < 0.f ? -gl[1] : 0.f);
-                        const P2 po = p2sub(p2fma(p2add(yv, yv), bs.b, p2fma(xv, bs.c, bs.a)), p2(l0, l1));
-                        if (doC) sm.PO[rc & 1][ch][lane] = f2p(po);
-                        if (GIMG && gown_base && doC) {
-                            // d loss / dx(p) = box(c_sx) + 2 x box(c_sxx) + y box(c_sxy) + (1 - alpha) g sign(x - y)
-                            const F2 pox = f2p(p2add(p2fma(p2add(xv, xv), bs.b, p2fma(yv, bs.c, p2add(xa1[ch].d, Hd))), p2(l0, l1)));
-                            float *dst = gown_base + (ch * gown_sc + rc * gown_sh + T.ix0 * gown_sw);
-                            if (T.colI[0]) atomic_add_float(dst, pox.x);
-                            if (T.colI[1]) atomic_add_float(dst + gown_sw, pox.y);
-                        }
-                    }
-                    cs_add(c2[ch], Hc, c1[ch]);   // c1 <- Hc(t-2) + Hc(t-1)
-                    c2[ch] = Hc;
-                    if (GIMG) { xa1[ch].d = p2add(xa2[ch].d, Hd); xa2[ch].d = Hd; }
+                }
+                cs_add(c2[ch], Hc, c1[ch]);   // c1 <- Hc(t-2) + Hc(t-1)
+                c2[ch] = Hc;
+                if (GIMG) { xa1[ch].d = p2add(xa2[ch].d, Hd); xa2[ch].d = Hd; }
+            };
+#if SNDE_SSIM_PHASED
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) phase_load(ch);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) phase_a(ch);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) phase_b(ch);
+            if (GRAD) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) phase_c1(ch);
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) phase_c2(ch);
+                if ((SNDE_SSIM_STRAIGHT || doC) && doC) {
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) sm.PO[rc & 1][ch][lane] = po3[ch];
                 }
             }
+#else
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                phase_load(ch); phase_a(ch); phase_b(ch);
+                if (GRAD) { phase_c1(ch); phase_c2(ch); }
+            }
+#endif
             }
             // ---- owner row t+3 starts its way into the ring (its slot held row t-5); row t+2 must have landed before the
             //      next barrier publishes it ----
             rows.prefetch_row(sm, T, lane, t + 3);
             row_copy_wait<1>();
             if (disp_in) rows.disparity_to_depth(sm, T, lane, t + 2);
-        }
+        };
+        for (int t = T.t_begin; t <= T.t_end + 1; ++t) row_step(t);
         row_copy_wait<0>();
         pair_barrier(who, bar);                  // the geometry warp is through with the ring: the next pass / task may refill it
         // ---- publish this pass: error sum of pair n ----
@@ -635,6 +721,7 @@ struct GeoLane {
     // accumulators
     float dP[12], dK[9], sx_acc, sy_acc;
     F2 sy_prev;               // signed smoothness weights of the vertical pairs starting one row above
+    unsigned vbits;           // SNDE_LERP_BLEND: validity of the lane's two pixels, two bits per issued row, newest lowest
 
     SNDE_STRIP_FN GeoLane(const DevLoss &p_, const DevScale &sc_, PairSmem &sm_, const StripTask &T_, int lane_)
         : p(p_), sc(sc_), sm(sm_), T(T_), lane(lane_) {}
@@ -644,7 +731,7 @@ struct GeoLane {
     // The two pixels run as packed fp32 pairs (lane-wise the scalar chain of reproject_fast / make_taps_valid).
     // wts = {wx0, wx1, wy0, wy1}, each the pair over the two pixels (all zero for a pixel that samples nothing); border
     // mode also needs the derivative gates, kept in dgate = {dx, dy}.
-    SNDE_STRIP_FN void a_issue(float yt, const F2 d, P2 (&wts)[4], P2 (&dgate)[2], float (&taps)[24], bool row_ok = true) const {
+    SNDE_STRIP_FN void a_issue(float yt, const F2 d, P2 (&wts)[4], P2 (&dgate)[2], float (&taps)[24], bool row_ok = true) {
         // (lanes whose columns lie outside the image go through the same motions with zero weights on pixel 0)
         const float *ob = oth_base;
         SNDE_PIN_PTR(ob);
@@ -687,9 +774,16 @@ struct GeoLane {
                 gq[q][0] = gq[q][1] = 1.f;
             }
         }
+        if (SNDE_LERP_BLEND && !EXTRA) {
+            // wts = {wx1, wy1, valid as 0/1}: the fractional parts as they are, validity as one factor
+            wts[0] = p2(wq[0][1], wq[1][1]); wts[1] = p2(wq[0][3], wq[1][3]);
+            wts[2] = p2(valid[0] ? 1.f : 0.f, valid[1] ? 1.f : 0.f);
+            vbits = (vbits >> 2) | (valid[0] ? 0x100u : 0u) | (valid[1] ? 0x200u : 0u);       // four pushes later the row's bits are bits 0, 1
+        } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) wts[i] = p2(valid[0] ? wq[0][i] : 0.f, valid[1] ? wq[1][i] : 0.f);
-        dgate[0] = p2(gq[0][0], gq[1][0]); dgate[1] = p2(gq[0][1], gq[1][1]);
+            for (int i = 0; i < 4; ++i) wts[i] = p2(valid[0] ? wq[0][i] : 0.f, valid[1] ? wq[1][i] : 0.f);
+            dgate[0] = p2(gq[0][0], gq[1][0]); dgate[1] = p2(gq[0][1], gq[1][1]);
+        }
         // Branch-free per pixel: an invalid pixel samples address 0 of the image with four zero weights.  The two tap rows
         // are walked channel by channel as pinned pointers (one 64-bit add per row and channel).
 #pragma unroll
@@ -720,6 +814,25 @@ struct GeoLane {
     // ---- phase A, second half (one step later): blend the gathered taps -> warped row (+ tap derivatives) ----
     SNDE_STRIP_FN void a_finish(int iy, const P2 (&wts)[4], const P2 (&dgate)[2], const float (&taps)[24], bool want_g,
                                 F2 (&y)[3], F2 (&g)[6]) const {
+        if (SNDE_LERP_BLEND && !EXTRA) {
+            // top = i00 + wx1 (i10 - i00), bot = i01 + wx1 (i11 - i01): the two rows interpolated along x; their difference is
+            // d/dy, the warped value is top + wy1 (bot - top), d/dx is the x differences interpolated along y.  The same
+            // numbers as the four-weight form up to rounding (wx0 + wx1 = wy0 + wy1 = 1 exactly for an in-image sample).
+            const P2 wx1 = wts[0], wy1 = wts[1], vm = wts[2];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const P2 i00 = p2(taps[4 * ch + 0], taps[12 + 4 * ch + 0]), i01 = p2(taps[4 * ch + 1], taps[12 + 4 * ch + 1]);
+                const P2 i10 = p2(taps[4 * ch + 2], taps[12 + 4 * ch + 2]), i11 = p2(taps[4 * ch + 3], taps[12 + 4 * ch + 3]);
+                const P2 a = p2sub(i10, i00), b = p2sub(i11, i01);
+                const P2 top = p2fma(wx1, a, i00), bot = p2fma(wx1, b, i01);
+                const P2 gy = p2sub(bot, top);
+                y[ch] = f2p(p2mul(p2fma(wy1, gy, top), vm));
+                // (formed on every row -- gy is needed for the value anyway -- and stored by the caller on inner rows only)
+                if (GRAD) { g[2 * ch] = f2p(p2fma(wy1, p2sub(b, a), a)); g[2 * ch + 1] = f2p(gy); }
+                else g[2 * ch] = g[2 * ch + 1] = F2{0.f, 0.f};
+            }
+            return;
+        }
         const P2 wx0 = wts[0], wx1 = wts[1], wy0 = wts[2], wy1 = wts[3];
         const P2 w00 = p2mul(wx0, wy0), w01 = p2mul(wx0, wy1), w10 = p2mul(wx1, wy0), w11 = p2mul(wx1, wy1);
 #pragma unroll
@@ -762,7 +875,9 @@ struct GeoLane {
         F2 gd_old = F2{0.f, 0.f};
         if (FAST && GRAD && k > 0 && to_disp && doG && T.colI[0]) gd_old = ldcg2(gd_base + (r * gd_sh + ix0));
         const bool g_on = GRAD && T.do_photo && doG;                          // (uniform over the warp)
-        const bool on[2] = {g_on && T.colI[0], g_on && (FAST ? T.colI[0] : T.colI[1])};
+        // (SNDE_LERP_BLEND: the tap derivatives of an invalid pixel are not zero by themselves; its validity bit switches it off)
+        const bool lerp = SNDE_LERP_BLEND && !EXTRA;
+        const bool on[2] = {g_on && T.colI[0] && (!lerp || (vbits & 1u)), g_on && (FAST ? T.colI[0] : T.colI[1]) && (!lerp || (vbits & 2u))};
         if (GRAD && (SNDE_GEO_STRAIGHT || on[0] || on[1])) {
             // both pixels as packed pairs (lane-wise reproject_nodiv / reproject_bwd_fast); a FAST lane holds two inner
             // pixels or none, a generic one may hold a single inner pixel.  SNDE_GEO_STRAIGHT: no branch around this -- an
@@ -839,9 +954,11 @@ struct GeoLane {
         // formed: they are the "pair above" of the first inner row.
         // Straight-line like the back-projection above: the loads and the arithmetic run on every row, a row that does
         // not exist (outside the image / before the segment) contributes selected zeros.
-        if (SMOOTH && smooth_now) {
+        if (SMOOTH && (SNDE_SMOOTH_ALWAYS || smooth_now)) {
             const int h = T.h;
-            const bool r_in = r >= y0 - 1 && r >= 0 && r < h, below = r_in && r + 1 < h;
+            // (SNDE_SMOOTH_ALWAYS: no branch around the term -- on the later passes over an owner it runs with every pair switched
+            // off, so that it shares a basic block, and the scheduler's attention, with the back-projection above)
+            const bool r_in = (!SNDE_SMOOTH_ALWAYS || smooth_now) && r >= y0 - 1 && r >= 0 && r < h, below = r_in && r + 1 < h;
             F2 xa[3], xb[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) { xa[ch] = sm.X[r & 7][ch][lane]; xb[ch] = sm.X[(r + 1) & 7][ch][lane]; }
@@ -947,7 +1064,7 @@ SNDE_STRIP_FN void geo_role(const DevLoss &p, int task, int who, PairSmem &sm, i
     const long long depth_n = clsF ? m : (long long)B + m;
     L.gd_base = GRAD ? sc.gdepth.p + depth_n * sc.gdepth.sn : nullptr; L.gd_sh = sc.gdepth.sh; L.gd_sw = sc.gdepth.sw;
     SNDE_PIN_PTR(L.gd_base);
-    L.sx_acc = 0.f; L.sy_acc = 0.f;
+    L.sx_acc = 0.f; L.sy_acc = 0.f; L.vbits = 0u;
 #pragma unroll
     for (int i = 0; i < 9; ++i) L.dK[i] = 0.f;
     const float *Kinv = sc.Kinv + 9 * b;

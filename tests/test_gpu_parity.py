@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from cases import CASES, EDGE, FULL, SMALL, check_depth_grads, close_except_flips, load_golden, oracle_inputs, pose_grad_tolerance, rel_l2
+from cases import CASES, EDGE, FULL, SMALL, check_depth_grads, close_except_flips, load_golden, oracle_inputs, pose_grad_tolerance, rel_l2, same_up_to_rounding
 
 pytestmark = pytest.mark.gpu
 
@@ -386,13 +386,14 @@ def _fused_lean(inp):
 
 @pytest.mark.parametrize("name", SMALL + ["config1_smooth"])
 def test_lean_instance_equals_general_instance(name):
-    """the two template instances share every arithmetic statement: identical depth gradients, same sums"""
+    """the lean and the general template instance: the same numbers up to fp32 rounding (the lean ones blend the taps as nested
+    linear interpolations, cases.LEAN_VS_GENERAL_TOL), same sums"""
     from snde_b200.synthetic import make_inputs
     inp = make_inputs(**CASES[name])
     a, b = _fused_lean(inp), _fused(inp)
     assert abs(a["loss_total"] - b["loss_total"]) < 1e-6 * abs(b["loss_total"])
     for s in range(inp.num_scales):
-        assert np.array_equal(a["grad_depth"][s], b["grad_depth"][s])
+        assert same_up_to_rounding(a["grad_depth"][s], b["grad_depth"][s])
     assert rel_l2(a["grad_poses"], b["grad_poses"]) < 1e-5
 
 
