@@ -131,7 +131,7 @@ def test_fused_autograd_matches_plan_and_scales_with_upstream():
     from snde_b200.loss_functions import geonet_loss
     from snde_b200.synthetic import make_inputs
     inp = make_inputs(**CASES["small_smooth"])
-    ref = _fused(inp)
+    ref = _fused_lean(inp)                  # the instance the autograd op runs (gradients to depth and poses only)
     d = inp.to(DEV)
     depth = [t.clone().requires_grad_(True) for t in d.depth_pyr]
     poses = d.poses.clone().requires_grad_(True)
@@ -380,7 +380,7 @@ def _fused_lean(inp):
     plan.run()
     torch.cuda.synchronize()
     lo = plan.loss_out.cpu().numpy()
-    return dict(loss_total=float(lo[0]), fwd_mean=lo[3::3], bwd_mean=lo[4::3], smooth=lo[5::3],
+    return dict(loss_total=float(lo[0]), loss_rigid_warp=float(lo[1]), fwd_mean=lo[3::3], bwd_mean=lo[4::3], smooth=lo[5::3],
                 grad_depth=[g.cpu().numpy() for g in plan.grad_depth], grad_poses=plan.grad_poses.cpu().numpy())
 
 
