@@ -676,7 +676,7 @@ def main():
                          "l1_data_pipe_frac": (prof["l1_data_pipe_wavefronts_per_launch"] / (sms * clk_mhz * 1e6 * ms_per_step * 1e-3)
                                                if prof.get("l1_data_pipe_wavefronts_per_launch") else None),
                          "issue_note": "issue_frac = warp-instructions of one strip-kernel launch (ncu, profiles/) / (SMs x 4 schedulers x SM clock x step time): "
-                                       "the share of all issue slots the kernel fills; the kernel is bound there and by dependent-issue latency, not by HBM",
+                                       "the share of all issue slots the kernel fills; l1_data_pipe_frac = L1 data-pipe wavefronts (tap gathers, shared memory, shuffles; same capture) per SM and clock -- ncu rates that pipe 70 % busy at config 2 and 84-86 % (90-92 % on the busiest SM) at the nyu / hires shapes: the kernel is bound by the L1 data pipe and instruction issue, not by HBM",
                          "peak_source": peak_src, "algorithmic_bytes_per_step": algo_bytes, "traffic_source": prof.get("source"),
                          "note": "duration = whole step (prep + strip kernel + finalize); the strip kernel is 98% of it "
                                  "(profiles/). Bytes per SURVEY 8(d): 60 B/warped px + 36 B/smooth px, as for separate fwd and bwd "
